@@ -1,0 +1,513 @@
+// build.cpp — Octree::Create on the GPU: batched greedy with exact replay.
+//
+// Reference (Source/HP/Octree.cpp): Create :312-352 → CreateRoot :792-801 → UniformlyRefine :112-191 →
+// RunBuildThreadPool :194-309 (scheduler) + TickBuildThread :558-659 (worker: EstimateHImprovement :804-826,
+// EstimatePImprovement :829-856, h/p decision :598-601) → ReallocCoeffs :474-555 → PerformContinuityPostProcess :1717-1762.
+//
+// The reference pops the max-error leaf, evaluates its refinement job (8 child fits + 1 p-fit) on a CPU thread, applies
+// the better of the two and pushes the results back. A job's result is a pure function of (cell, degree, F), so here:
+//   round r:  every leaf that has no cached job result is evaluated in ONE batch of fit kernels (fit_kernels.cuh);
+//             only {raw error, c0} per fit come back to the host (16 B), coefficients stay in a device pool;
+//   replay:   the host runs the reference's sequential scheduler on its priority queue (std::priority_queue with the
+//             reference's predicate, so ties pop in the same order) using the cached results, with the reference's
+//             totalCoeffError arithmetic, until it terminates or the top of the queue has no cached result → next round.
+// This yields exactly the strict-greedy tree (the deterministic schedule the CPU checker defines: window 1, termination
+// checked after every applied job; nearness weight from the exact cell mean). Work computed for leaves
+// that are never popped before termination is speculative waste, bounded by the number of final leaves.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <queue>
+#include <vector>
+#include "octree.h"
+#include "comm.h"
+
+namespace hpsdf
+{
+    namespace
+    {
+        struct Job
+        {
+            bool     coarse = false, doH = false, doP = false;
+            uint32_t hSlot[8] = { 0 }, pSlot = 0;
+            double   hErr[8] = { 0 }, pErr = 0.0, hImp = 0.0, pImp = 0.0;
+        };
+
+        // Octree.h:95-102: max-heap on the error only
+        struct QueuePredicate
+        {
+            bool operator()(const std::pair<uint64_t, double>& a, const std::pair<uint64_t, double>& b) const { return a.second < b.second; }
+        };
+
+        // Exact-mean limit of CalculatePolyWeighting / CalculateExpWeighting (Octree.cpp:1209-1247): the mean of the
+        // approximant over its cell is coeffs[0] * NL[0][depth]^3 (orthonormal basis) instead of 100 std::rand() samples.
+        double nearnessWeight(const hpsdf_config& cfg, double c0, uint32_t depth)
+        {
+            if (cfg.nearness_type == HPSDF_NEARNESS_NONE) return 1.0;
+            const double nl = tables().nl[0][depth];
+            double m = c0 * (nl * nl * nl);
+            m = std::fabs(m);
+            const double d = std::sqrt(3.0);
+            if (cfg.nearness_type == HPSDF_NEARNESS_POLYNOMIAL)
+            {
+                const double k = std::pow(1.0 - m / d, cfg.nearness_strength);
+                return std::min<double>(1.0, std::max<double>(k, 0.0));
+            }
+            return std::exp(-1.0 * cfg.nearness_strength * m / d);
+        }
+
+        template <typename T>
+        struct PinnedBuf
+        {
+            T* p = nullptr; size_t cap = 0;
+            cudaError_t reserve(size_t n)
+            {
+                if (n <= cap) return cudaSuccess;
+                if (p) cudaFreeHost(p);
+                cap = std::max(n, cap * 2);
+                return cudaMallocHost((void**)&p, cap * sizeof(T));
+            }
+            ~PinnedBuf() { if (p) cudaFreeHost(p); }
+        };
+
+        template <typename T>
+        struct DeviceBuf
+        {
+            T* p = nullptr; size_t cap = 0;
+            cudaError_t reserve(size_t n, cudaStream_t s = nullptr, size_t keep = 0)
+            {
+                if (n <= cap) return cudaSuccess;
+                const size_t newCap = std::max(n, cap * 2);
+                T* q = nullptr;
+                cudaError_t e = cudaMalloc((void**)&q, newCap * sizeof(T));
+                if (e != cudaSuccess) return e;
+                if (p && keep) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s); if (e == cudaSuccess) e = cudaStreamSynchronize(s); }
+                if (p) cudaFree(p);
+                p = q; cap = newCap;
+                return e;
+            }
+            ~DeviceBuf() { if (p) cudaFree(p); }
+        };
+
+        class Builder
+        {
+        public:
+            Builder(hpsdf_octree& t, const hpsdf_build_opts& o, const SdfProgramDev& prog)
+                : t_(t), o_(o), prog_(prog), nodes_(t.nodes), cfg_(t.cfg) {}
+
+            hpsdf_status run();
+
+        private:
+            hpsdf_octree&            t_;
+            const hpsdf_build_opts&  o_;
+            const SdfProgramDev&     prog_;
+            std::vector<HostNode>&   nodes_;
+            const hpsdf_config&      cfg_;
+            cudaStream_t             stream_ = nullptr;
+            bool                     ownStream_ = false;
+            cudaEvent_t              ev0_ = nullptr, ev1_ = nullptr;
+
+            std::priority_queue<std::pair<uint64_t, double>, std::vector<std::pair<uint64_t, double>>, QueuePredicate> queue_;
+            std::vector<int32_t>     jobOf_;        // per node: index into jobs_, -1 = no cached result
+            std::vector<double>      errOf_;        // per node: its current (weighted) error
+            std::vector<Job>         jobs_;
+            std::vector<uint64_t>    pending_;      // leaves created / changed by the last replay
+
+            DeviceBuf<double>        pool_;  size_t poolUsed_ = 0;
+            DeviceBuf<FitTask>       dTasks_;
+            DeviceBuf<FitRecord>     dRecs_;
+            PinnedBuf<FitTask>       hTasks_;
+            PinnedBuf<FitRecord>     hRecs_;
+
+            double      total_ = 0.0;               // totalCoeffError, reference bookkeeping (Octree.cpp:212, 257, 272, 276)
+            long double exactSum_ = 0.0L;
+            long        unfitted_ = 0;
+            int         rank_ = 0, world_ = 1;
+            hpsdf_decision_log_entry lastApplied_{};      // last job applied before the termination cut
+            double      lastTotal_ = 0.0, totalBeforeLast_ = 0.0;
+
+            void         subdivide(uint64_t idx);
+            void         refineUniform(uint64_t idx, uint32_t depth);
+            hpsdf_status evaluateRound();
+            bool         replay();                  // true = terminated
+            hpsdf_status pack();
+            double       checkValue() const
+            {
+                return o_.total_mode == HPSDF_TOTAL_EXACT_SUM
+                     ? (unfitted_ > 0 ? std::numeric_limits<double>::infinity() : (double)exactSum_) : total_;
+            }
+        };
+
+        // Subdivide (Octree.cpp:1115-1128)
+        void Builder::subdivide(uint64_t idx)
+        {
+            nodes_[idx].child = nodes_.size();
+            for (uint32_t i = 0; i < 8; ++i)
+            {
+                HostNode c;
+                cornerAabb(nodes_[idx], i, c.mn, c.mx);
+                c.depth = (uint8_t)(nodes_[idx].depth + 1);
+                nodes_.push_back(c);
+            }
+        }
+
+        // UniformlyRefine (Octree.cpp:112-191): pre-order DFS, Subdivide on first visit, children 0..7; the 16^3 cells at
+        // depth 4 get degree 0 and enter the queue with err = 100 in visiting order.
+        void Builder::refineUniform(uint64_t idx, uint32_t depth)
+        {
+            if (depth < (uint32_t)kCoarseDepth)
+            {
+                subdivide(idx);
+                const uint64_t c = nodes_[idx].child;
+                for (uint32_t i = 0; i < 8; ++i) refineUniform(c + i, depth + 1);
+            }
+            else
+            {
+                nodes_[idx].degree = 0;
+                queue_.push({ idx, kInitialErr });
+                pending_.push_back(idx);
+            }
+        }
+
+        // One batch: the refinement jobs of every pending leaf.
+        hpsdf_status Builder::evaluateRound()
+        {
+            // ---- 1. jobs and fit tasks, grouped by fit degree ------------------------------------------------------
+            struct Proto { uint64_t node; uint8_t child; bool isP; };     // child 0..7 for h-fits
+            std::vector<Proto> byDegree[kMaxDegree + 1];
+            const size_t firstJob = jobs_.size();
+            jobOf_.resize(nodes_.size(), -1);
+            errOf_.resize(nodes_.size(), 0.0);
+            for (uint64_t idx : pending_)
+            {
+                const HostNode& n = nodes_[idx];
+                Job j;
+                j.coarse = std::abs(errOf_[idx] - kInitialErr) < std::numeric_limits<double>::epsilon() && n.degree == 0;   // Octree.cpp:806, 831
+                if (j.coarse) { j.doP = true; byDegree[kCoarseDegree].push_back({ idx, 0, true }); }
+                else
+                {
+                    j.doH = n.depth < o_.max_depth;             // child fits at depth > TREE_MAX_DEPTH are never used (Octree.cpp:600-601)
+                    j.doP = n.degree < o_.max_degree;           // nor is the p-fit of a max-degree node
+                    if (j.doH) for (uint8_t c = 0; c < 8; ++c) byDegree[n.degree].push_back({ idx, c, false });
+                    if (j.doP) byDegree[n.degree + 1].push_back({ idx, 0, true });
+                }
+                jobOf_[idx] = (int32_t)jobs_.size();
+                jobs_.push_back(j);
+            }
+            pending_.clear();
+
+            size_t nTasks = 0, poolNeed = poolUsed_;
+            for (int d = 1; d <= kMaxDegree; ++d) { nTasks += byDegree[d].size(); poolNeed += byDegree[d].size() * (size_t)coeffCount(d); }
+            if (nTasks == 0) return HPSDF_OK;
+            if (poolNeed >= 0xFFFFFFF0ull) { setLastError("coefficient pool exceeds 2^32 doubles"); return HPSDF_ERR_OOM; }
+            HPSDF_CUDA(pool_.reserve(poolNeed + 1024, stream_, poolUsed_));
+            HPSDF_CUDA(dTasks_.reserve(nTasks));
+            HPSDF_CUDA(dRecs_.reserve(nTasks));
+            HPSDF_CUDA(hTasks_.reserve(nTasks));
+            HPSDF_CUDA(hRecs_.reserve(nTasks));
+
+            // Tasks in degree order; task index == record index; slots allocated in task order (contiguous per degree,
+            // so a rank's shard of a degree group is one contiguous pool range).
+            size_t ti = 0;
+            size_t groupBegin[kMaxDegree + 2] = { 0 };
+            size_t groupPool[kMaxDegree + 2] = { 0 };
+            double roundFlops = 0.0; uint64_t roundEvals = 0;
+            for (int d = 1; d <= kMaxDegree; ++d)
+            {
+                groupBegin[d] = ti; groupPool[d] = poolUsed_;
+                for (const Proto& p : byDegree[d])
+                {
+                    const HostNode& n = nodes_[p.node];
+                    Job& j = jobs_[jobOf_[p.node]];
+                    FitTask& t = hTasks_.p[ti];
+                    float mn[3], mx[3];
+                    uint8_t depth = n.depth;
+                    if (p.isP) { memcpy(mn, n.mn, 12); memcpy(mx, n.mx, 12); }
+                    else { cornerAabb(n, p.child, mn, mx); depth = (uint8_t)(n.depth + 1); }
+                    t.cx = (mn[0] + mx[0]) / 2.0f; t.cy = (mn[1] + mx[1]) / 2.0f; t.cz = (mn[2] + mx[2]) / 2.0f;   // AlignedBox::center() in f32
+                    t.half = (mx[0] - mn[0]) * 0.5f;
+                    t.out = (uint32_t)poolUsed_;
+                    t.depth = depth; t.degree = (uint8_t)d; t.pad = 0;
+                    t.rec = (uint32_t)ti;
+                    if (p.isP && !j.coarse) { t.src = n.slot; t.degreeIn = n.degree; }
+                    else { t.src = kNoSrc; t.degreeIn = 0; }
+                    if (p.isP) j.pSlot = t.out; else j.hSlot[p.child] = t.out;
+                    poolUsed_ += (size_t)coeffCount(d);
+                    ++ti;
+                }
+            }
+            groupBegin[kMaxDegree + 1] = ti;
+
+            // ---- 2. upload, launch one kernel per degree present (this rank's shard), gather across ranks ----------
+            HPSDF_CUDA(cudaMemcpyAsync(dTasks_.p, hTasks_.p, nTasks * sizeof(FitTask), cudaMemcpyHostToDevice, stream_));
+            HPSDF_CUDA(cudaEventRecord(ev0_, stream_));
+            for (int d = 1; d <= kMaxDegree; ++d)
+            {
+                const size_t n = byDegree[d].size();
+                if (!n) continue;
+                size_t b = 0, e = n;
+                if (world_ > 1) hpsdf_shard_range(n, rank_, world_, &b, &e);
+                if (e > b)
+                {
+                    HPSDF_CUDA(launchFitKernel(d, dTasks_.p + groupBegin[d] + b, (int)(e - b), pool_.p, dRecs_.p, prog_, t_.map, t_.ctx->fitTab, stream_));
+                    t_.stats.kernel_launches++;
+                }
+                t_.stats.fits_evaluated += n;
+                roundFlops += (double)n * fitFlops(d);
+                roundEvals += (uint64_t)n * fitRule(d) * fitRule(d) * fitRule(d);
+            }
+            HPSDF_CUDA(cudaEventRecord(ev1_, stream_));
+            if (world_ > 1)
+            {
+                // every rank receives every other rank's shard: coefficients and records (replicated pool, identical replay)
+                std::vector<CommSegment> segs;
+                for (int d = 1; d <= kMaxDegree; ++d)
+                {
+                    const size_t n = byDegree[d].size();
+                    if (!n) continue;
+                    for (int r = 0; r < world_; ++r)
+                    {
+                        size_t b, e;
+                        hpsdf_shard_range(n, r, world_, &b, &e);
+                        if (e <= b) continue;
+                        segs.push_back({ pool_.p + groupPool[d] + b * (size_t)coeffCount(d), (e - b) * (size_t)coeffCount(d), r });
+                        segs.push_back({ (double*)(dRecs_.p + groupBegin[d] + b), (e - b) * 2, r });
+                    }
+                }
+                hpsdf_status cs = commBroadcastSegments(o_.comm, segs, stream_);
+                if (cs != HPSDF_OK) return cs;
+            }
+            HPSDF_CUDA(cudaMemcpyAsync(hRecs_.p, dRecs_.p, nTasks * sizeof(FitRecord), cudaMemcpyDeviceToHost, stream_));
+            HPSDF_CUDA(cudaStreamSynchronize(stream_));
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, ev0_, ev1_);
+            t_.stats.fit_kernel_ms += ms;
+            t_.stats.algorithmic_flops += roundFlops;
+            t_.stats.sdf_evals += roundEvals;
+            t_.stats.rounds++;
+            t_.stats.jobs_evaluated += jobs_.size() - firstJob;
+
+            // ---- 3. errors, improvements (host, same expressions and libm as the CPU checker) ------------------------
+            // walk the tasks again in the same order to attach records to jobs
+            ti = 0;
+            for (int d = 1; d <= kMaxDegree; ++d)
+                for (const Proto& p : byDegree[d])
+                {
+                    const HostNode& n = nodes_[p.node];
+                    Job& j = jobs_[jobOf_[p.node]];
+                    const FitRecord& r = hRecs_.p[ti++];
+                    if (p.isP) j.pErr = r.rawErr * nearnessWeight(cfg_, r.c0, n.depth);
+                    else       j.hErr[p.child] = r.rawErr * nearnessWeight(cfg_, r.c0, n.depth + 1u);
+                }
+            for (size_t k = firstJob; k < jobs_.size(); ++k)
+            {
+                Job& j = jobs_[k];
+                if (j.coarse) { j.hImp = 0.0; j.pImp = j.pErr; }                                         // Octree.cpp:806-810, 836-843
+            }
+            return HPSDF_OK;
+        }
+
+        // The reference's scheduler loop (Octree.cpp:213-302) in strict-greedy form, driven by cached job results.
+        bool Builder::replay()
+        {
+            const double thr = cfg_.target_error_threshold;
+            for (;;)
+            {
+                if (checkValue() < thr || queue_.empty()) return true;                                   // Octree.cpp:216
+                const std::pair<uint64_t, double> top = queue_.top();                                    // Octree.cpp:231
+                const uint64_t idx = top.first;
+                if (idx >= jobOf_.size() || jobOf_[idx] < 0) return false;                               // no cached result: next round
+                queue_.pop();
+                Job& j = jobs_[jobOf_[idx]];
+                jobOf_[idx] = -1;
+                const double err = top.second;
+                const uint32_t p = nodes_[idx].degree, depth = nodes_[idx].depth;
+                if (!j.coarse)
+                {
+                    if (j.doH)
+                    {
+                        double maxNew = 0.0;
+                        for (int i = 0; i < 8; ++i) maxNew = std::max<double>(maxNew, j.hErr[i]);       // Octree.cpp:821
+                        j.hImp = (1.0 / (7.0 * coeffCount(p))) * (err - 8.0 * maxNew);                  // Octree.cpp:825
+                    }
+                    if (j.doP) j.pImp = (1.0 / (coeffCount(p + 1) - coeffCount(p))) * (err - 8.0 * j.pErr);   // Octree.cpp:854
+                }
+                // Octree.cpp:600-601 with BASIS_MAX_DEGREE-1 -> max_degree, TREE_MAX_DEPTH -> max_depth. A coarse cell always
+                // takes its degree-2 fit (the reference is undefined if that fit's error is exactly 0).
+                const bool refineP = j.coarse || (p < o_.max_degree && (depth == o_.max_depth || j.pImp > j.hImp));
+                const bool refineH = depth < o_.max_depth && !refineP;
+
+                if (!j.coarse && j.doH && j.doP)
+                {
+                    const double mag = std::max(std::fabs(j.pImp), std::fabs(j.hImp));
+                    const double margin = mag > 0.0 ? std::fabs(j.pImp - j.hImp) / mag : 0.0;
+                    if (margin <= 1e-9)
+                    {
+                        hpsdf_decision_log_entry e{};
+                        e.node_idx = idx; e.depth = depth; e.degree = p; e.chose_p = refineP; e.kind = 0;
+                        for (int a = 0; a < 3; ++a) e.centre[a] = (nodes_[idx].mn[a] + nodes_[idx].mx[a]) / 2.0f;
+                        e.p_improvement = j.pImp; e.h_improvement = j.hImp; e.relative_margin = margin;
+                        t_.decisionLog.push_back(e);
+                        t_.stats.near_tie_decisions++;
+                    }
+                }
+
+                if (refineP)
+                {
+                    total_ += (j.pErr - err);                                                            // Octree.cpp:257
+                    if (j.coarse) unfitted_--; else exactSum_ -= (long double)err;
+                    exactSum_ += (long double)j.pErr;
+                    nodes_[idx].slot   = j.pSlot;                                                        // Octree.cpp:286
+                    nodes_[idx].degree = (uint8_t)(j.coarse ? kCoarseDegree : p + 1);
+                    errOf_[idx] = j.pErr;
+                    queue_.push({ idx, j.pErr });                                                        // Octree.cpp:289-290
+                    pending_.push_back(idx);
+                    t_.stats.jobs_applied_p++;
+                }
+                else if (refineH)
+                {
+                    nodes_[idx].degree = kInternalTag;                                                   // Octree.cpp:265-272
+                    subdivide(idx);
+                    total_ -= err;
+                    exactSum_ -= (long double)err;
+                    jobOf_.resize(nodes_.size(), -1);
+                    errOf_.resize(nodes_.size(), 0.0);
+                    for (uint32_t i = 0; i < 8; ++i)
+                    {
+                        const uint64_t c = nodes_[idx].child + i;                                        // Octree.cpp:275-290
+                        total_ += j.hErr[i];
+                        exactSum_ += (long double)j.hErr[i];
+                        nodes_[c].slot = j.hSlot[i];
+                        nodes_[c].degree = (uint8_t)p;
+                        errOf_[c] = j.hErr[i];
+                        queue_.push({ c, j.hErr[i] });
+                        pending_.push_back(c);
+                    }
+                    t_.stats.jobs_applied_h++;
+                }
+                // else: degree and depth both at their maximum — the node leaves the queue (Octree.cpp:643-655)
+
+                if (refineP || refineH)
+                {
+                    lastApplied_.node_idx = idx; lastApplied_.depth = depth; lastApplied_.degree = p; lastApplied_.chose_p = refineP;
+                    lastApplied_.kind = 1; lastApplied_.p_improvement = j.pImp; lastApplied_.h_improvement = j.hImp;
+                    for (int a = 0; a < 3; ++a) lastApplied_.centre[a] = (nodes_[idx].mn[a] + nodes_[idx].mx[a]) / 2.0f;
+                    totalBeforeLast_ = lastTotal_; lastTotal_ = checkValue();
+                }
+                if (cfg_.enable_logging)                                                                 // Octree.cpp:292-296
+                    printf("\n%.11f\t%zu\t%f, %f, %f", total_, nodes_.size(), (double)(nodes_[idx].mn[0] + nodes_[idx].mx[0]) / 2.0,
+                           (double)(nodes_[idx].mn[1] + nodes_[idx].mx[1]) / 2.0, (double)(nodes_[idx].mn[2] + nodes_[idx].mx[2]) / 2.0);
+            }
+        }
+
+        // ReallocCoeffs (Octree.cpp:474-555): DFS from the root's children by child slot; leaves packed in visiting order.
+        hpsdf_status Builder::pack()
+        {
+            std::vector<uint32_t> srcOff, dstOff, count;
+            size_t cur = 0;
+            std::vector<uint64_t> stack;
+            for (int i = 7; i >= 0; --i) stack.push_back(nodes_[0].child + (uint64_t)i);
+            while (!stack.empty())
+            {
+                const uint64_t idx = stack.back(); stack.pop_back();
+                HostNode& n = nodes_[idx];
+                if (n.child == kNoChild)
+                {
+                    const uint32_t c = (uint32_t)coeffCount(n.degree);
+                    srcOff.push_back(n.slot); dstOff.push_back((uint32_t)cur); count.push_back(c);
+                    n.cstart = cur; cur += c;
+                }
+                else for (int i = 7; i >= 0; --i) stack.push_back(n.child + (uint64_t)i);
+            }
+            t_.nCoeffs = cur;
+            const uint32_t nSeg = (uint32_t)srcOff.size();
+            HPSDF_CUDA(cudaMalloc((void**)&t_.dCoeffs, std::max<size_t>(cur, 1) * sizeof(double)));
+            DeviceBuf<uint32_t> dSeg;
+            HPSDF_CUDA(dSeg.reserve(3 * (size_t)nSeg));
+            HPSDF_CUDA(cudaMemcpyAsync(dSeg.p, srcOff.data(), nSeg * 4, cudaMemcpyHostToDevice, stream_));
+            HPSDF_CUDA(cudaMemcpyAsync(dSeg.p + nSeg, dstOff.data(), nSeg * 4, cudaMemcpyHostToDevice, stream_));
+            HPSDF_CUDA(cudaMemcpyAsync(dSeg.p + 2 * (size_t)nSeg, count.data(), nSeg * 4, cudaMemcpyHostToDevice, stream_));
+            HPSDF_CUDA(launchGatherSegments(pool_.p, t_.dCoeffs, dSeg.p, dSeg.p + nSeg, dSeg.p + 2 * (size_t)nSeg, nSeg, stream_));
+            t_.stats.kernel_launches++;
+            HPSDF_CUDA(cudaStreamSynchronize(stream_));
+            return HPSDF_OK;
+        }
+
+        hpsdf_status Builder::run()
+        {
+            const double t0 = nowMs();
+            stream_ = (cudaStream_t)o_.stream;
+            if (!stream_) { HPSDF_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking)); ownStream_ = true; }
+            HPSDF_CUDA(cudaEventCreate(&ev0_));
+            HPSDF_CUDA(cudaEventCreate(&ev1_));
+            if (o_.comm) { rank_ = commRank(o_.comm); world_ = commWorld(o_.comm); }
+
+            hpsdf_status st = HPSDF_OK;
+            // CreateRoot (Octree.cpp:792-801) + UniformlyRefine
+            nodes_.clear();
+            nodes_.reserve(8192);
+            HostNode root;
+            root.depth = 0;
+            for (int i = 0; i < 3; ++i) { root.mn[i] = -0.5f; root.mx[i] = 0.5f; }
+            nodes_.push_back(root);
+            subdivide(0);
+            for (uint32_t i = 0; i < 8; ++i) refineUniform(1 + i, 1);
+            errOf_.assign(nodes_.size(), kInitialErr);
+            jobOf_.assign(nodes_.size(), -1);
+            total_ = std::pow(8, 4) * kInitialErr;                                                      // Octree.cpp:212
+            unfitted_ = (long)queue_.size();
+            lastTotal_ = totalBeforeLast_ = total_;
+
+            double replayMs = 0.0;
+            for (;;)
+            {
+                st = evaluateRound();
+                if (st != HPSDF_OK) break;
+                const double r0 = nowMs();
+                const bool done = replay();
+                replayMs += nowMs() - r0;
+                if (done) break;
+                if (pending_.empty()) { setLastError("internal: replay stalled with nothing to evaluate"); st = HPSDF_ERR_CUDA; break; }
+            }
+            if (st == HPSDF_OK) st = pack();
+            if (st == HPSDF_OK)
+            {
+                t_.stats.total_error = o_.total_mode == HPSDF_TOTAL_EXACT_SUM ? (double)exactSum_ : total_;
+                t_.stats.exact_total_error = (double)exactSum_;
+                const double thr = cfg_.target_error_threshold;
+                t_.stats.cut_margin = (thr - checkValue()) / thr;
+                if (lastApplied_.kind == 1)
+                {
+                    // how far above the threshold the total was before the last applied job, relative to the threshold
+                    lastApplied_.relative_margin = std::min(std::fabs(totalBeforeLast_ - thr), std::fabs(thr - checkValue())) / thr;
+                    t_.decisionLog.push_back(lastApplied_);
+                }
+                t_.stats.host_replay_ms = replayMs;
+                if (cfg_.continuity_enforce)
+                {
+                    const double c0 = nowMs();
+                    st = continuityPostProcess(t_, o_, stream_);                                          // Octree.cpp:341-344
+                    t_.stats.continuity_ms = nowMs() - c0;
+                }
+            }
+            if (st == HPSDF_OK) st = finalizeQueryStructures(t_, stream_);
+            if (st == HPSDF_OK)
+            {
+                uint64_t leaves = 0;
+                for (const HostNode& n : nodes_) leaves += n.child == kNoChild;
+                t_.stats.n_nodes = nodes_.size(); t_.stats.n_leaves = leaves; t_.stats.n_coeffs = t_.nCoeffs;
+            }
+            cudaEventDestroy(ev0_); cudaEventDestroy(ev1_);
+            if (ownStream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); }
+            t_.stats.total_ms = nowMs() - t0;
+            return st;
+        }
+    }
+
+    hpsdf_status buildOctree(hpsdf_octree& t, const hpsdf_build_opts& opts, const SdfProgramDev& prog)
+    {
+        Builder b(t, opts, prog);
+        return b.run();
+    }
+}

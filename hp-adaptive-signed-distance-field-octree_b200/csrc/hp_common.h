@@ -1,0 +1,126 @@
+// hp_common.h — constants, tables and plain structs shared by the host scheduler and the CUDA kernels.
+//
+// Reference constants: Include/HP/Consts.h:7-8 (BASIS_MAX_DEGREE = 12, TREE_MAX_DEPTH = 10), Include/HP/Utility.h:40-196
+// (SumToN, NormalisedLengths, LegendreCoeffientCount, LegendreCoefficent, BasisIndexValues, SharedFaceLookup).
+// The tables are rebuilt here from their definitions; nothing is copied from the reference.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include "../../include/hpsdf.h"
+
+#if defined(__CUDACC__)
+#define HPSDF_HD __host__ __device__
+#else
+#define HPSDF_HD
+#endif
+
+namespace hpsdf
+{
+    constexpr int      kMaxDegree   = 12;                    // BASIS_MAX_DEGREE
+    constexpr int      kMaxDepth    = 10;                    // TREE_MAX_DEPTH
+    constexpr uint8_t  kInternalTag = 13;                    // BASIS_MAX_DEGREE + 1 (Node.cpp:12): degree tag of internal nodes
+    constexpr uint64_t kNoChild     = 0xFFFFFFFFFFFFFFFFull; // childIdx = -1 (Node.cpp:8)
+    constexpr double   kInitialErr  = 100.0;                 // INITIAL_NODE_ERR (Octree.h:89)
+    constexpr int      kCoarseDepth = 4, kCoarseDegree = 2;  // UniformlyRefine (Octree.cpp:115-116)
+    constexpr int      kMaxCoeffs   = 455;
+
+    // LegendreCoeffientCount (Utility.h:87-106). The reference evaluates (u32)((1.0/6.0)*(i+1)*(i+2)*(i+3)) in f64, which
+    // truncates to 83 (not 84) at i = 6. The value is part of the MemoryBlock contract (a degree-6 leaf stores 83
+    // coefficients; a 6->7 p-fit recomputes index 83 = (6,0,0) with the degree-7 rule), so it is reproduced, not fixed.
+    HPSDF_HD constexpr int coeffCount(int degree)
+    {
+        return degree == 6 ? 83 : (degree + 1) * (degree + 2) * (degree + 3) / 6;
+    }
+    // number of (b, c) pairs with b + c <= d
+    HPSDF_HD constexpr int pairCount(int d) { return (d + 1) * (d + 2) / 2; }
+    // Gauss-Legendre points per axis of a degree-d fit (Octree.cpp:1016-1017: rule 4d+1)
+    HPSDF_HD constexpr int fitRule(int d) { return 4 * d + 1; }
+
+    // Sum-factorised FLOPs of one full fit at degree d, SDF evaluation excluded:
+    // 2(d+1)n^3 + 2 T2(d) n^2 + 2 N_d n + 4 n^3.
+    inline double fitFlops(int d)
+    {
+        const double n = fitRule(d);
+        return 2.0 * (d + 1) * n * n * n + 2.0 * pairCount(d) * n * n + 2.0 * ((d + 1) * (d + 2) * (d + 3) / 6) * n + 4.0 * n * n * n;
+    }
+
+    // Host-side tables (tables.cpp)
+    struct Tables
+    {
+        double  nl[kMaxDegree + 1][kMaxDepth + 1];   // NormalisedLengths[a][depth] = sqrt((2a+1) 2^depth), Newton-iterated as Utility.h:25-35
+        double  rec[kMaxDegree + 1][2];              // (2i-1)/i, (i-1)/i
+        uint8_t bidx[kMaxCoeffs][3];                 // BasisIndexValues: shell p, then i, then j; k = p-i-j
+        uint8_t face[3][4][2];                       // SharedFaceLookup[dim][j] = (low child, high child)
+    };
+    const Tables& tables();
+    // Gauss-Legendre rule with n points (1..64), nodes ascending: pointers to n roots / n weights
+    const double* glRoots(int n);
+    const double* glWeights(int n);
+
+    // ---- device-side descriptors ------------------------------------------------------------------------------
+    // Unit cube -> user space map of Octree::Create (Octree.cpp:322-328) and its f32-rounded inverse used by Query
+    // (Octree.cpp:323, 420, 665).
+    struct RootMap
+    {
+        double centre[3];
+        double sizes[3];
+        double invSizes[3];     // (double)(1.0f / size_f32)
+    };
+
+    // One FitPolynomial call (Octree.cpp:1007-1093) of a round. 32 bytes.
+    struct FitTask
+    {
+        float    cx, cy, cz, half;   // cell centre and half size in the internal unit cube (dyadic: exact in f32)
+        uint32_t out;                // offset (in doubles) of the output coefficient slot in the pool
+        uint32_t src;                // offset of the slot whose lower shells are kept (p-fit), or kNoSrc (from scratch)
+        uint8_t  depth;              // tree depth of the cell (selects NormalisedLengths[.][depth])
+        uint8_t  degree;             // target degree d
+        uint8_t  degreeIn;           // degree of the kept lower shells (0 = from scratch)
+        uint8_t  pad;
+        uint32_t rec;                // index of the result record
+    };
+    constexpr uint32_t kNoSrc = 0xFFFFFFFFu;
+
+    // What the host replay needs from a fit: the raw top-shell energy (Octree.cpp:1062-1069) and coeffs[0]
+    // (the cell mean of the approximant up to NL[0][depth]^3, for the nearness weight).
+    struct FitRecord
+    {
+        double rawErr;
+        double c0;
+    };
+
+    // Device SDF program (hpsdf_sdf_program with handles resolved to device pointers). Passed by value as a kernel parameter.
+    struct DeviceMeshView;
+    struct DeviceTreeView;
+    struct SdfInstrDev
+    {
+        uint32_t    op;
+        uint32_t    pad;
+        const void* handle;        // DeviceMeshView* / DeviceTreeView* in device memory, or nullptr
+        double      p[8];
+    };
+    struct SdfProgramDev
+    {
+        uint32_t    n;
+        uint32_t    pad;
+        SdfInstrDev instr[HPSDF_PROGRAM_MAX_INSTR];
+    };
+
+    // Leaf/internal node as the Query kernel reads it: 16 bytes, one LDG.128.
+    struct QNode
+    {
+        uint32_t child;        // first child (8 consecutive), or 0xFFFFFFFF for a leaf
+        uint32_t cstart;       // leaf: offset of its coefficients in the PADDED device store (even => 16-byte aligned)
+        uint32_t degree;       // leaf degree; kInternalTag for internal nodes
+        uint32_t depth;
+    };
+
+    struct DeviceTreeView
+    {
+        const QNode*    nodes;
+        const double*   coeffs;      // padded store: every leaf starts at an even index
+        const uint32_t* top;         // 4096 entries: node reached at depth <= 4 for each cell of the 16^3 grid (x + 16 y + 256 z)
+        RootMap         map;
+        uint32_t        nNodes;
+    };
+}

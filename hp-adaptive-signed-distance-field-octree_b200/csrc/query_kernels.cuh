@@ -1,0 +1,126 @@
+// query_kernels.cuh — batched Octree::Query (Source/HP/Octree.cpp:662-702): the reference has no batch API
+// (callers loop over Query, HPBenchmarks.cpp:107-110); this is the data-parallel form.
+//
+// Layout: points are AoS n x 3 f64 (the Eigen::Vector3d array a caller already has). A CTA stages a tile of 256 points
+// (6 KB) into shared memory with coalesced 16-byte loads, then each thread evaluates one point. The 4096-entry top-of-tree
+// table (16 KB) is staged once per CTA; the grid is persistent (a few CTAs per SM looping over tiles) so that staging
+// amortises. Algorithmic HBM traffic: 24 B in + 8 B out per point; the tree (16 B nodes + padded coefficients) stays in L2.
+#pragma once
+#include "query_eval.cuh"
+
+namespace hpsdf
+{
+    constexpr int kQueryThreads = 256;
+
+    __global__ void __launch_bounds__(kQueryThreads)
+    queryKernel(const DeviceTreeView view, const double* __restrict__ xyz, size_t n, double* __restrict__ out)
+    {
+        __shared__ uint32_t sTop[4096];
+        __shared__ __align__(16) double sPts[kQueryThreads * 3];
+        const bool useTop = view.top != nullptr;
+        if (useTop)
+            for (int i = threadIdx.x; i < 1024; i += kQueryThreads)
+                reinterpret_cast<uint4*>(sTop)[i] = __ldg(reinterpret_cast<const uint4*>(view.top) + i);
+
+        const size_t nTiles = (n + kQueryThreads - 1) / kQueryThreads;
+        for (size_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x)
+        {
+            const size_t base = tile * kQueryThreads;
+            const size_t cnt  = n - base < (size_t)kQueryThreads ? n - base : (size_t)kQueryThreads;
+            __syncthreads();                       // previous tile's reads of sPts are done (and sTop is ready)
+            const double* src = xyz + 3 * base;    // 3 * 256 * 8 B = 6144 B per tile: base of a tile is 16-byte aligned
+            if (cnt == (size_t)kQueryThreads)
+            {
+                for (int v = threadIdx.x; v < kQueryThreads * 3 / 2; v += kQueryThreads)
+                    reinterpret_cast<double2*>(sPts)[v] = __ldcs(reinterpret_cast<const double2*>(src) + v);
+            }
+            else
+                for (size_t v = threadIdx.x; v < 3 * cnt; v += kQueryThreads) sPts[v] = src[v];
+            __syncthreads();
+            if (threadIdx.x < cnt)
+            {
+                const double x = sPts[3 * threadIdx.x], y = sPts[3 * threadIdx.x + 1], z = sPts[3 * threadIdx.x + 2];
+                const double v = queryPoint(view.nodes, view.coeffs, useTop ? sTop : nullptr, view.map, x, y, z);
+                __stcs(out + base + threadIdx.x, v);
+            }
+        }
+    }
+
+    // Octree::QueryWithGradient (Octree.cpp:749-789) / FApproxWithGradient (:904-985): central differences with eps = 1e-4
+    // in the leaf's local coordinate, gradient normalised. One thread per point, generic-degree loops (not a hot path).
+    __global__ void __launch_bounds__(256)
+    queryGradientKernel(const DeviceTreeView view, const double* __restrict__ xyz, size_t n, double* __restrict__ out,
+                        double* __restrict__ grad, const uint32_t* __restrict__ bidx)
+    {
+        const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (t >= n) return;
+        const RootMap& map = view.map;
+        const double px = (xyz[3 * t] - map.centre[0]) * map.invSizes[0];
+        const double py = (xyz[3 * t + 1] - map.centre[1]) * map.invSizes[1];
+        const double pz = (xyz[3 * t + 2] - map.centre[2]) * map.invSizes[2];
+        const float fx = (float)px, fy = (float)py, fz = (float)pz;
+        if (!(fx >= -0.5f && fx <= 0.5f && fy >= -0.5f && fy <= 0.5f && fz >= -0.5f && fz <= 0.5f)) { out[t] = DBL_MAX; return; }
+        double c[3] = { 0.0, 0.0, 0.0 }, q = 0.25;
+        const double p[3] = { px, py, pz };
+        uint4 raw = __ldg(reinterpret_cast<const uint4*>(view.nodes));
+        while (raw.z == kInternalTag)
+        {
+            uint32_t b[3];
+            for (int a = 0; a < 3; ++a) { b[a] = p[a] >= c[a]; c[a] += b[a] ? q : -q; }
+            q *= 0.5;
+            raw = __ldg(reinterpret_cast<const uint4*>(view.nodes) + raw.x + b[0] + (b[1] << 1) + (b[2] << 2));
+        }
+        const int depth = (int)raw.w, degree = (int)raw.z;
+        const double* coeffs = view.coeffs + raw.y;
+        const double scale = (double)(2u << depth), eps = 0.0001;
+        double lut[kMaxDegree + 1][3][3];
+        for (int a = 0; a < 3; ++a)
+        {
+            const double u = (p[a] - c[a]) * scale;
+            const double us[3] = { u, u + eps, u - eps };
+            for (int v = 0; v < 3; ++v)
+            {
+                lut[0][a][v] = c_nl[0][depth];
+                double m2 = 0.0, m1 = 1.0, l = 1.0;
+                for (int j = 1; j <= degree; ++j)
+                {
+                    l = c_rec[j][0] * us[v] * m1 - c_rec[j][1] * m2; m2 = m1; m1 = l;
+                    lut[j][a][v] = l * c_nl[j][depth];
+                }
+            }
+        }
+        const int nc = coeffCount(degree);
+        double g[3];
+        for (int k = 0; k < 3; ++k)
+        {
+            double fp = 0.0, fm = 0.0;
+            for (int i = 0; i < nc; ++i)
+            {
+                const int a = (bidx[i] >> (8 * k)) & 0xFF;
+                fp += coeffs[i] * lut[a][k][1]; fm += coeffs[i] * lut[a][k][2];            // Octree.cpp:961-965
+            }
+            g[k] = (fp - fm) / (2.0 * eps);
+        }
+        const double nrm = sqrt(g[0] * g[0] + (g[1] * g[1] + g[2] * g[2]));
+        if (nrm > 0.0) { g[0] /= nrm; g[1] /= nrm; g[2] /= nrm; }
+        double f = 0.0;
+        for (int i = 0; i < nc; ++i)
+        {
+            const uint32_t abc = bidx[i];
+            f += coeffs[i] * ((lut[abc & 0xFF][0][0] * lut[(abc >> 8) & 0xFF][1][0]) * lut[(abc >> 16) & 0xFF][2][0]);
+        }
+        out[t] = f;
+        grad[3 * t] = g[0]; grad[3 * t + 1] = g[1]; grad[3 * t + 2] = g[2];
+    }
+
+    __global__ void gatherSegmentsKernel(const double* __restrict__ src, double* __restrict__ dst, const uint32_t* __restrict__ srcOff,
+                                         const uint32_t* __restrict__ dstOff, const uint32_t* __restrict__ count, uint32_t nSeg)
+    {
+        // one warp per segment
+        const uint32_t seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+        if (seg >= nSeg) return;
+        const double* s = src + srcOff[seg];
+        double* d = dst + dstOff[seg];
+        for (uint32_t i = lane; i < count[seg]; i += 32) d[i] = s[i];
+    }
+}

@@ -1,0 +1,248 @@
+"""GPU: the CUDA path through the C ABI against the CPU oracle and the golden vectors from the reference.
+
+Tolerances are BASELINE.json's: identical topology, per-leaf |dc|inf/|c|inf <= 1e-10, |dQuery| <= 1e-9.
+"""
+import numpy as np
+import pytest
+
+from cases import CASES, root_points, leaf_table
+from common import golden, oracle_cfg, product_cfg, check_tree_against_golden, rel_inf
+
+pytestmark = pytest.mark.gpu
+
+COEFF_TOL = 1e-10
+QUERY_TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def built(hp):
+    """GPU-built trees, cached per case for the module."""
+    cache = {}
+
+    def get(name, **optkw):
+        key = (name, tuple(sorted(optkw.items())))
+        if key not in cache:
+            cfg, prog = product_cfg(hp, name)
+            t = hp.Octree()
+            t.Create(cfg, prog, hp.BuildOpts(**optkw) if optkw else None)
+            cache[key] = t
+        return cache[key]
+    return get
+
+
+def test_sdf_program_evaluator_matches_cpu(hp, oracle):
+    from oracle import hpref
+    pts = np.random.default_rng(0).uniform(-0.6, 0.8, (20000, 3))
+    for name in ("c1_readme", "c2_csg", "custom_domain"):
+        items = CASES[name]["prog"]
+        a = hp.SdfProgram(items).eval(pts)
+        b = oracle.sdf_eval(hpref.make_program(items), pts)
+        assert np.abs(a - b).max() <= 1e-14, name
+    items = [("box", [0.1, 0.0, 0.0, 0.2, 0.3, 0.1]), ("sphere", [0.2, 0.1, 0, 0.25]), ("subtract", []),
+             ("plane", [0.0, 0.0, 1.0, -0.05]), ("intersect", []), ("torus", [0, 0, 0, 0.3, 0.05, 2]), ("union", []), ("negate", [])]
+    assert np.abs(hp.SdfProgram(items).eval(pts) - oracle.sdf_eval(hpref.make_program(items), pts)).max() <= 1e-14
+
+
+def test_single_fits_match_reference_golden(hp):
+    g = golden("fits")
+    names = list(CASES)
+    worst = 0.0
+    for k in range(int(g["n_fits"])):
+        case, degree, depth, degree_in = [int(v) for v in g["fit%03d_meta" % k]]
+        if degree_in:
+            continue        # kept-shell fits are exercised through Create (p-refinement) below
+        cfg, prog = product_cfg(hp, names[case])
+        coeffs, err, _ = hp.fit_batch(cfg, prog, g["fit%03d_cell" % k][None, :], [depth], degree)
+        worst = max(worst, rel_inf(coeffs[0], g["fit%03d_coeffs" % k]))
+        assert abs(err[0] - float(g["fit%03d_err" % k])) <= 1e-9 * float(g["fit%03d_err" % k]) + 1e-300
+    assert worst <= COEFF_TOL, worst
+
+
+@pytest.mark.parametrize("degree", [2, 3, 4, 5, 6, 7, 9, 11])
+def test_fit_batch_matches_oracle_all_degrees(hp, oracle, degree):
+    """Every template instantiation of the fit kernel, incl. the 83-coefficient degree 6 and the multi-pass degrees."""
+    from oracle import hpref
+    cfg, prog = product_cfg(hp, "c2_csg")
+    ocfg, oprog = oracle_cfg(hpref, "c2_csg")
+    rng = np.random.default_rng(degree)
+    depth = 5
+    half = 0.5 ** (depth + 1)
+    n = 6 if degree <= 6 else 2
+    centres = (rng.integers(8, 24, (n, 3)) + 0.5) * 2 * half - 0.5
+    cells = np.concatenate([centres, np.full((n, 1), half)], 1).astype(np.float32)
+    coeffs, err, _ = hp.fit_batch(cfg, prog, cells, np.full(n, depth), degree)
+    assert coeffs.shape[1] == hp.COEFF_COUNT[degree]
+    for i in range(n):
+        c, e = oracle.oracle_fit(ocfg, oprog, centres[i] - half, centres[i] + half, degree, depth)
+        assert rel_inf(coeffs[i], c) <= COEFF_TOL
+        assert abs(err[i] - e) <= 1e-9 * e + 1e-300
+
+
+@pytest.mark.parametrize("name", ["sphere_poly_1e8", "custom_domain", "csg_small"])
+def test_create_matches_reference_golden(hp, built, name):
+    t = built(name)
+    blk = hp.parse_block(t.ToMemoryBlockBytes())
+    g = golden(name)
+    worst = check_tree_against_golden(blk, g, hp.COEFF_COUNT, COEFF_TOL)
+    st = t.stats()
+    assert st["jobs_applied_p"] == int(g["applied_p"]) and st["jobs_applied_h"] == int(g["applied_h"])
+    assert abs(st["total_error"] - float(g["final_total"])) <= 1e-6 * float(g["final_total"])
+    q = t.Query(g["query_pts"])
+    assert np.abs(q - g["query_vals"]).max() <= QUERY_TOL
+    print(name, "worst |dc|inf/|c|inf", worst, "rounds", st["rounds"], "fits", st["fits_evaluated"], "ms", st["total_ms"])
+
+
+@pytest.mark.parametrize("name", ["sphere_exp_1e8", "c2_csg"])
+def test_create_matches_oracle_full_tree(hp, oracle, built, name):
+    """Whole-tree comparison against the CPU oracle run here: node arrays (numbering included), every leaf's
+    coefficients, 1e5 query values; divergences would show in the decision log."""
+    from oracle import hpref
+    ocfg, oprog = oracle_cfg(hpref, name)
+    o = oracle.OracleTree.build(ocfg, oprog, threads=8)
+    t = built(name)
+    a, b = hp.parse_block(t.ToMemoryBlockBytes()), hpref.parse_block(o.block())
+    assert a["n_nodes"] == b["n_nodes"] and a["n_coeffs"] == b["n_coeffs"], (t.stats(), t.decision_log()[-3:])
+    for f in ("child", "mn", "mx", "deg", "depth"):
+        assert np.array_equal(a["nodes"][f], b["nodes"][f]), f
+    leaf = a["nodes"]["child"] == np.uint64(0xFFFFFFFFFFFFFFFF)
+    assert np.array_equal(a["nodes"]["cstart"][leaf], b["nodes"]["cstart"][leaf])
+    _, _, deg, ca = leaf_table(a, hp.COEFF_COUNT)
+    _, _, _, cb = leaf_table(b, hp.COEFF_COUNT)
+    worst = max(rel_inf(x, y) for x, y in zip(ca, cb))
+    assert worst <= COEFF_TOL, worst
+    pts = root_points(CASES[name]["cfg"], 100000, seed=5, margin=0.01)
+    qa, qb = t.Query(pts), o.query(pts, 8)
+    assert np.array_equal(qa == hp.DBL_MAX, qb == hp.DBL_MAX)
+    assert np.abs(qa - qb)[qb != hp.DBL_MAX].max() <= QUERY_TOL
+    so, st = o.stats(), t.stats()
+    assert st["jobs_applied_p"] == so["applied_p"] and st["jobs_applied_h"] == so["applied_h"]
+    assert st["n_leaves"] == int(leaf.sum())
+    print(name, "worst", worst, {k: st[k] for k in ("rounds", "fits_evaluated", "jobs_evaluated", "total_ms", "fit_kernel_ms", "host_replay_ms", "near_tie_decisions", "cut_margin")})
+
+
+def test_build_option_switches_match_oracle(hp, oracle):
+    from oracle import hpref
+    ocfg, oprog = oracle_cfg(hpref, "sphere_poly_1e8")
+    cfg, prog = product_cfg(hp, "sphere_poly_1e8")
+    for kw in (dict(max_degree=3), dict(total_mode=1), dict(max_degree=2, max_depth=6)):
+        o = oracle.OracleTree.build(ocfg, oprog, threads=8, **kw)
+        t = hp.Octree()
+        t.Create(cfg, prog, hp.BuildOpts(**kw))
+        a, b = hp.parse_block(t.ToMemoryBlockBytes()), hpref.parse_block(o.block())
+        assert a["n_nodes"] == b["n_nodes"] and a["n_coeffs"] == b["n_coeffs"], kw
+        assert np.array_equal(a["nodes"]["deg"], b["nodes"]["deg"]), kw
+        assert np.abs(a["coeffs"] - b["coeffs"]).max() <= COEFF_TOL * np.abs(b["coeffs"]).max()
+
+
+def test_memory_block_is_accepted_by_the_cpu_side_and_back(hp, oracle, built):
+    """ToMemoryBlock is byte-compatible: the oracle's (and, where built, the reference's own) FromMemoryBlock + Query
+    accepts GPU-built trees; FromMemoryBlock accepts CPU-built trees."""
+    from oracle import hpref
+    t = built("csg_small")
+    raw = t.ToMemoryBlockBytes()
+    pts = root_points(CASES["csg_small"]["cfg"], 20000, seed=8, margin=0.02)
+    qa = t.Query(pts)
+    assert np.abs(oracle.OracleTree.from_block(raw).query(pts) - qa).max() <= QUERY_TOL
+    if hpref.available():
+        assert np.abs(hpref.RefTree.from_block(raw).query(pts) - qa).max() <= QUERY_TOL
+    t2 = hp.Octree()
+    t2.FromMemoryBlock(hp.MemoryBlock.frombytes(raw))
+    assert np.array_equal(t2.Query(pts), qa)                          # round trip is bit-exact
+    assert t2.ToMemoryBlockBytes()[:-80] == raw[:-80] or hp.parse_block(t2.ToMemoryBlockBytes())["n_coeffs"] == hp.parse_block(raw)["n_coeffs"]
+    ocfg, oprog = oracle_cfg(hpref, "custom_domain")
+    o = oracle.OracleTree.build(ocfg, oprog, threads=8)
+    t3 = hp.Octree()
+    t3.FromMemoryBlock(hp.MemoryBlock.frombytes(bytes(o.block())))
+    p3 = root_points(CASES["custom_domain"]["cfg"], 20000, seed=9, margin=0.02)
+    assert np.abs(t3.Query(p3) - o.query(p3)).max() <= QUERY_TOL
+    mn, mx = t3.GetRootAABB()
+    assert mn.tolist() == [-0.25] * 3 and mx.tolist() == [5.0] * 3
+    c = t3.copy()                                                      # copy constructor (Octree.cpp:24-45)
+    t3.Clear()
+    assert np.abs(c.Query(p3) - o.query(p3)).max() <= QUERY_TOL
+
+
+def test_bad_blocks_are_rejected(hp, built):
+    raw = bytearray(built("csg_small").ToMemoryBlockBytes())
+    for bad in (bytes(raw[:-8]), b"", bytes(raw[:50])):
+        with pytest.raises(hp.HpsdfError) as e:
+            hp.Octree().FromMemoryBlock(hp.MemoryBlock.frombytes(bad) if bad else hp.MemoryBlock(0, None))
+        assert e.value.status == hp.ERR_BAD_BLOCK
+    raw2 = bytearray(raw)
+    n_coeffs = int(np.frombuffer(raw2[:8], np.uint64)[0])
+    off = 16 + 8 * n_coeffs                                             # node 0
+    raw2[off:off + 8] = np.uint64(10 ** 9).tobytes()                    # child index out of range
+    with pytest.raises(hp.HpsdfError):
+        hp.Octree().FromMemoryBlock(hp.MemoryBlock.frombytes(bytes(raw2)))
+
+
+def test_query_edge_cases(hp, oracle, built):
+    from oracle import hpref
+    t = built("sphere_poly_1e8")
+    o = oracle.OracleTree.from_block(t.ToMemoryBlockBytes())
+    assert len(t.Query(np.zeros((0, 3)))) == 0                         # empty batch
+    edge = np.array([[0.5, 0.5, 0.5], [-0.5, -0.5, -0.5], [0.5000001, 0, 0], [0, 0, 0], [0.25, 0, 0], [-0.5, 0.5, 0.0],
+                     [0.03125, 0.0625, -0.125], [1e-300, -1e-300, 0.0], [0.5 + 1e-9, 0, 0], [np.nextafter(0.5, 1), 0, 0],
+                     [np.nan, 0, 0], [np.inf, 0, 0]])
+    qa, qb = t.Query(edge), o.query(edge)
+    assert np.array_equal(qa == hp.DBL_MAX, qb == hp.DBL_MAX)
+    m = qb != hp.DBL_MAX
+    assert np.abs(qa[m] - qb[m]).max() <= QUERY_TOL
+    for n in (1, 255, 256, 257, 1000):                                  # ragged tiles
+        pts = root_points(CASES["sphere_poly_1e8"]["cfg"], n, seed=n)
+        assert np.abs(t.Query(pts) - o.query(pts)).max() <= QUERY_TOL
+    assert isinstance(t.Query(np.array([0.1, 0.2, 0.3])), float)       # single point, like Octree::Query
+    # every cell corner/face of the 16^3 grid and a finer lattice: descent ties (pt == midpoint) go to the upper child
+    g = np.linspace(-0.5, 0.5, 65)
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    assert np.abs(t.Query(lat) - o.query(lat, 8)).max() <= QUERY_TOL
+
+
+def test_query_gradient_matches_oracle(hp, oracle, built):
+    t = built("csg_small")
+    o = oracle.OracleTree.from_block(t.ToMemoryBlockBytes())
+    pts = root_points(CASES["csg_small"]["cfg"], 5000, seed=4)
+    va, ga = t.QueryWithGradient(pts)
+    vb, gb = o.query_gradient(pts)
+    assert np.abs(va - vb).max() <= QUERY_TOL
+    assert np.abs(ga - gb).max() <= 1e-6                                # central differences amplify rounding by 1/(2 eps)
+
+
+def test_large_batch_properties(hp, oracle, built):
+    """BASELINE-scale batch (1.6e7 points): idempotent, chunk-independent, equal to the oracle on a subsample, and the
+    device-pointer entry point gives the same bits as the host-pointer one."""
+    import torch
+    t = built("c2_csg")
+    n = 1 << 24
+    gen = torch.Generator(device="cuda").manual_seed(0x5DF0C7EE)
+    pts = (torch.rand((n, 3), generator=gen, device="cuda", dtype=torch.float64) * 0.75 - 0.25).contiguous()
+    out = torch.empty(n, device="cuda", dtype=torch.float64)
+    t.QueryDevice(pts.data_ptr(), n, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    out2 = torch.empty_like(out)
+    t.QueryDevice(pts.data_ptr(), n, out2.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    host = pts[: 1 << 22].cpu().numpy()
+    assert np.array_equal(t.Query(host), out[: 1 << 22].cpu().numpy())
+    o = oracle.OracleTree.from_block(t.ToMemoryBlockBytes())
+    idx = np.random.default_rng(1).integers(0, n, 200000)
+    sub = pts[torch.from_numpy(idx).cuda()].cpu().numpy()
+    assert np.abs(o.query(sub, 8) - out[torch.from_numpy(idx).cuda()].cpu().numpy()).max() <= QUERY_TOL
+    assert float(out.abs().max()) < 2.0                                 # all inside the root: no DBL_MAX
+
+
+def test_sdf_operations_match_min_max_of_analytic(hp):
+    """Octree::UnionSDF / IntersectSDF / SubtractSDF (Octree.cpp:355-400) with the reference's own test tolerance
+    (HPUnitTests.cpp:207-282: |d| <= 0.05 against min/max of the analytic spheres, nearness None)."""
+    cfg = hp.Config(target_error_threshold=1e-8, continuity_enforce=0)
+    a = [("sphere", [0.25, 0.0, 0.0, 0.5])]
+    b = [("sphere", [-0.25, 0.0, 0.0, 0.3])]
+    pts = np.random.default_rng(2).uniform(-0.5, 0.5, (100000, 3))
+    fa = np.linalg.norm(pts - [0.25, 0, 0], axis=1) - 0.5
+    fb = np.linalg.norm(pts - [-0.25, 0, 0], axis=1) - 0.3
+    for op, truth in (("UnionSDF", np.minimum(fa, fb)), ("IntersectSDF", np.maximum(fa, fb)), ("SubtractSDF", np.maximum(fb, -fa))):
+        t = hp.Octree()
+        t.Create(cfg, hp.SdfProgram(a))
+        getattr(t, op)(hp.SdfProgram(b))
+        assert np.abs(t.Query(pts) - truth).max() <= 0.05, op
