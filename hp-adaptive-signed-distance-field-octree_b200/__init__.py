@@ -99,6 +99,12 @@ class DecisionLogEntry(C.Structure):
                 ("h_improvement", C.c_double), ("relative_margin", C.c_double)]
 
 
+class ApplyLogEntry(C.Structure):
+    _fields_ = [("node_idx", C.c_uint64), ("kind", C.c_uint32), ("degree", C.c_uint32), ("initial_err", C.c_double),
+                ("new_err", C.c_double), ("p_improvement", C.c_double), ("h_improvement", C.c_double),
+                ("total_after", C.c_double)]
+
+
 class FrontierBench(C.Structure):
     _fields_ = [("ms_per_launch", C.c_double), ("jobs", C.c_uint64), ("fits", C.c_uint64), ("sdf_evals", C.c_uint64),
                 ("algorithmic_flops", C.c_double), ("checksum", C.c_double)]
@@ -112,7 +118,7 @@ EXPORTS = [
     "hpsdf_config_validate", "hpsdf_build_opts_default", "hpsdf_sdf_eval", "hpsdf_mesh_create",
     "hpsdf_mesh_signed_distance", "hpsdf_mesh_aabb", "hpsdf_mesh_destroy", "hpsdf_create", "hpsdf_query",
     "hpsdf_query_device", "hpsdf_query_with_gradient", "hpsdf_to_memory_block", "hpsdf_from_memory_block", "hpsdf_clone",
-    "hpsdf_get_root_aabb", "hpsdf_destroy", "hpsdf_get_build_stats", "hpsdf_get_decision_log", "hpsdf_fit_batch",
+    "hpsdf_get_root_aabb", "hpsdf_destroy", "hpsdf_get_build_stats", "hpsdf_get_decision_log", "hpsdf_get_apply_log", "hpsdf_fit_batch",
     "hpsdf_bench_frontier", "hpsdf_measure_fp64_peak", "hpsdf_comm_get_unique_id", "hpsdf_comm_init",
     "hpsdf_comm_destroy", "hpsdf_shard_range",
 ]
@@ -164,6 +170,8 @@ def lib():
     L.hpsdf_get_build_stats.argtypes = [vp, C.POINTER(BuildStats)]
     L.hpsdf_get_decision_log.argtypes = [vp, vp, sz]
     L.hpsdf_get_decision_log.restype = sz
+    L.hpsdf_get_apply_log.argtypes = [vp, vp, sz]
+    L.hpsdf_get_apply_log.restype = sz
     L.hpsdf_fit_batch.argtypes = [C.POINTER(Config), C.POINTER(_Program), vp, vp, sz, u32, vp, vp, i32, C.POINTER(C.c_float)]
     L.hpsdf_bench_frontier.argtypes = [C.POINTER(Config), C.POINTER(_Program), u32, u32, u32, i32, vp, C.POINTER(FrontierBench)]
     L.hpsdf_measure_fp64_peak.argtypes = [i32, vp, C.POINTER(dbl)]
@@ -365,6 +373,16 @@ class Octree:
         return [dict(node_idx=e.node_idx, depth=e.depth, degree=e.degree, centre=tuple(e.centre), chose_p=e.chose_p,
                      kind=e.kind, p_improvement=e.p_improvement, h_improvement=e.h_improvement,
                      relative_margin=e.relative_margin) for e in arr[:n]]
+
+    def apply_log(self):
+        """(n, 8) array: node, kind (0 P / 1 H), degree, initial_err, new_err, p_imp, h_imp, total_after — the same
+        columns the CPU checker's apply log has."""
+        self._need()
+        n = lib().hpsdf_get_apply_log(self._h, None, 0)
+        arr = (ApplyLogEntry * max(n, 1))()
+        lib().hpsdf_get_apply_log(self._h, arr, n)
+        return np.array([[e.node_idx, e.kind, e.degree, e.initial_err, e.new_err, e.p_improvement, e.h_improvement,
+                          e.total_after] for e in arr[:n]], np.float64).reshape(n, 8)
 
     def _need(self):
         if not self._h:

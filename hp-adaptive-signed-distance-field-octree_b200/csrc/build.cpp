@@ -364,6 +364,7 @@ namespace hpsdf
                     queue_.push({ idx, j.pErr });                                                        // Octree.cpp:289-290
                     pending_.push_back(idx);
                     t_.stats.jobs_applied_p++;
+                    t_.applyLog.push_back({ idx, 0u, p, err, j.pErr, j.pImp, j.hImp, checkValue() });
                 }
                 else if (refineH)
                 {
@@ -385,6 +386,9 @@ namespace hpsdf
                         pending_.push_back(c);
                     }
                     t_.stats.jobs_applied_h++;
+                    double mx = 0.0;
+                    for (int i = 0; i < 8; ++i) mx = std::max(mx, j.hErr[i]);
+                    t_.applyLog.push_back({ idx, 1u, p, err, mx, j.pImp, j.hImp, checkValue() });
                 }
                 // else: degree and depth both at their maximum — the node leaves the queue (Octree.cpp:643-655)
 

@@ -208,7 +208,7 @@ extern "C"
         HPSDF_CUDA(cudaSetDevice(tree->device));
         hpsdf_octree* t = new hpsdf_octree();
         t->device = tree->device; t->ctx = tree->ctx; t->cfg = tree->cfg; t->map = tree->map;
-        t->nodes = tree->nodes; t->nCoeffs = tree->nCoeffs; t->stats = tree->stats; t->decisionLog = tree->decisionLog;
+        t->nodes = tree->nodes; t->nCoeffs = tree->nCoeffs; t->stats = tree->stats; t->decisionLog = tree->decisionLog; t->applyLog = tree->applyLog;
         cudaError_t e = cudaMalloc((void**)&t->dCoeffs, std::max<size_t>(t->nCoeffs, 1) * 8);
         if (e == cudaSuccess) e = cudaMemcpy(t->dCoeffs, tree->dCoeffs, t->nCoeffs * 8, cudaMemcpyDeviceToDevice);
         if (e != cudaSuccess) { delete t; return failCuda(e, "hpsdf_clone"); }
@@ -239,6 +239,14 @@ extern "C"
         if (!tree) return 0;
         const size_t n = tree->decisionLog.size();
         if (out) memcpy(out, tree->decisionLog.data(), std::min(n, capacity) * sizeof(hpsdf_decision_log_entry));
+        return n;
+    }
+
+    HPSDF_API size_t hpsdf_get_apply_log(const hpsdf_octree* tree, hpsdf_apply_log_entry* out, size_t capacity)
+    {
+        if (!tree) return 0;
+        const size_t n = tree->applyLog.size();
+        if (out) memcpy(out, tree->applyLog.data(), std::min(n, capacity) * sizeof(hpsdf_apply_log_entry));
         return n;
     }
 

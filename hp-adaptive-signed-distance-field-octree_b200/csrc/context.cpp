@@ -71,6 +71,9 @@ namespace hpsdf
             rOff[d] = host.size();
             for (int k = 0; k < n; ++k) host.push_back(r[k]);
         }
+        const size_t glOff = host.size();
+        for (int i = 0; i < 2080; ++i) host.push_back(glRoots(1)[i]);
+        for (int i = 0; i < 2080; ++i) host.push_back(glWeights(1)[i]);
         const size_t bidxOff = host.size();
         std::vector<uint32_t> bidx(kMaxCoeffs + 1, 0);
         for (int i = 0; i < kMaxCoeffs; ++i)
@@ -91,6 +94,7 @@ namespace hpsdf
             ctx->fitTab.roots[d] = d ? base + rOff[d] : nullptr;
         }
         ctx->fitTab.bidx = (const uint32_t*)(base + bidxOff);
+        ctx->glRoots = base + glOff; ctx->glWeights = base + glOff + 2080;
         setBidxDev(device, ctx->fitTab.bidx);
         cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
         uploadConstants();

@@ -1,12 +1,139 @@
-// continuity.cpp — PerformContinuityPostProcess (Source/HP/Octree.cpp:1717-1762) on the device. Placeholder until the
-// face-pair assembly and CG kernels land (task 5).
+// continuity.cpp — PerformContinuityPostProcess (Source/HP/Octree.cpp:1717-1762): host orchestration.
+//
+//   RunContinuityThreadPool :1663-1714   face enumeration (NodeProc :1549-1571, FaceProc :1574-1612) on the host —
+//                                        O(leaves) pointer chasing, microseconds; the reference reruns NodeProc from
+//                                        every node and dedupes with a std::map, a walk from the root visits each shared
+//                                        face exactly once;
+//   TickContinuityThread :1615-1660      one CTA per face on the device (continuity_kernels.cuh);
+//   setFromTriplets + lambda :1724-1735  COO -> sorted, duplicate-summed CSR on the device;
+//   ConjugateGradient :1751-1756         persistent cooperative CG kernel, x0 = b = lambda * c.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
 #include "octree.h"
 
 namespace hpsdf
 {
-    hpsdf_status continuityPostProcess(hpsdf_octree&, const hpsdf_build_opts&, cudaStream_t)
+    namespace
     {
-        setLastError("continuity post-process is not available in this build");
-        return HPSDF_ERR_UNSUPPORTED;
+        struct FaceEnumerator
+        {
+            const std::vector<HostNode>& nodes;
+            std::vector<FaceJobDev>&     out;
+
+            // FaceProc (Octree.cpp:1574-1612)
+            void faceProc(uint64_t a, uint64_t b, uint8_t dim)
+            {
+                const bool ac = nodes[a].child != kNoChild, bc = nodes[b].child != kNoChild;
+                if (ac || bc)
+                {
+                    for (int i = 0; i < 4; ++i)
+                        faceProc(ac ? nodes[a].child + tables().face[dim][i][1] : a,
+                                 bc ? nodes[b].child + tables().face[dim][i][0] : b, dim);
+                    return;
+                }
+                const bool aLow = nodes[a].mn[dim] < nodes[b].mn[dim];                       // Octree.cpp:1593-1594
+                const HostNode& A = nodes[aLow ? a : b];
+                const HostNode& B = nodes[aLow ? b : a];
+                FaceJobDev f;
+                memset(&f, 0, sizeof(f));
+                f.cstartA = (uint32_t)A.cstart; f.cstartB = (uint32_t)B.cstart;
+                f.degA = A.degree; f.degB = B.degree; f.depthA = A.depth; f.depthB = B.depth; f.dim = dim;
+                f.analytic = A.depth == B.depth;                                            // Octree.cpp:1651
+                if (!f.analytic)
+                {
+                    const int t1 = (dim + 1) % 3, t2 = (dim + 2) % 3;
+                    // shared face = A.aabb clamped to B.aabb; scale = sizes * 0.5 (Octree.cpp:1265-1266)
+                    double fs[3];
+                    for (int i = 0; i < 3; ++i)
+                    {
+                        const float lo = std::max(A.mn[i], B.mn[i]), hi = std::min(A.mx[i], B.mx[i]);
+                        fs[i] = (double)(hi - lo) * 0.5;
+                    }
+                    f.faceScale = fs[t1] * fs[t2];
+                    const uint32_t depthDiff = A.depth > B.depth ? (uint32_t)(A.depth - B.depth) : (uint32_t)(B.depth - A.depth);
+                    f.invDist = 1.0 / std::pow(2.0, (double)depthDiff);                       // Octree.cpp:1275-1276
+                    const HostNode& fine = A.depth > B.depth ? A : B;                        // translation of the finer cell's centre
+                    const HostNode& coarse = A.depth > B.depth ? B : A;                      // in units of the finer cell's half size
+                    auto centre = [](const HostNode& n, int k) { return (n.mn[k] + n.mx[k]) / 2.0f; };
+                    f.invTr1 = (double)(centre(fine, t1) - centre(coarse, t1)) / ((double)(fine.mx[t1] - fine.mn[t1]) * 0.5);   // :1280-1289
+                    f.invTr2 = (double)(centre(fine, t2) - centre(coarse, t2)) / ((double)(fine.mx[t2] - fine.mn[t2]) * 0.5);
+                    f.invTr1 *= f.invDist; f.invTr2 *= f.invDist;                              // Octree.cpp:1290
+                }
+                out.push_back(f);
+            }
+
+            // NodeProc (Octree.cpp:1549-1571)
+            void nodeProc(uint64_t idx)
+            {
+                const HostNode& n = nodes[idx];
+                if (n.child == kNoChild) return;
+                for (int i = 0; i < 8; ++i) nodeProc(n.child + i);
+                for (uint8_t d = 0; d < 3; ++d)
+                    for (int j = 0; j < 4; ++j) faceProc(n.child + tables().face[d][j][0], n.child + tables().face[d][j][1], d);
+            }
+        };
+
+        // number of (i, j) with equal tangential indices, i < N_degR, j < N_degC (entries an analytic block emits)
+        uint32_t matchCount(int degR, int degC, int dim)
+        {
+            static uint32_t memo[3][kMaxDegree + 1][kMaxDegree + 1];
+            static bool     have[3][kMaxDegree + 1][kMaxDegree + 1] = {};
+            if (have[dim][degR][degC]) return memo[dim][degR][degC];
+            const int t1 = (dim + 1) % 3, t2 = (dim + 2) % 3;
+            uint32_t c = 0;
+            for (int i = 0; i < coeffCount(degR); ++i)
+                for (int j = 0; j < coeffCount(degC); ++j)
+                    c += tables().bidx[i][t1] == tables().bidx[j][t1] && tables().bidx[i][t2] == tables().bidx[j][t2];
+            memo[dim][degR][degC] = c; have[dim][degR][degC] = true;
+            return c;
+        }
+    }
+
+    hpsdf_status continuityPostProcess(hpsdf_octree& t, const hpsdf_build_opts& o, cudaStream_t stream)
+    {
+        const uint32_t n = (uint32_t)t.nCoeffs;
+        if (!n) return HPSDF_OK;
+        if (t.nCoeffs >= 0xFFFFFFFFull) { setLastError("continuity: more than 2^32 unknowns"); return HPSDF_ERR_UNSUPPORTED; }
+        std::vector<FaceJobDev> faces;
+        FaceEnumerator en{ t.nodes, faces };
+        en.nodeProc(0);
+
+        // COO layout: [0, n) the lambda diagonal, then each face's entries
+        uint64_t cur = n;
+        for (FaceJobDev& f : faces)
+        {
+            f.cooOffset = cur;
+            const uint64_t nA = coeffCount(f.degA), nB = coeffCount(f.degB);
+            if (f.analytic) cur += matchCount(f.degA, f.degA, f.dim) + 2ull * matchCount(f.degA, f.degB, f.dim) + matchCount(f.degB, f.degB, f.dim);
+            else            cur += nA * nA + 2 * nA * nB + nB * nB;
+        }
+        if (cur >= 0x7FFFFFFFull) { setLastError("continuity: COO exceeds 2^31 entries"); return HPSDF_ERR_UNSUPPORTED; }
+
+        FaceJobDev* dFaces = nullptr; uint64_t* keys = nullptr; double* vals = nullptr; double* b = nullptr;
+        CsrDev csr;
+        double result[2] = { 0.0, 0.0 };
+        cudaError_t e = cudaMalloc((void**)&dFaces, std::max<size_t>(faces.size(), 1) * sizeof(FaceJobDev));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&keys, cur * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&vals, cur * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&b, (size_t)n * 8);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dFaces, faces.data(), faces.size() * sizeof(FaceJobDev), cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = launchDiagEmit(keys, vals, n, t.cfg.continuity_strength, stream);
+        if (e == cudaSuccess) e = launchFaceEmit(dFaces, (uint32_t)faces.size(), *t.ctx, keys, vals, stream);
+        if (e == cudaSuccess) e = cooToCsr(keys, vals, cur, n, csr, stream);
+        // b = lambda * c, x0 = b (Octree.cpp:1738-1741, 1755: the scaled vector is also the initial guess)
+        if (e == cudaSuccess) e = launchScale(t.dCoeffs, b, n, t.cfg.continuity_strength, stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(t.dCoeffs, b, (size_t)n * 8, cudaMemcpyDeviceToDevice, stream);
+        const double tol = o.cg_tolerance > 0.0 ? o.cg_tolerance : (double)0.000001f;        // setTolerance(EPSILON_F32), :1754
+        const uint32_t maxIt = o.cg_max_iterations ? o.cg_max_iterations : 2u * n;            // Eigen's default: 2n
+        if (e == cudaSuccess) e = launchCg(csr, b, t.dCoeffs, tol, maxIt, t.ctx->smCount, result, stream);   // coeffStore <- x (:1756)
+        t.stats.kernel_launches += 6 + 4;      // diag, faces, sort (~4 CUB kernels), reduce, rowptr, scale, cg
+        t.stats.cg_iterations = (uint64_t)result[0];
+        t.stats.cg_relative_residual = result[1];
+        cudaFree(dFaces); cudaFree(keys); cudaFree(vals); cudaFree(b);
+        cudaFree(csr.rowPtr); cudaFree(csr.col); cudaFree(csr.val);
+        if (e != cudaSuccess) return failCuda(e, "continuityPostProcess");
+        return HPSDF_OK;
     }
 }

@@ -17,10 +17,29 @@ namespace hpsdf
 
     struct DeviceCtx
     {
-        int          device = -1;
-        FitTablesDev fitTab{};
-        void*        tabMem = nullptr;
-        int          smCount = 0;
+        int           device = -1;
+        FitTablesDev  fitTab{};
+        void*         tabMem = nullptr;
+        int           smCount = 0;
+        const double* glRoots = nullptr;      // all 64 rules, rule n at n(n-1)/2, ascending nodes
+        const double* glWeights = nullptr;
+    };
+
+    // One leaf-leaf shared face (ContinuityThreadPool::Input, ContinuityThreadPool.h:24-28) with everything
+    // EvaluateSharedFaceIntegral{Analytically,Numerically} derives from the two nodes precomputed on the host.
+    struct FaceJobDev
+    {
+        uint64_t cooOffset;                   // where this face's entries start in the COO arrays
+        uint32_t cstartA, cstartB;            // coeffsStart of the low-side (A) and high-side (B) leaf
+        uint8_t  degA, degB, depthA, depthB, dim, analytic, pad0, pad1;
+        double   faceScale;                   // sharedFaceScale(t1) * sharedFaceScale(t2)   (Octree.cpp:1265-1267, 1333)
+        double   invDist, invTr1, invTr2;     // 2^-depthDiff and the tangential translations (Octree.cpp:1275-1290)
+    };
+
+    struct CsrDev
+    {
+        uint32_t* rowPtr = nullptr; uint32_t* col = nullptr; double* val = nullptr;
+        uint32_t  n = 0, nnz = 0;
     };
 
     // Lazily creates the context of `device` (uploads tables and constant memory). nullptr + err on failure.
@@ -34,6 +53,15 @@ namespace hpsdf
     cudaError_t launchDfmaPeak(double* dOut, int blocks, cudaStream_t stream);
     cudaError_t launchQuery(const DeviceTreeView& view, const double* dXyz, size_t n, double* dOut, int smCount, cudaStream_t stream);
     cudaError_t launchQueryGradient(const DeviceTreeView& view, const double* dXyz, size_t n, double* dOut, double* dGrad, cudaStream_t stream);
+    // continuity (continuity_kernels.cuh)
+    cudaError_t launchFaceEmit(const FaceJobDev* dFaces, uint32_t nFaces, const DeviceCtx& ctx, uint64_t* keys, double* vals, cudaStream_t stream);
+    cudaError_t launchDiagEmit(uint64_t* keys, double* vals, uint32_t n, double lambda, cudaStream_t stream);
+    // sort COO by (row, col), sum duplicates, build CSR (allocates csr.*; the caller frees them)
+    cudaError_t cooToCsr(uint64_t* keys, double* vals, size_t nCoo, uint32_t n, CsrDev& csr, cudaStream_t stream);
+    // (A) x = b by preconditioned CG from the guess in x; result[0] = iterations, result[1] = relative residual
+    cudaError_t launchCg(const CsrDev& csr, const double* b, double* x, double tol, uint32_t maxIt, int smCount,
+                         double* hostResult, cudaStream_t stream);
+    cudaError_t launchScale(const double* in, double* out, uint32_t n, double s, cudaStream_t stream);
     // dst[dstOff[s] + i] = src[srcOff[s] + i], i < count[s], for nSeg segments (ReallocCoeffs, Octree.cpp:474-555, on device)
     cudaError_t launchGatherSegments(const double* src, double* dst, const uint32_t* srcOff, const uint32_t* dstOff,
                                      const uint32_t* count, uint32_t nSeg, cudaStream_t stream);

@@ -15,6 +15,7 @@ namespace hpsdf
 #include "sdf_eval.cuh"
 #include "fit_kernels.cuh"
 #include "query_kernels.cuh"
+#include "continuity_kernels.cuh"
 
 namespace hpsdf
 {
@@ -22,6 +23,20 @@ namespace hpsdf
     {
         cudaMemcpyToSymbol(c_nl, tables().nl, sizeof(c_nl));
         cudaMemcpyToSymbol(c_rec, tables().rec, sizeof(c_rec));
+        // LpX(a, +-1) with the reference's recurrence (Octree.cpp:988-1004); the host code is built with -ffp-contract=off
+        double lp1[kMaxDegree + 1], lm1[kMaxDegree + 1];
+        for (int a = 0; a <= kMaxDegree; ++a)
+        {
+            for (int sgn = 0; sgn < 2; ++sgn)
+            {
+                const double x = sgn ? -1.0 : 1.0;
+                double m2 = 0.0, m1 = 1.0, l = 1.0;
+                for (int i = 1; i <= a; ++i) { l = tables().rec[i][0] * x * m1 - tables().rec[i][1] * m2; m2 = m1; m1 = l; }
+                (sgn ? lm1 : lp1)[a] = l;
+            }
+        }
+        cudaMemcpyToSymbol(c_lp1, lp1, sizeof(lp1));
+        cudaMemcpyToSymbol(c_lm1, lm1, sizeof(lm1));
     }
 
     cudaError_t launchQuery(const DeviceTreeView& view, const double* dXyz, size_t n, double* dOut, int smCount, cudaStream_t stream)
@@ -54,5 +69,89 @@ namespace hpsdf
         const unsigned blocks = (unsigned)(((size_t)nSeg * 32 + 255) / 256);
         gatherSegmentsKernel<<<blocks, 256, 0, stream>>>(src, dst, srcOff, dstOff, count, nSeg);
         return cudaGetLastError();
+    }
+
+    cudaError_t launchFaceEmit(const FaceJobDev* dFaces, uint32_t nFaces, const DeviceCtx& ctx, uint64_t* keys, double* vals, cudaStream_t stream)
+    {
+        if (!nFaces) return cudaSuccess;
+        faceEmitKernel<<<nFaces, kFaceThreads, 0, stream>>>(dFaces, nFaces, ctx.fitTab.bidx, ctx.glRoots, ctx.glWeights, keys, vals);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchDiagEmit(uint64_t* keys, double* vals, uint32_t n, double lambda, cudaStream_t stream)
+    {
+        if (!n) return cudaSuccess;
+        diagEmitKernel<<<(n + 255) / 256, 256, 0, stream>>>(keys, vals, n, lambda);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchScale(const double* in, double* out, uint32_t n, double s, cudaStream_t stream)
+    {
+        if (!n) return cudaSuccess;
+        scaleKernel<<<(n + 255) / 256, 256, 0, stream>>>(in, out, n, s);
+        return cudaGetLastError();
+    }
+
+    cudaError_t cooToCsr(uint64_t* keys, double* vals, size_t nCoo, uint32_t n, CsrDev& csr, cudaStream_t stream)
+    {
+        uint64_t* keysAlt = nullptr; double* valsAlt = nullptr; uint64_t* uniq = nullptr; uint32_t* dNum = nullptr; void* tmp = nullptr;
+        cudaError_t e = cudaMalloc((void**)&keysAlt, nCoo * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&valsAlt, nCoo * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&uniq, nCoo * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&dNum, 4);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&csr.val, nCoo * 8);
+        size_t tmpSort = 0, tmpRed = 0;
+        cub::DoubleBuffer<uint64_t> kb(keys, keysAlt);
+        cub::DoubleBuffer<double>   vb(vals, valsAlt);
+        // keys are (row << 32 | col) with row, col < n: only the significant bits need sorting; radix sort is stable, so
+        // duplicates keep their emission order and are summed in that order
+        int bits = 1; while (bits < 32 && (1ull << bits) < (uint64_t)n) ++bits;
+        if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmpSort, kb, vb, (int)nCoo, 0, 32 + bits, stream);
+        if (e == cudaSuccess) e = cub::DeviceReduce::ReduceByKey(nullptr, tmpRed, keys, uniq, vals, csr.val, dNum, cub::Sum(), (int)nCoo, stream);
+        if (e == cudaSuccess) e = cudaMalloc(&tmp, tmpSort > tmpRed ? tmpSort : tmpRed);
+        if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmpSort, kb, vb, (int)nCoo, 0, 32 + bits, stream);
+        if (e == cudaSuccess) e = cub::DeviceReduce::ReduceByKey(tmp, tmpRed, kb.Current(), uniq, vb.Current(), csr.val, dNum, cub::Sum(), (int)nCoo, stream);
+        uint32_t nnz = 0;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&nnz, dNum, 4, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&csr.rowPtr, ((size_t)n + 1) * 4);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&csr.col, (size_t)(nnz ? nnz : 1) * 4);
+        if (e == cudaSuccess)
+        {
+            rowPtrKernel<<<(nnz + 1 + 255) / 256, 256, 0, stream>>>(uniq, nnz, n, csr.rowPtr, csr.col);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        csr.n = n; csr.nnz = nnz;
+        cudaFree(keysAlt); cudaFree(valsAlt); cudaFree(uniq); cudaFree(dNum); cudaFree(tmp);
+        return e;
+    }
+
+    cudaError_t launchCg(const CsrDev& csr, const double* b, double* x, double tol, uint32_t maxIt, int smCount,
+                         double* hostResult, cudaStream_t stream)
+    {
+        int perSm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, cgKernel, kCgThreads, 0);
+        if (e != cudaSuccess) return e;
+        if (perSm < 1) return cudaErrorLaunchOutOfResources;
+        // enough blocks for 4 lanes per row, at most 2 resident blocks per SM (grid syncs get dearer with more blocks)
+        int grid = (int)(((size_t)csr.n * kCgLanesPerRow + kCgThreads - 1) / kCgThreads);
+        const int cap = smCount * (perSm < 2 ? perSm : 2);
+        if (grid > cap) grid = cap;
+        if (grid < 1) grid = 1;
+        double* scratch = nullptr;      // r, p, ap, invDiag (4n) + partial (3 grid) + result (2)
+        const size_t nd = 4 * (size_t)csr.n + 3 * (size_t)grid + 2;
+        e = cudaMalloc((void**)&scratch, nd * 8);
+        if (e != cudaSuccess) return e;
+        CgParams P;
+        P.rowPtr = csr.rowPtr; P.col = csr.col; P.val = csr.val; P.n = csr.n; P.maxIt = maxIt; P.tol = tol; P.b = b; P.x = x;
+        P.r = scratch; P.p = scratch + csr.n; P.ap = scratch + 2 * (size_t)csr.n; P.invDiag = scratch + 3 * (size_t)csr.n;
+        P.partial = scratch + 4 * (size_t)csr.n; P.result = P.partial + 3 * (size_t)grid;
+        void* args[] = { (void*)&P };
+        e = cudaLaunchCooperativeKernel((void*)cgKernel, dim3(grid), dim3(kCgThreads), args, 0, stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hostResult, P.result, 16, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        cudaFree(scratch);
+        return e;
     }
 }

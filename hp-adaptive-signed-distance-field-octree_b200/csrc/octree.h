@@ -53,6 +53,7 @@ struct hpsdf_octree
 
     hpsdf_build_stats   stats{};
     std::vector<hpsdf_decision_log_entry> decisionLog;
+    std::vector<hpsdf_apply_log_entry>    applyLog;
 
     // scratch of the host-pointer Query path
     std::mutex          queryMutex;

@@ -246,6 +246,20 @@ typedef struct hpsdf_decision_log_entry
 
 HPSDF_API size_t hpsdf_get_decision_log(const hpsdf_octree* tree, hpsdf_decision_log_entry* out, size_t capacity);
 
+/* Every refinement applied by the last Create, in order (what enableLogging printf()s one line for, Octree.cpp:292-296):
+ * lets a caller diff two builds job by job. */
+typedef struct hpsdf_apply_log_entry
+{
+    uint64_t node_idx;
+    uint32_t kind;                /* 0 = P (degree + 1), 1 = H (split into 8) */
+    uint32_t degree;              /* degree before the job */
+    double   initial_err, new_err;/* new_err: P: the new error; H: the largest child error */
+    double   p_improvement, h_improvement;
+    double   total_after;         /* totalCoeffError after applying it */
+} hpsdf_apply_log_entry;
+
+HPSDF_API size_t hpsdf_get_apply_log(const hpsdf_octree* tree, hpsdf_apply_log_entry* out, size_t capacity);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Kernel-level entry points (benchmarks / parity of single stages)                             */
 /* ------------------------------------------------------------------------------------------ */

@@ -54,7 +54,9 @@ def test_single_fits_match_reference_golden(hp):
         cfg, prog = product_cfg(hp, names[case])
         coeffs, err, _ = hp.fit_batch(cfg, prog, g["fit%03d_cell" % k][None, :], [depth], degree)
         worst = max(worst, rel_inf(coeffs[0], g["fit%03d_coeffs" % k]))
-        assert abs(err[0] - float(g["fit%03d_err" % k])) <= 1e-9 * float(g["fit%03d_err" % k]) + 1e-300
+        # the raw error is a sum of squares: where the SDF is exactly polynomial in the cell it is rounding noise
+        floor = (1e-12 * np.abs(g["fit%03d_coeffs" % k]).max()) ** 2
+        assert abs(err[0] - float(g["fit%03d_err" % k])) <= 1e-9 * float(g["fit%03d_err" % k]) + floor
     assert worst <= COEFF_TOL, worst
 
 
@@ -75,7 +77,7 @@ def test_fit_batch_matches_oracle_all_degrees(hp, oracle, degree):
     for i in range(n):
         c, e = oracle.oracle_fit(ocfg, oprog, centres[i] - half, centres[i] + half, degree, depth)
         assert rel_inf(coeffs[i], c) <= COEFF_TOL
-        assert abs(err[i] - e) <= 1e-9 * e + 1e-300
+        assert abs(err[i] - e) <= 1e-9 * e + (1e-12 * np.abs(c).max()) ** 2
 
 
 @pytest.mark.parametrize("name", ["sphere_poly_1e8", "custom_domain", "csg_small"])
@@ -102,14 +104,21 @@ def test_create_matches_oracle_full_tree(hp, oracle, built, name):
     t = built(name)
     a, b = hp.parse_block(t.ToMemoryBlockBytes()), hpref.parse_block(o.block())
     assert a["n_nodes"] == b["n_nodes"] and a["n_coeffs"] == b["n_coeffs"], (t.stats(), t.decision_log()[-3:])
-    for f in ("child", "mn", "mx", "deg", "depth"):
-        assert np.array_equal(a["nodes"][f], b["nodes"][f]), f
-    leaf = a["nodes"]["child"] == np.uint64(0xFFFFFFFFFFFFFFFF)
-    assert np.array_equal(a["nodes"]["cstart"][leaf], b["nodes"]["cstart"][leaf])
-    _, _, deg, ca = leaf_table(a, hp.COEFF_COUNT)
-    _, _, _, cb = leaf_table(b, hp.COEFF_COUNT)
+    # canonical comparison (DFS by child slot): node NUMBERING may differ where two cells have errors equal to the last
+    # bits (mirror-symmetric cells) and pop in the other order — same tree, children allocated in another order
+    pa, da, ga, ca = leaf_table(a, hp.COEFF_COUNT)
+    pb, db, gb, cb = leaf_table(b, hp.COEFF_COUNT)
+    assert pa == pb, "leaf paths differ (topology)"
+    assert np.array_equal(da, db) and np.array_equal(ga, gb), "leaf depth/degree differ (topology)"
     worst = max(rel_inf(x, y) for x, y in zip(ca, cb))
     assert worst <= COEFF_TOL, worst
+    same_numbering = all(np.array_equal(a["nodes"][f], b["nodes"][f]) for f in ("child", "deg", "depth"))
+    la, lb = t.apply_log(), o.apply_log()
+    assert la.shape == lb.shape
+    # the same multiset of jobs was applied, with errors equal to rounding
+    assert np.array_equal(np.sort(la[:, 1]), np.sort(lb[:, 1]))
+    assert np.abs(np.sort(la[:, 4]) - np.sort(lb[:, 4])).max() <= 1e-9 * np.abs(lb[:, 4]).max()
+    leaf = a["nodes"]["child"] == np.uint64(0xFFFFFFFFFFFFFFFF)
     pts = root_points(CASES[name]["cfg"], 100000, seed=5, margin=0.01)
     qa, qb = t.Query(pts), o.query(pts, 8)
     assert np.array_equal(qa == hp.DBL_MAX, qb == hp.DBL_MAX)
@@ -117,7 +126,26 @@ def test_create_matches_oracle_full_tree(hp, oracle, built, name):
     so, st = o.stats(), t.stats()
     assert st["jobs_applied_p"] == so["applied_p"] and st["jobs_applied_h"] == so["applied_h"]
     assert st["n_leaves"] == int(leaf.sum())
-    print(name, "worst", worst, {k: st[k] for k in ("rounds", "fits_evaluated", "jobs_evaluated", "total_ms", "fit_kernel_ms", "host_replay_ms", "near_tie_decisions", "cut_margin")})
+    print(name, "worst", worst, "same node numbering:", same_numbering, {k: st[k] for k in ("rounds", "fits_evaluated", "jobs_evaluated", "total_ms", "fit_kernel_ms", "host_replay_ms", "near_tie_decisions", "cut_margin")})
+
+
+@pytest.mark.parametrize("name", ["c1_readme", "sphere_cont_1e8"])
+def test_continuity_matches_reference_golden(hp, built, name):
+    """PerformContinuityPostProcess: the converged solution of (M + lambda I) x = lambda c (CG to 1e-13) against the
+    reference's, plus the gap of a reference-tolerance (1e-6) solve."""
+    t = built(name, cg_tolerance=1e-13)
+    g = golden(name)
+    blk = hp.parse_block(t.ToMemoryBlockBytes())
+    worst = check_tree_against_golden(blk, g, hp.COEFF_COUNT, COEFF_TOL)
+    assert np.abs(t.Query(g["query_pts"]) - g["query_vals"]).max() <= QUERY_TOL
+    st = t.stats()
+    assert st["cg_relative_residual"] <= 1e-13 and st["cg_iterations"] > 0
+    t6 = built(name)                                                     # default tolerance = the reference's 1e-6f
+    b6 = hp.parse_block(t6.ToMemoryBlockBytes())
+    gap = np.abs(b6["coeffs"] - blk["coeffs"]).max()
+    assert gap <= 1e-6 * np.abs(blk["coeffs"]).max() * 10
+    print(name, "worst", worst, "cg its", st["cg_iterations"], "res", st["cg_relative_residual"], "ms", st["continuity_ms"],
+          "tol-1e-6 gap", gap, "its", t6.stats()["cg_iterations"])
 
 
 def test_build_option_switches_match_oracle(hp, oracle):
@@ -130,8 +158,10 @@ def test_build_option_switches_match_oracle(hp, oracle):
         t.Create(cfg, prog, hp.BuildOpts(**kw))
         a, b = hp.parse_block(t.ToMemoryBlockBytes()), hpref.parse_block(o.block())
         assert a["n_nodes"] == b["n_nodes"] and a["n_coeffs"] == b["n_coeffs"], kw
-        assert np.array_equal(a["nodes"]["deg"], b["nodes"]["deg"]), kw
-        assert np.abs(a["coeffs"] - b["coeffs"]).max() <= COEFF_TOL * np.abs(b["coeffs"]).max()
+        _, da, ga, ca = leaf_table(a, hp.COEFF_COUNT)
+        _, db, gb, cb = leaf_table(b, hp.COEFF_COUNT)
+        assert np.array_equal(da, db) and np.array_equal(ga, gb), kw
+        assert max(rel_inf(x, y) for x, y in zip(ca, cb)) <= COEFF_TOL
 
 
 def test_memory_block_is_accepted_by_the_cpu_side_and_back(hp, oracle, built):
