@@ -132,6 +132,7 @@ namespace hpsdf
             hpsdf_status evaluateRound();
             bool         replay();                  // true = terminated
             hpsdf_status pack();
+            void         logCutTies();
             double       checkValue() const
             {
                 return o_.total_mode == HPSDF_TOTAL_EXACT_SUM
@@ -405,6 +406,42 @@ namespace hpsdf
             }
         }
 
+        // Near-threshold divergence log (BASELINE north_star): the greedy loop stops in the middle of a run of leaves whose
+        // errors are equal to rounding (mirror-symmetric cells have errors equal to the last bits). WHICH of them were
+        // refined before the cut depends on the last bits, so another implementation of the same algorithm may refine
+        // other members of the group. Log the whole group: kind 2 = refined before the cut, kind 3 = left unrefined.
+        void Builder::logCutTies()
+        {
+            if (t_.applyLog.empty() || queue_.empty()) return;
+            const double eLast = t_.applyLog.back().initial_err;
+            if (!(eLast > 0.0) || std::abs(eLast - kInitialErr) < 1e-9) return;
+            const double band = 1e-9 * eLast;
+            auto entry = [&](uint64_t idx, uint32_t degree, uint32_t kind, double err)
+            {
+                hpsdf_decision_log_entry e{};
+                e.node_idx = idx; e.depth = nodes_[idx].depth; e.degree = degree; e.kind = kind; e.chose_p = 0;
+                for (int a = 0; a < 3; ++a) e.centre[a] = (nodes_[idx].mn[a] + nodes_[idx].mx[a]) / 2.0f;
+                e.relative_margin = std::fabs(err - eLast) / eLast;
+                t_.decisionLog.push_back(e);
+            };
+            size_t refined = 0, unrefined = 0;
+            for (size_t k = t_.applyLog.size(); k-- > 0;)
+            {
+                const hpsdf_apply_log_entry& a = t_.applyLog[k];
+                if (std::fabs(a.initial_err - eLast) > band) break;
+                entry(a.node_idx, a.degree, 2u, a.initial_err);
+                t_.decisionLog.back().chose_p = a.kind == 0;
+                ++refined;
+            }
+            for (uint64_t idx = 0; idx < nodes_.size(); ++idx)
+                if (nodes_[idx].child == kNoChild && std::fabs(errOf_[idx] - eLast) <= band) { entry(idx, nodes_[idx].degree, 3u, errOf_[idx]); ++unrefined; }
+            if (unrefined == 0)
+            {
+                // nothing was left behind: the cut does not fall inside a tie group, drop the kind-2 entries again
+                t_.decisionLog.resize(t_.decisionLog.size() - refined);
+            }
+        }
+
         // ReallocCoeffs (Octree.cpp:474-555): DFS from the root's children by child slot; leaves packed in visiting order.
         hpsdf_status Builder::pack()
         {
@@ -487,6 +524,7 @@ namespace hpsdf
                     lastApplied_.relative_margin = std::min(std::fabs(totalBeforeLast_ - thr), std::fabs(thr - checkValue())) / thr;
                     t_.decisionLog.push_back(lastApplied_);
                 }
+                logCutTies();
                 t_.stats.host_replay_ms = replayMs;
                 if (cfg_.continuity_enforce)
                 {

@@ -239,7 +239,8 @@ typedef struct hpsdf_decision_log_entry
     uint32_t depth, degree;
     float    centre[3];           /* cell centre in the internal unit cube */
     uint32_t chose_p;             /* 1 = p-refinement, 0 = h-refinement */
-    uint32_t kind;                /* 0 = h/p near-tie, 1 = last job applied before the termination cut */
+    uint32_t kind;                /* 0 = h/p near-tie, 1 = last job applied before the termination cut,
+                                     2 / 3 = member of the group of equal-error leaves the cut falls into: refined / left unrefined */
     double   p_improvement, h_improvement;
     double   relative_margin;
 } hpsdf_decision_log_entry;

@@ -58,3 +58,38 @@ def leaf_table(block_dict, ncount):
             for i in range(7, -1, -1):
                 stack.append((c + i, path + (i,)))
     return paths, np.array(depths), np.array(degs), cs
+
+
+def path_code(path):
+    """Child-slot path -> integer (3 bits per level, level 1 in the lowest bits)."""
+    code = 0
+    for level, c in enumerate(path):
+        code |= int(c) << (3 * level)
+    return code
+
+
+def cell_of(code, depth):
+    """(depth, centre) of the cell a path code names, in the internal unit cube [-0.5, 0.5]^3."""
+    c = np.zeros(3)
+    for level in range(depth):
+        child = (code >> (3 * level)) & 7
+        q = 0.5 ** (level + 2)
+        c += np.array([q if child & 1 else -q, q if child & 2 else -q, q if child & 4 else -q])
+    return depth, tuple(float(x) for x in c)
+
+
+def divergent_cells(leaves_a, leaves_b):
+    """leaves_*: dict (code, depth) -> degree. Returns the set of (code, depth) cells on which the two trees differ:
+    a leaf with another degree, or a leaf in one tree that is split in the other (reported as the coarser cell)."""
+    out = set()
+    for (la, lb) in ((leaves_a, leaves_b), (leaves_b, leaves_a)):
+        for (code, depth), deg in la.items():
+            if (code, depth) in lb:
+                if lb[(code, depth)] != deg:
+                    out.add((code, depth))
+                continue
+            # not a leaf in the other tree: either an ancestor is a leaf there, or this cell is split there
+            anc = [(code & ((1 << (3 * d)) - 1), d) for d in range(depth)]
+            hit = [a for a in anc if a in lb]
+            out.add(hit[0] if hit else (code, depth))
+    return out

@@ -7,7 +7,7 @@ The fixtures travel to the GPU box, where /root/reference does not exist.
 
 Contents per case (deterministic driver: strict greedy, exact-mean nearness, reference totalCoeffError bookkeeping,
 CG converged to 1e-13 where continuity is on):
-  leaf_depth, leaf_degree   leaves in DFS order by child slot (canonical topology)
+  leaf_depth, leaf_degree, leaf_code   leaves in DFS order by child slot (canonical topology; code = child slots, 3 bits/level)
   leaf_c0, leaf_norm        coeffs[0] and the 2-norm of each leaf's coefficients
   sample_leaves, sample_coeffs   full coefficients of 48 seeded leaves (concatenated)
   query_pts, query_vals     2000 seeded points in (a slightly enlarged) root and the reference's Query values
@@ -23,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 from oracle import hpref            # noqa: E402
-from cases import CASES, root_points, leaf_table  # noqa: E402
+from cases import CASES, root_points, leaf_table, path_code  # noqa: E402
 
 TREE_CASES = ["c1_readme", "sphere_poly_1e8", "sphere_cont_1e8", "custom_domain", "csg_small"]
 
@@ -41,6 +41,7 @@ def tree_golden(name):
     st = t.stats()
     np.savez_compressed(os.path.join(HERE, name + ".npz"),
                         leaf_depth=depth.astype(np.uint8), leaf_degree=deg.astype(np.uint8),
+                        leaf_code=np.array([path_code(p) for p in paths], np.uint64),
                         leaf_c0=np.array([x[0] for x in cs]), leaf_norm=np.array([np.linalg.norm(x) for x in cs]),
                         sample_leaves=sample, sample_coeffs=np.concatenate([cs[i] for i in sample]),
                         query_pts=pts, query_vals=t.query(pts),

@@ -52,7 +52,8 @@ def test_tree_matches_reference_golden(oracle, name):
     g = golden(name)
     blk = hpref.parse_block(t.block())
     tol = 1e-10 if CASES[name]["cfg"].get("continuity", True) else 1e-13     # CG iterate is not pinned, its limit is
-    check_tree_against_golden(blk, g, oracle.NCOUNT, tol)
+    worst, ndiv = check_tree_against_golden(blk, g, oracle.NCOUNT, tol)
+    assert ndiv == 0          # the restatement is bit-identical to the reference: no tie can resolve differently
     st = t.stats()
     assert st["applied_p"] == float(g["applied_p"]) and st["applied_h"] == float(g["applied_h"])
     assert abs(st["final_total"] - float(g["final_total"])) <= 1e-12 * abs(float(g["final_total"]))
