@@ -292,7 +292,8 @@ def main():
             fb = hp.bench_frontier(cfg, prog, 5, p, repeats=3, device=local, stream=stream)
             frontier["p%d" % p] = {"ms": fb["ms_per_launch"], "jobs": fb["jobs"], "fits_per_s": fb["fits"] / (fb["ms_per_launch"] * 1e-3),
                                    "sdf_evals_per_s": fb["sdf_evals"] / (fb["ms_per_launch"] * 1e-3),
-                                   "contraction_tflops": fb["algorithmic_flops"] / (fb["ms_per_launch"] * 1e-3) / 1e12}
+                                   "algorithmic_tflops": fb["algorithmic_flops"] / (fb["ms_per_launch"] * 1e-3) / 1e12,
+                                   "frac_of_fp64_peak": fb["algorithmic_flops"] / (fb["ms_per_launch"] * 1e-3) / 1e12 / fp64_peak}
 
     if rank != 0:
         if comm is not None:
@@ -317,9 +318,10 @@ def main():
         "roofline": {"kernel": "fitKernel<D> (all fit launches of the timed builds)", "bound": "fp64",
                      "achieved": fit_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fit_tflops / fp64_peak,
                      "traffic": None,
-                     "note": "achieved = sum-factorised contraction FLOPs (SURVEY.md 8d formula, SDF evaluation excluded) / device "
-                             "time of the fit launches; peak = DFMA rate measured in this run (hpsdf_measure_fp64_peak), "
-                             "MEASURED_PEAKS.json holds no FP64 figure; a C2 build has only ~%d fits per round" % (stats["fits_evaluated"] // max(stats["rounds"], 1)),
+                     "note": "achieved = SURVEY.md 8d algorithmic FLOPs (sum-factorised contraction + c_F = %.0f per SDF sample, sqrt/div "
+                             "counted as 1) / device time of the fit launches; peak = DFMA rate measured in this run "
+                             "(hpsdf_measure_fp64_peak; MEASURED_PEAKS.json holds no FP64 figure); a C2 build has only ~%d fits per "
+                             "round, see roofline_frontier for full-GPU launches" % (stats["sdf_flops_per_eval"], stats["fits_evaluated"] // max(stats["rounds"], 1)),
                      "fit_kernel_ms_per_step": agg["fit_ms"] / args.steps, "host_replay_ms_per_step": agg["replay_ms"] / args.steps},
         "roofline_frontier": frontier,
         "query": {"metric": "query_points_per_s", "value": q_value, "unit": "points/s", "points_per_gpu": n_q, "ms": q_ms,

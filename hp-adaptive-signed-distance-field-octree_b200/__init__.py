@@ -84,7 +84,7 @@ class BuildStats(C.Structure):
     _fields_ = [("n_nodes", C.c_uint64), ("n_leaves", C.c_uint64), ("n_coeffs", C.c_uint64), ("rounds", C.c_uint64),
                 ("jobs_evaluated", C.c_uint64), ("jobs_applied_p", C.c_uint64), ("jobs_applied_h", C.c_uint64),
                 ("fits_evaluated", C.c_uint64), ("sdf_evals", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("algorithmic_flops", C.c_double), ("total_error", C.c_double), ("exact_total_error", C.c_double),
+                ("algorithmic_flops", C.c_double), ("sdf_flops_per_eval", C.c_double), ("total_error", C.c_double), ("exact_total_error", C.c_double),
                 ("cut_margin", C.c_double), ("fit_kernel_ms", C.c_double), ("continuity_ms", C.c_double),
                 ("host_replay_ms", C.c_double), ("total_ms", C.c_double), ("cg_iterations", C.c_uint64),
                 ("cg_relative_residual", C.c_double), ("near_tie_decisions", C.c_uint64)]
@@ -107,7 +107,7 @@ class ApplyLogEntry(C.Structure):
 
 class FrontierBench(C.Structure):
     _fields_ = [("ms_per_launch", C.c_double), ("jobs", C.c_uint64), ("fits", C.c_uint64), ("sdf_evals", C.c_uint64),
-                ("algorithmic_flops", C.c_double), ("checksum", C.c_double)]
+                ("algorithmic_flops", C.c_double), ("sdf_flops_per_eval", C.c_double), ("checksum", C.c_double)]
 
 
 assert C.sizeof(Config) == 80 and C.sizeof(Instr) == 80

@@ -15,9 +15,11 @@
 // checked after every applied job; nearness weight from the exact cell mean). Work computed for leaves
 // that are never popped before termination is speculative waste, bounded by the number of final leaves.
 #include <algorithm>
+#include <functional>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <queue>
 #include <vector>
 #include "octree.h"
@@ -57,39 +59,6 @@ namespace hpsdf
             return std::exp(-1.0 * cfg.nearness_strength * m / d);
         }
 
-        template <typename T>
-        struct PinnedBuf
-        {
-            T* p = nullptr; size_t cap = 0;
-            cudaError_t reserve(size_t n)
-            {
-                if (n <= cap) return cudaSuccess;
-                if (p) cudaFreeHost(p);
-                cap = std::max(n, cap * 2);
-                return cudaMallocHost((void**)&p, cap * sizeof(T));
-            }
-            ~PinnedBuf() { if (p) cudaFreeHost(p); }
-        };
-
-        template <typename T>
-        struct DeviceBuf
-        {
-            T* p = nullptr; size_t cap = 0;
-            cudaError_t reserve(size_t n, cudaStream_t s = nullptr, size_t keep = 0)
-            {
-                if (n <= cap) return cudaSuccess;
-                const size_t newCap = std::max(n, cap * 2);
-                T* q = nullptr;
-                cudaError_t e = cudaMalloc((void**)&q, newCap * sizeof(T));
-                if (e != cudaSuccess) return e;
-                if (p && keep) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s); if (e == cudaSuccess) e = cudaStreamSynchronize(s); }
-                if (p) cudaFree(p);
-                p = q; cap = newCap;
-                return e;
-            }
-            ~DeviceBuf() { if (p) cudaFree(p); }
-        };
-
         class Builder
         {
         public:
@@ -111,19 +80,22 @@ namespace hpsdf
             std::priority_queue<std::pair<uint64_t, double>, std::vector<std::pair<uint64_t, double>>, QueuePredicate> queue_;
             std::vector<int32_t>     jobOf_;        // per node: index into jobs_, -1 = no cached result
             std::vector<double>      errOf_;        // per node: its current (weighted) error
+            std::vector<uint8_t>     inQueue_;      // per node: 1 while the leaf is in the priority queue
             std::vector<Job>         jobs_;
             std::vector<uint64_t>    pending_;      // leaves created / changed by the last replay
 
-            DeviceBuf<double>        pool_;  size_t poolUsed_ = 0;
-            DeviceBuf<FitTask>       dTasks_;
-            DeviceBuf<FitRecord>     dRecs_;
-            PinnedBuf<FitTask>       hTasks_;
-            PinnedBuf<FitRecord>     hRecs_;
+            BuildWorkspace&          ws_ = t_.ctx->ws;
+            DeviceBuf<double>&       pool_ = ws_.pool;  size_t poolUsed_ = 0;
+            DeviceBuf<FitTask>&      dTasks_ = ws_.tasks;
+            DeviceBuf<FitRecord>&    dRecs_ = ws_.recs;
+            PinnedBuf<FitTask>&      hTasks_ = ws_.hTasks;
+            PinnedBuf<FitRecord>&    hRecs_ = ws_.hRecs;
 
             double      total_ = 0.0;               // totalCoeffError, reference bookkeeping (Octree.cpp:212, 257, 272, 276)
             long double exactSum_ = 0.0L;
             long        unfitted_ = 0;
             int         rank_ = 0, world_ = 1;
+            double      sdfFlops_ = 0.0;
             hpsdf_decision_log_entry lastApplied_{};      // last job applied before the termination cut
             double      lastTotal_ = 0.0, totalBeforeLast_ = 0.0;
 
@@ -180,9 +152,33 @@ namespace hpsdf
             const size_t firstJob = jobs_.size();
             jobOf_.resize(nodes_.size(), -1);
             errOf_.resize(nodes_.size(), 0.0);
+            // Which uncached leaves to evaluate now. A leaf is certainly popped by the strict greedy loop if, taking the
+            // queue in decreasing error order, the total minus the errors before it is still >= the threshold (popping
+            // an entry and any of its descendants lowers the total by at most that entry's error). Everything down to
+            // that guaranteed level L is needed work; entries down to L / 8^speculate are pre-evaluated speculatively so
+            // the replay stalls less often. Leaves below stay pending until the level reaches them.
+            double level = 0.0;
+            {
+                std::vector<double> errs;
+                errs.reserve(nodes_.size());
+                for (uint64_t i = 0; i < nodes_.size(); ++i) if (nodes_[i].child == kNoChild && inQueue_[i]) errs.push_back(errOf_[i]);
+                std::sort(errs.begin(), errs.end(), std::greater<double>());
+                const double thr = cfg_.target_error_threshold;
+                double remaining = checkValue();
+                level = errs.empty() ? 0.0 : errs.front();
+                for (double e : errs)
+                {
+                    if (!(remaining >= thr)) break;
+                    level = e;
+                    remaining -= e * (1.0 + 1e-9);
+                }
+                for (uint32_t k = 0; k < o_.speculate; ++k) level *= 0.125;
+            }
+            std::vector<uint64_t> later;
             for (uint64_t idx : pending_)
             {
                 const HostNode& n = nodes_[idx];
+                if (errOf_[idx] < level) { later.push_back(idx); continue; }
                 Job j;
                 j.coarse = std::abs(errOf_[idx] - kInitialErr) < std::numeric_limits<double>::epsilon() && n.degree == 0;   // Octree.cpp:806, 831
                 if (j.coarse) { j.doP = true; byDegree[kCoarseDegree].push_back({ idx, 0, true }); }
@@ -196,7 +192,7 @@ namespace hpsdf
                 jobOf_[idx] = (int32_t)jobs_.size();
                 jobs_.push_back(j);
             }
-            pending_.clear();
+            pending_.swap(later);
 
             size_t nTasks = 0, poolNeed = poolUsed_;
             for (int d = 1; d <= kMaxDegree; ++d) { nTasks += byDegree[d].size(); poolNeed += byDegree[d].size() * (size_t)coeffCount(d); }
@@ -255,7 +251,7 @@ namespace hpsdf
                     t_.stats.kernel_launches++;
                 }
                 t_.stats.fits_evaluated += n;
-                roundFlops += (double)n * fitFlops(d);
+                roundFlops += (double)n * (fitFlops(d) + sdfFlops_ * fitRule(d) * fitRule(d) * fitRule(d));
                 roundEvals += (uint64_t)n * fitRule(d) * fitRule(d) * fitRule(d);
             }
             HPSDF_CUDA(cudaEventRecord(ev1_, stream_));
@@ -320,6 +316,7 @@ namespace hpsdf
                 const uint64_t idx = top.first;
                 if (idx >= jobOf_.size() || jobOf_[idx] < 0) return false;                               // no cached result: next round
                 queue_.pop();
+                inQueue_[idx] = 0;
                 Job& j = jobs_[jobOf_[idx]];
                 jobOf_[idx] = -1;
                 const double err = top.second;
@@ -363,6 +360,7 @@ namespace hpsdf
                     nodes_[idx].degree = (uint8_t)(j.coarse ? kCoarseDegree : p + 1);
                     errOf_[idx] = j.pErr;
                     queue_.push({ idx, j.pErr });                                                        // Octree.cpp:289-290
+                    inQueue_[idx] = 1;
                     pending_.push_back(idx);
                     t_.stats.jobs_applied_p++;
                     t_.applyLog.push_back({ idx, 0u, p, err, j.pErr, j.pImp, j.hImp, checkValue() });
@@ -375,6 +373,7 @@ namespace hpsdf
                     exactSum_ -= (long double)err;
                     jobOf_.resize(nodes_.size(), -1);
                     errOf_.resize(nodes_.size(), 0.0);
+                    inQueue_.resize(nodes_.size(), 0);
                     for (uint32_t i = 0; i < 8; ++i)
                     {
                         const uint64_t c = nodes_[idx].child + i;                                        // Octree.cpp:275-290
@@ -384,6 +383,7 @@ namespace hpsdf
                         nodes_[c].degree = (uint8_t)p;
                         errOf_[c] = j.hErr[i];
                         queue_.push({ c, j.hErr[i] });
+                        inQueue_[c] = 1;
                         pending_.push_back(c);
                     }
                     t_.stats.jobs_applied_h++;
@@ -463,26 +463,30 @@ namespace hpsdf
             }
             t_.nCoeffs = cur;
             const uint32_t nSeg = (uint32_t)srcOff.size();
-            HPSDF_CUDA(cudaMalloc((void**)&t_.dCoeffs, std::max<size_t>(cur, 1) * sizeof(double)));
-            DeviceBuf<uint32_t> dSeg;
-            HPSDF_CUDA(dSeg.reserve(3 * (size_t)nSeg));
-            HPSDF_CUDA(cudaMemcpyAsync(dSeg.p, srcOff.data(), nSeg * 4, cudaMemcpyHostToDevice, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(dSeg.p + nSeg, dstOff.data(), nSeg * 4, cudaMemcpyHostToDevice, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(dSeg.p + 2 * (size_t)nSeg, count.data(), nSeg * 4, cudaMemcpyHostToDevice, stream_));
-            HPSDF_CUDA(launchGatherSegments(pool_.p, t_.dCoeffs, dSeg.p, dSeg.p + nSeg, dSeg.p + 2 * (size_t)nSeg, nSeg, stream_));
+            hpsdf_status st = allocTreeBlob(t_);
+            if (st != HPSDF_OK) return st;
+            HPSDF_CUDA(ws_.segs.reserve(3 * (size_t)nSeg + 16));
+            HPSDF_CUDA(ws_.hSegs.reserve(3 * (size_t)nSeg + 16));
+            memcpy(ws_.hSegs.p, srcOff.data(), nSeg * 4);
+            memcpy(ws_.hSegs.p + nSeg, dstOff.data(), nSeg * 4);
+            memcpy(ws_.hSegs.p + 2 * (size_t)nSeg, count.data(), nSeg * 4);
+            HPSDF_CUDA(cudaMemcpyAsync(ws_.segs.p, ws_.hSegs.p, 3 * (size_t)nSeg * 4, cudaMemcpyHostToDevice, stream_));
+            HPSDF_CUDA(launchGatherSegments(pool_.p, t_.dCoeffs, ws_.segs.p, ws_.segs.p + nSeg, ws_.segs.p + 2 * (size_t)nSeg, nSeg, stream_));
             t_.stats.kernel_launches++;
-            HPSDF_CUDA(cudaStreamSynchronize(stream_));
+            HPSDF_CUDA(cudaStreamSynchronize(stream_));       // the pinned segment staging is reused by finalizeQueryStructures
             return HPSDF_OK;
         }
 
         hpsdf_status Builder::run()
         {
             const double t0 = nowMs();
-            stream_ = (cudaStream_t)o_.stream;
-            if (!stream_) { HPSDF_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking)); ownStream_ = true; }
-            HPSDF_CUDA(cudaEventCreate(&ev0_));
-            HPSDF_CUDA(cudaEventCreate(&ev1_));
+            std::lock_guard<std::mutex> wsLock(*(std::mutex*)t_.ctx->wsMutex);
+            stream_ = o_.stream ? (cudaStream_t)o_.stream : ws_.stream;
+            ev0_ = ws_.ev0; ev1_ = ws_.ev1;
             if (o_.comm) { rank_ = commRank(o_.comm); world_ = commWorld(o_.comm); }
+            sdfFlops_ = 6.0;
+            for (uint32_t i = 0; i < prog_.n; ++i) sdfFlops_ += sdfOpFlops(prog_.instr[i].op);
+            t_.stats.sdf_flops_per_eval = sdfFlops_;
 
             hpsdf_status st = HPSDF_OK;
             // CreateRoot (Octree.cpp:792-801) + UniformlyRefine
@@ -496,6 +500,8 @@ namespace hpsdf
             for (uint32_t i = 0; i < 8; ++i) refineUniform(1 + i, 1);
             errOf_.assign(nodes_.size(), kInitialErr);
             jobOf_.assign(nodes_.size(), -1);
+            inQueue_.assign(nodes_.size(), 0);
+            for (uint64_t idx : pending_) inQueue_[idx] = 1;
             total_ = std::pow(8, 4) * kInitialErr;                                                      // Octree.cpp:212
             unfitted_ = (long)queue_.size();
             lastTotal_ = totalBeforeLast_ = total_;
@@ -540,8 +546,7 @@ namespace hpsdf
                 for (const HostNode& n : nodes_) leaves += n.child == kNoChild;
                 t_.stats.n_nodes = nodes_.size(); t_.stats.n_leaves = leaves; t_.stats.n_coeffs = t_.nCoeffs;
             }
-            cudaEventDestroy(ev0_); cudaEventDestroy(ev1_);
-            if (ownStream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); }
+            cudaStreamSynchronize(stream_);
             t_.stats.total_ms = nowMs() - t0;
             return st;
         }

@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include "octree.h"
@@ -209,10 +210,12 @@ extern "C"
         hpsdf_octree* t = new hpsdf_octree();
         t->device = tree->device; t->ctx = tree->ctx; t->cfg = tree->cfg; t->map = tree->map;
         t->nodes = tree->nodes; t->nCoeffs = tree->nCoeffs; t->stats = tree->stats; t->decisionLog = tree->decisionLog; t->applyLog = tree->applyLog;
-        cudaError_t e = cudaMalloc((void**)&t->dCoeffs, std::max<size_t>(t->nCoeffs, 1) * 8);
-        if (e == cudaSuccess) e = cudaMemcpy(t->dCoeffs, tree->dCoeffs, t->nCoeffs * 8, cudaMemcpyDeviceToDevice);
+        hpsdf_status st = allocTreeBlob(*t);
+        if (st != HPSDF_OK) { delete t; return st; }
+        cudaError_t e = cudaMemcpy(t->dCoeffs, tree->dCoeffs, t->nCoeffs * 8, cudaMemcpyDeviceToDevice);
         if (e != cudaSuccess) { delete t; return failCuda(e, "hpsdf_clone"); }
-        const hpsdf_status st = finalizeQueryStructures(*t, nullptr);
+        std::lock_guard<std::mutex> wsLock(*(std::mutex*)t->ctx->wsMutex);
+        st = finalizeQueryStructures(*t, t->ctx->ws.stream);
         if (st != HPSDF_OK) { delete t; return st; }
         *out = t;
         return HPSDF_OK;
@@ -370,7 +373,10 @@ extern "C"
         out->jobs = jobs; out->fits = nH + nP;
         const uint64_t nh = fitRule((int)degree), np = fitRule((int)degree + 1);
         out->sdf_evals = nH * nh * nh * nh + nP * np * np * np;
-        out->algorithmic_flops = (double)nH * fitFlops((int)degree) + (double)nP * fitFlops((int)degree + 1);
+        double cF = 6.0;
+        for (uint32_t i = 0; i < dp.n; ++i) cF += sdfOpFlops(dp.instr[i].op);
+        out->sdf_flops_per_eval = cF;
+        out->algorithmic_flops = (double)nH * fitFlops((int)degree) + (double)nP * fitFlops((int)degree + 1) + cF * (double)out->sdf_evals;
         for (const FitRecord& r : recs) out->checksum += r.rawErr;
         return HPSDF_OK;
     }

@@ -98,6 +98,14 @@ namespace hpsdf
         setBidxDev(device, ctx->fitTab.bidx);
         cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
         uploadConstants();
+        ctx->wsMutex = new std::mutex();
+        cudaStreamCreateWithFlags(&ctx->ws.stream, cudaStreamNonBlocking);
+        cudaEventCreate(&ctx->ws.ev0);
+        cudaEventCreate(&ctx->ws.ev1);
+        // a first pool of 32 M doubles (256 MB) and pinned staging for 128 K fits: a README-sized build never reallocates
+        ctx->ws.pool.reserve((size_t)32 << 20);
+        ctx->ws.tasks.reserve((size_t)1 << 17); ctx->ws.recs.reserve((size_t)1 << 17);
+        ctx->ws.hTasks.reserve((size_t)1 << 17); ctx->ws.hRecs.reserve((size_t)1 << 17);
         if ((e = cudaDeviceSynchronize()) != cudaSuccess) { err = cudaGetErrorString(e); delete ctx; cudaFree(mem); return nullptr; }
         g_ctx[device] = ctx;
         return ctx;

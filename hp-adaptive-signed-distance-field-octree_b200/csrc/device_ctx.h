@@ -15,6 +15,54 @@ namespace hpsdf
         const uint32_t* bidx;
     };
 
+    template <typename T>
+    struct PinnedBuf
+    {
+        T* p = nullptr; size_t cap = 0;
+        cudaError_t reserve(size_t n)
+        {
+            if (n <= cap) return cudaSuccess;
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = n > cap * 2 ? n : cap * 2;
+            return cudaMallocHost((void**)&p, cap * sizeof(T));
+        }
+    };
+
+    template <typename T>
+    struct DeviceBuf
+    {
+        T* p = nullptr; size_t cap = 0;
+        // grows geometrically; `keep` leading elements survive a reallocation
+        cudaError_t reserve(size_t n, cudaStream_t s = nullptr, size_t keep = 0)
+        {
+            if (n <= cap) return cudaSuccess;
+            const size_t newCap = n > cap * 2 ? n : cap * 2;
+            T* q = nullptr;
+            cudaError_t e = cudaMalloc((void**)&q, newCap * sizeof(T));
+            if (e != cudaSuccess) return e;
+            if (p && keep) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s); if (e == cudaSuccess) e = cudaStreamSynchronize(s); }
+            if (p) cudaFree(p);
+            p = q; cap = newCap;
+            return e;
+        }
+    };
+
+    // Build scratch that survives between Create calls on a device (one build at a time per device): the coefficient
+    // pool, task / record buffers and their pinned host mirrors. Allocation is what dominates a millisecond-scale build.
+    struct BuildWorkspace
+    {
+        DeviceBuf<double>    pool;
+        DeviceBuf<FitTask>   tasks;
+        DeviceBuf<FitRecord> recs;
+        DeviceBuf<uint32_t>  segs;
+        PinnedBuf<FitTask>   hTasks;
+        PinnedBuf<FitRecord> hRecs;
+        PinnedBuf<uint32_t>  hSegs;
+        cudaStream_t         stream = nullptr;
+        cudaEvent_t          ev0 = nullptr, ev1 = nullptr;
+    };
+
     struct DeviceCtx
     {
         int           device = -1;
@@ -23,6 +71,8 @@ namespace hpsdf
         int           smCount = 0;
         const double* glRoots = nullptr;      // all 64 rules, rule n at n(n-1)/2, ascending nodes
         const double* glWeights = nullptr;
+        BuildWorkspace ws;
+        void*          wsMutex = nullptr;     // std::mutex*, serialises builds on this device
     };
 
     // One leaf-leaf shared face (ContinuityThreadPool::Input, ContinuityThreadPool.h:24-28) with everything

@@ -44,6 +44,24 @@ namespace hpsdf
         return 2.0 * (d + 1) * n * n * n + 2.0 * pairCount(d) * n * n + 2.0 * ((d + 1) * (d + 2) * (d + 3) / 6) * n + 4.0 * n * n * n;
     }
 
+    // FLOPs of one evaluation of a primitive / operator, counting sqrt and divide as one each (they expand to ~25-30 FP64
+    // instructions on the device): the c_F term of the SURVEY.md §8d formula. 6 more for the unit-cube -> root map.
+    inline double sdfOpFlops(uint32_t op)
+    {
+        switch (op)
+        {
+            case HPSDF_PRIM_SPHERE:  return 10.0;   // 3 sub, 3 mul, 2 add, sqrt, sub
+            case HPSDF_PRIM_BOX:     return 22.0;   // 3 sub, 3 abs, 3 sub, 3 max, 3 mul, 2 add, sqrt, 2 max, min, add
+            case HPSDF_PRIM_TORUS:   return 13.0;   // 3 sub, 2 mul, add, sqrt, sub, 2 mul, add, sqrt, sub
+            case HPSDF_PRIM_CAPSULE: return 32.0;   // 6 sub, 2 dot (5 each), div, 2 clamp, 3 fma (6), 5, sqrt, sub
+            case HPSDF_PRIM_PLANE:   return 6.0;
+            case HPSDF_OP_NEGATE:    return 1.0;
+            case HPSDF_OP_UNION: case HPSDF_OP_INTERSECT: return 1.0;
+            case HPSDF_OP_SUBTRACT:  return 2.0;
+            default:                 return 0.0;    // mesh / octree primitives: report evaluations per second instead
+        }
+    }
+
     // Host-side tables (tables.cpp)
     struct Tables
     {

@@ -43,6 +43,7 @@ struct hpsdf_octree
     std::vector<hpsdf::HostNode> nodes;
     size_t              nCoeffs = 0;
 
+    void*               dBlob = nullptr;         // one allocation: packed store | padded store | QNodes | top table | view
     double*             dCoeffs = nullptr;       // packed store, MemoryBlock order (DFS leaf order)
     double*             dCoeffsPad = nullptr;    // Query layout: every leaf starts at an even index
     size_t              nCoeffsPad = 0;
@@ -68,6 +69,8 @@ struct hpsdf_octree
 namespace hpsdf
 {
     void          setRootMap(const hpsdf_config& cfg, RootMap& map);
+    // One device allocation for everything a finished tree owns; needs t.nodes (with degrees) and t.nCoeffs.
+    hpsdf_status  allocTreeBlob(hpsdf_octree& t);
     // Build QNodes, the padded coefficient store and the top table from nodes + dCoeffs.
     hpsdf_status  finalizeQueryStructures(hpsdf_octree& t, cudaStream_t stream);
     // SDF program with handles resolved to device views; fails on malformed programs.

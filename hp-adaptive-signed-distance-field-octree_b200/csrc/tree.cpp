@@ -11,7 +11,7 @@
 hpsdf_octree::~hpsdf_octree()
 {
     if (ctx) cudaSetDevice(device);
-    cudaFree(dCoeffs); cudaFree(dCoeffsPad); cudaFree(dNodes); cudaFree(dTop); cudaFree(dView);
+    cudaFree(dBlob);
     for (int i = 0; i < 3; ++i)
     {
         cudaFree(dScratchIn[i]); cudaFree(dScratchOut[i]);
@@ -21,13 +21,47 @@ hpsdf_octree::~hpsdf_octree()
 
 namespace hpsdf
 {
+    static size_t paddedCoeffCount(const hpsdf_octree& t)
+    {
+        size_t pad = 0;
+        for (const HostNode& n : t.nodes) if (n.child == kNoChild) pad += ((size_t)coeffCount(n.degree) + 1u) & ~(size_t)1u;
+        return pad;
+    }
+
+    hpsdf_status allocTreeBlob(hpsdf_octree& t)
+    {
+        auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t nNodes = t.nodes.size();
+        t.nCoeffsPad = paddedCoeffCount(t);
+        const size_t bCoeffs = align(std::max<size_t>(t.nCoeffs, 1) * 8), bPad = align(std::max<size_t>(t.nCoeffsPad, 2) * 8);
+        const size_t bNodes = align(nNodes * sizeof(QNode)), bTop = align(4096 * 4), bView = align(sizeof(DeviceTreeView));
+        cudaFree(t.dBlob);
+        t.dBlob = nullptr;
+        HPSDF_CUDA(cudaMalloc(&t.dBlob, bCoeffs + bPad + bNodes + bTop + bView));
+        char* p = (char*)t.dBlob;
+        t.dCoeffs = (double*)p; p += bCoeffs;
+        t.dCoeffsPad = (double*)p; p += bPad;
+        t.dNodes = (QNode*)p; p += bNodes;
+        t.dTop = (uint32_t*)p; p += bTop;
+        t.dView = (DeviceTreeView*)p;
+        return HPSDF_OK;
+    }
+
     hpsdf_status finalizeQueryStructures(hpsdf_octree& t, cudaStream_t stream)
     {
         const size_t nNodes = t.nodes.size();
         if (nNodes >= 0xFFFFFFFFull) { setLastError("too many nodes for the 32-bit query layout"); return HPSDF_ERR_UNSUPPORTED; }
-        std::vector<QNode> q(nNodes);
-        std::vector<uint32_t> srcOff, dstOff, count;
-        size_t padCur = 0;
+        // staging: [QNodes][top 4096][src|dst|count segments] in one pinned buffer, one H2D copy
+        size_t nLeaves = 0;
+        for (const HostNode& n : t.nodes) nLeaves += n.child == kNoChild;
+        const size_t wNodes = nNodes * 4, wTop = 4096, wSeg = 3 * nLeaves;
+        BuildWorkspace& ws = t.ctx->ws;
+        HPSDF_CUDA(ws.hSegs.reserve(wNodes + wTop + wSeg + 16));
+        HPSDF_CUDA(ws.segs.reserve(wSeg + 16));
+        QNode* q = (QNode*)ws.hSegs.p;
+        uint32_t* top = ws.hSegs.p + wNodes;
+        uint32_t* srcOff = top + wTop; uint32_t* dstOff = srcOff + nLeaves; uint32_t* count = dstOff + nLeaves;
+        size_t padCur = 0, li = 0;
         for (size_t i = 0; i < nNodes; ++i)
         {
             const HostNode& n = t.nodes[i];
@@ -36,7 +70,7 @@ namespace hpsdf
             {
                 const uint32_t c = (uint32_t)coeffCount(n.degree);
                 q[i].child = 0xFFFFFFFFu; q[i].degree = n.degree; q[i].cstart = (uint32_t)padCur;
-                srcOff.push_back((uint32_t)n.cstart); dstOff.push_back((uint32_t)padCur); count.push_back(c);
+                srcOff[li] = (uint32_t)n.cstart; dstOff[li] = (uint32_t)padCur; count[li] = c; ++li;
                 padCur += (c + 1u) & ~1u;                                // next leaf starts at an even index (16-byte aligned)
             }
             else { q[i].child = (uint32_t)n.child; q[i].degree = kInternalTag; q[i].cstart = 0; }
@@ -44,7 +78,6 @@ namespace hpsdf
         if (padCur >= 0xFFFFFFF0ull) { setLastError("coefficient store exceeds the 32-bit query layout"); return HPSDF_ERR_UNSUPPORTED; }
 
         // depth-4 entry table: valid only if every 16^3 cell exists at depth 4 (always true for trees the reference builds)
-        std::vector<uint32_t> top(4096);
         bool topOk = true;
         for (uint32_t code = 0; code < 4096 && topOk; ++code)
         {
@@ -57,34 +90,17 @@ namespace hpsdf
             }
             top[code] = (uint32_t)cur;
         }
+        if (padCur != t.nCoeffsPad || !t.dBlob) { setLastError("internal: tree blob not allocated for this tree"); return HPSDF_ERR_CUDA; }
 
-        cudaFree(t.dNodes); cudaFree(t.dCoeffsPad); cudaFree(t.dTop); cudaFree(t.dView);
-        t.dNodes = nullptr; t.dCoeffsPad = nullptr; t.dTop = nullptr; t.dView = nullptr;
-        t.nCoeffsPad = padCur;
-        HPSDF_CUDA(cudaMalloc((void**)&t.dNodes, nNodes * sizeof(QNode)));
-        HPSDF_CUDA(cudaMalloc((void**)&t.dCoeffsPad, std::max<size_t>(padCur, 2) * sizeof(double)));
-        HPSDF_CUDA(cudaMemsetAsync(t.dCoeffsPad, 0, std::max<size_t>(padCur, 2) * sizeof(double), stream));
-        HPSDF_CUDA(cudaMemcpyAsync(t.dNodes, q.data(), nNodes * sizeof(QNode), cudaMemcpyHostToDevice, stream));
-        if (topOk)
-        {
-            HPSDF_CUDA(cudaMalloc((void**)&t.dTop, 4096 * sizeof(uint32_t)));
-            HPSDF_CUDA(cudaMemcpyAsync(t.dTop, top.data(), 4096 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        }
-        const uint32_t nSeg = (uint32_t)srcOff.size();
-        uint32_t* dSeg = nullptr;
-        HPSDF_CUDA(cudaMalloc((void**)&dSeg, std::max<size_t>(3 * (size_t)nSeg, 1) * sizeof(uint32_t)));
-        cudaError_t e = cudaMemcpyAsync(dSeg, srcOff.data(), nSeg * 4, cudaMemcpyHostToDevice, stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(dSeg + nSeg, dstOff.data(), nSeg * 4, cudaMemcpyHostToDevice, stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(dSeg + 2 * (size_t)nSeg, count.data(), nSeg * 4, cudaMemcpyHostToDevice, stream);
-        if (e == cudaSuccess) e = launchGatherSegments(t.dCoeffs, t.dCoeffsPad, dSeg, dSeg + nSeg, dSeg + 2 * (size_t)nSeg, nSeg, stream);
+        HPSDF_CUDA(cudaMemcpyAsync(t.dNodes, q, nNodes * sizeof(QNode), cudaMemcpyHostToDevice, stream));
+        HPSDF_CUDA(cudaMemcpyAsync(t.dTop, top, 4096 * 4, cudaMemcpyHostToDevice, stream));
+        HPSDF_CUDA(cudaMemcpyAsync(ws.segs.p, srcOff, wSeg * 4, cudaMemcpyHostToDevice, stream));
+        HPSDF_CUDA(cudaMemsetAsync(t.dCoeffsPad, 0, std::max<size_t>(padCur, 2) * 8, stream));
+        HPSDF_CUDA(launchGatherSegments(t.dCoeffs, t.dCoeffsPad, ws.segs.p, ws.segs.p + nLeaves, ws.segs.p + 2 * nLeaves, (uint32_t)nLeaves, stream));
         t.stats.kernel_launches++;
-
-        t.view.nodes = t.dNodes; t.view.coeffs = t.dCoeffsPad; t.view.top = t.dTop; t.view.map = t.map; t.view.nNodes = (uint32_t)nNodes;
-        if (e == cudaSuccess) e = cudaMalloc((void**)&t.dView, sizeof(DeviceTreeView));
-        if (e == cudaSuccess) e = cudaMemcpyAsync(t.dView, &t.view, sizeof(DeviceTreeView), cudaMemcpyHostToDevice, stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        cudaFree(dSeg);
-        if (e != cudaSuccess) return failCuda(e, "finalizeQueryStructures");
+        t.view.nodes = t.dNodes; t.view.coeffs = t.dCoeffsPad; t.view.top = topOk ? t.dTop : nullptr; t.view.map = t.map; t.view.nNodes = (uint32_t)nNodes;
+        HPSDF_CUDA(cudaMemcpyAsync(t.dView, &t.view, sizeof(DeviceTreeView), cudaMemcpyHostToDevice, stream));
+        HPSDF_CUDA(cudaStreamSynchronize(stream));
         return HPSDF_OK;
     }
 
@@ -213,12 +229,14 @@ namespace hpsdf
             }
         }
         t.nCoeffs = nc;
-        HPSDF_CUDA(cudaMalloc((void**)&t.dCoeffs, std::max<uint64_t>(nc, 1) * 8));
+        hpsdf_status st = allocTreeBlob(t);
+        if (st != HPSDF_OK) return st;
         HPSDF_CUDA(cudaMemcpy(t.dCoeffs, p + 8, nc * 8, cudaMemcpyHostToDevice));
         uint64_t leaves = 0;
         for (const HostNode& n : t.nodes) leaves += n.child == kNoChild;
         t.stats.n_nodes = nn; t.stats.n_leaves = leaves; t.stats.n_coeffs = nc;
-        return finalizeQueryStructures(t, nullptr);
+        std::lock_guard<std::mutex> wsLock(*(std::mutex*)t.ctx->wsMutex);
+        return finalizeQueryStructures(t, t.ctx->ws.stream);
     }
 
     // Octree::Query for host arrays: chunks of points go H2D -> kernel -> D2H on three rotating streams so the copies of

@@ -216,7 +216,8 @@ typedef struct hpsdf_build_stats
     uint64_t fits_evaluated;      /* FitPolynomial-equivalents computed (coarse fit, child fit or p-fit) */
     uint64_t sdf_evals;           /* SDF samples evaluated */
     uint64_t kernel_launches;     /* kernels of this library launched by the build */
-    double   algorithmic_flops;   /* sum-factorised FLOPs of those fits (SURVEY.md §8d formula, SDF evaluation excluded) */
+    double   algorithmic_flops;   /* sum-factorised FLOPs of those fits incl. sdf_evals * sdf_flops_per_eval (SURVEY.md §8d formula) */
+    double   sdf_flops_per_eval;  /* c_F of the SDF program: closed-form FLOPs per sample, sqrt and divide counted as one */
     double   total_error;         /* totalCoeffError at termination (reference bookkeeping or exact, per total_mode) */
     double   exact_total_error;   /* plain sum of leaf errors at termination */
     double   cut_margin;          /* (threshold - total)/threshold at termination: small = near-threshold stop */
@@ -282,7 +283,8 @@ typedef struct hpsdf_frontier_bench
 {
     double   ms_per_launch;
     uint64_t jobs, fits, sdf_evals;
-    double   algorithmic_flops;     /* contraction FLOPs only */
+    double   algorithmic_flops;     /* contraction FLOPs + sdf_evals * sdf_flops_per_eval */
+    double   sdf_flops_per_eval;
     double   checksum;              /* sum of all error outputs, so the work cannot be elided */
 } hpsdf_frontier_bench;
 

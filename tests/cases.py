@@ -25,6 +25,9 @@ CASES = {
     # custom domain (HPUnitTests.cpp:285-316): root [-0.25,5]^3, radius 0.75 sphere
     "custom_domain": dict(cfg=dict(threshold=1e-8, nearness=1, strength=3.0, continuity=False,
                                    root_min=(-0.25,) * 3, root_max=(5.0,) * 3), prog=[("sphere", [2.0, 2.0, 2.0, 0.75])]),
+    # continuity on a tree with h-splits (mixed-depth faces -> numeric face integrals) and no mirror symmetry
+    "csg_cont": dict(cfg=dict(threshold=3e-7, nearness=0, strength=0.0, continuity=True, cstrength=8.0,
+                              root_min=(-0.25,) * 3, root_max=(0.5,) * 3), prog=CSG_C2),
     # cheap case with h-splits and several degrees, for fast CPU tests
     "csg_small": dict(cfg=dict(threshold=3e-7, nearness=0, strength=0.0, continuity=False,
                                root_min=(-0.25,) * 3, root_max=(0.5,) * 3), prog=CSG_C2),

@@ -25,7 +25,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 from oracle import hpref            # noqa: E402
 from cases import CASES, root_points, leaf_table, path_code  # noqa: E402
 
-TREE_CASES = ["c1_readme", "sphere_poly_1e8", "sphere_cont_1e8", "custom_domain", "csg_small"]
+TREE_CASES = ["c1_readme", "sphere_poly_1e8", "csg_cont", "custom_domain", "csg_small"]
 
 
 def tree_golden(name):

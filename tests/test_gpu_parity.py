@@ -151,7 +151,7 @@ def test_create_matches_oracle_full_tree(hp, oracle, built, name):
     print(name, "worst", worst, "same node numbering:", same_numbering, "divergent cells:", len(div), "logged group:", len(allowed), {k: st[k] for k in ("rounds", "fits_evaluated", "jobs_evaluated", "total_ms", "fit_kernel_ms", "host_replay_ms", "near_tie_decisions", "cut_margin")})
 
 
-@pytest.mark.parametrize("name", ["c1_readme", "sphere_cont_1e8"])
+@pytest.mark.parametrize("name", ["c1_readme", "csg_cont"])
 def test_continuity_matches_reference_golden(hp, built, name):
     """PerformContinuityPostProcess: the converged solution of (M + lambda I) x = lambda c (CG to 1e-13) against the
     reference's, plus the gap of a reference-tolerance (1e-6) solve."""
