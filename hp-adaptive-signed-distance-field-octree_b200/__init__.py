@@ -63,7 +63,7 @@ class BuildOpts(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("max_degree", C.c_uint32), ("max_depth", C.c_uint32),
                 ("nearness_mode", C.c_uint32), ("total_mode", C.c_uint32), ("cg_max_iterations", C.c_uint32),
                 ("cg_tolerance", C.c_double), ("device", C.c_int32), ("speculate", C.c_uint32),
-                ("comm", C.c_void_p), ("stream", C.c_void_p)]
+                ("strict_order", C.c_uint32), ("comm", C.c_void_p), ("stream", C.c_void_p)]
 
     def __init__(self, **kw):
         super().__init__()
@@ -86,7 +86,8 @@ class BuildStats(C.Structure):
                 ("fits_evaluated", C.c_uint64), ("sdf_evals", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("algorithmic_flops", C.c_double), ("sdf_flops_per_eval", C.c_double), ("total_error", C.c_double), ("exact_total_error", C.c_double),
                 ("cut_margin", C.c_double), ("fit_kernel_ms", C.c_double), ("continuity_ms", C.c_double),
-                ("host_replay_ms", C.c_double), ("total_ms", C.c_double), ("cg_iterations", C.c_uint64),
+                ("host_replay_ms", C.c_double), ("host_select_ms", C.c_double), ("host_tasks_ms", C.c_double),
+                ("device_wait_ms", C.c_double), ("pack_ms", C.c_double), ("finalize_ms", C.c_double), ("total_ms", C.c_double), ("cg_iterations", C.c_uint64),
                 ("cg_relative_residual", C.c_double), ("near_tie_decisions", C.c_uint64)]
 
     def as_dict(self):

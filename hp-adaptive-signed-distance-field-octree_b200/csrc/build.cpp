@@ -77,7 +77,17 @@ namespace hpsdf
             bool                     ownStream_ = false;
             cudaEvent_t              ev0_ = nullptr, ev1_ = nullptr;
 
-            std::priority_queue<std::pair<uint64_t, double>, std::vector<std::pair<uint64_t, double>>, QueuePredicate> queue_;
+            struct Heap : std::priority_queue<std::pair<uint64_t, double>, std::vector<std::pair<uint64_t, double>>, QueuePredicate>
+            {
+                const std::vector<std::pair<uint64_t, double>>& entries() const { return c; }
+            } queue_;
+            // error histogram of the queue by binary exponent (bucket b holds errors in [2^(b-1101), 2^(b-1100)))
+            static constexpr int kBuckets = 2200;
+            std::vector<double>      bucketSum_ = std::vector<double>(kBuckets, 0.0);
+            std::vector<uint32_t>    bucketCount_ = std::vector<uint32_t>(kBuckets, 0u);
+            double                   applyLevel_ = std::numeric_limits<double>::infinity();   // entries >= this are certain to be popped
+            size_t                   levelLogStart_ = 0;     // first apply-log entry of the current level
+            std::vector<std::pair<uint64_t, double>> deferred_;
             std::vector<int32_t>     jobOf_;        // per node: index into jobs_, -1 = no cached result
             std::vector<double>      errOf_;        // per node: its current (weighted) error
             std::vector<uint8_t>     inQueue_;      // per node: 1 while the leaf is in the priority queue
@@ -105,6 +115,29 @@ namespace hpsdf
             bool         replay();                  // true = terminated
             hpsdf_status pack();
             void         logCutTies();
+            void         applyJob(uint64_t idx, double err);
+            void         computeLevel();
+            static int   bucketOf(double e)
+            {
+                int ex = -1100;
+                if (e > 0.0) std::frexp(e, &ex);
+                return std::min(std::max(ex + 1100, 0), kBuckets - 1);
+            }
+            void qPush(uint64_t idx, double err)
+            {
+                queue_.push({ idx, err });
+                inQueue_[idx] = 1;
+                const int b = bucketOf(err);
+                bucketSum_[b] += err; bucketCount_[b]++;
+            }
+            void qPop()
+            {
+                const std::pair<uint64_t, double> t = queue_.top();
+                queue_.pop();
+                inQueue_[t.first] = 0;
+                const int b = bucketOf(t.second);
+                if (--bucketCount_[b] == 0) bucketSum_[b] = 0.0; else bucketSum_[b] -= t.second;
+            }
             double       checkValue() const
             {
                 return o_.total_mode == HPSDF_TOTAL_EXACT_SUM
@@ -138,8 +171,7 @@ namespace hpsdf
             else
             {
                 nodes_[idx].degree = 0;
-                queue_.push({ idx, kInitialErr });
-                pending_.push_back(idx);
+                pending_.push_back(idx);        // enters the queue with err = 100 in run(), in this (visiting) order
             }
         }
 
@@ -157,23 +189,13 @@ namespace hpsdf
             // an entry and any of its descendants lowers the total by at most that entry's error). Everything down to
             // that guaranteed level L is needed work; entries down to L / 8^speculate are pre-evaluated speculatively so
             // the replay stalls less often. Leaves below stay pending until the level reaches them.
-            double level = 0.0;
-            {
-                std::vector<double> errs;
-                errs.reserve(nodes_.size());
-                for (uint64_t i = 0; i < nodes_.size(); ++i) if (nodes_[i].child == kNoChild && inQueue_[i]) errs.push_back(errOf_[i]);
-                std::sort(errs.begin(), errs.end(), std::greater<double>());
-                const double thr = cfg_.target_error_threshold;
-                double remaining = checkValue();
-                level = errs.empty() ? 0.0 : errs.front();
-                for (double e : errs)
-                {
-                    if (!(remaining >= thr)) break;
-                    level = e;
-                    remaining -= e * (1.0 + 1e-9);
-                }
-                for (uint32_t k = 0; k < o_.speculate; ++k) level *= 0.125;
-            }
+            // Which uncached leaves to evaluate now: everything at or above the guaranteed level (computeLevel) is needed
+            // work; `speculate` octaves (factors of 8) below it are pre-evaluated so later levels find their results cached.
+            const double tSel0 = nowMs();
+            double level = std::min(applyLevel_, queue_.empty() ? 0.0 : queue_.top().second);
+            for (uint32_t k = 0; k < o_.speculate; ++k) level *= 0.125;
+            t_.stats.host_select_ms += nowMs() - tSel0;
+            const double tTask0 = nowMs();
             std::vector<uint64_t> later;
             for (uint64_t idx : pending_)
             {
@@ -236,6 +258,7 @@ namespace hpsdf
             }
             groupBegin[kMaxDegree + 1] = ti;
 
+            t_.stats.host_tasks_ms += nowMs() - tTask0;
             // ---- 2. upload, launch one kernel per degree present (this rank's shard), gather across ranks ----------
             HPSDF_CUDA(cudaMemcpyAsync(dTasks_.p, hTasks_.p, nTasks * sizeof(FitTask), cudaMemcpyHostToDevice, stream_));
             HPSDF_CUDA(cudaEventRecord(ev0_, stream_));
@@ -276,7 +299,9 @@ namespace hpsdf
                 if (cs != HPSDF_OK) return cs;
             }
             HPSDF_CUDA(cudaMemcpyAsync(hRecs_.p, dRecs_.p, nTasks * sizeof(FitRecord), cudaMemcpyDeviceToHost, stream_));
+            const double tWait0 = nowMs();
             HPSDF_CUDA(cudaStreamSynchronize(stream_));
+            t_.stats.device_wait_ms += nowMs() - tWait0;
             float ms = 0.0f;
             cudaEventElapsedTime(&ms, ev0_, ev1_);
             t_.stats.fit_kernel_ms += ms;
@@ -305,105 +330,163 @@ namespace hpsdf
             return HPSDF_OK;
         }
 
-        // The reference's scheduler loop (Octree.cpp:213-302) in strict-greedy form, driven by cached job results.
+        // Guaranteed level. Take the queue in decreasing error order e1 >= e2 >= ...: entry k is certainly popped by the
+        // strict greedy loop before it terminates if total - (e1 + ... + e_{k-1}) >= threshold, because popping an entry and
+        // any of its descendants lowers the total by at most that entry's error. So is every descendant with a larger
+        // error than e_k (the loop pops it before e_k). Entries at or above the level can therefore be applied in ANY
+        // order without changing which leaves end up refined; only node numbering and the last bits of the running total
+        // depend on the order. Computed from the per-exponent histogram, exact inside the bucket where the bound runs out.
+        void Builder::computeLevel()
+        {
+            const double tSel0 = nowMs();
+            const double inf = std::numeric_limits<double>::infinity();
+            const double thr = cfg_.target_error_threshold;
+            levelLogStart_ = t_.applyLog.size();
+            applyLevel_ = inf;
+            double remaining = checkValue();
+            if (o_.strict_order || !(remaining >= thr) || queue_.empty()) { t_.stats.host_select_ms += nowMs() - tSel0; return; }
+            int b = kBuckets - 1, crossing = -1;
+            for (; b >= 0; --b)
+            {
+                if (!bucketCount_[b]) continue;
+                const double after = remaining - bucketSum_[b] * (1.0 + 1e-9);
+                if (after >= thr) { remaining = after; applyLevel_ = std::ldexp(0.5, b - 1100); continue; }   // whole bucket guaranteed
+                crossing = b;
+                break;
+            }
+            if (crossing >= 0)
+            {
+                std::vector<double> errs;
+                for (const auto& e : queue_.entries()) if (bucketOf(e.second) == crossing) errs.push_back(e.second);
+                std::sort(errs.begin(), errs.end(), std::greater<double>());
+                size_t k = 0;
+                for (; k < errs.size() && remaining >= thr; ++k) remaining -= errs[k] * (1.0 + 1e-9);
+                // keep whole groups of equal errors together: never split a tie group out of order
+                while (k > 0 && k < errs.size() && errs[k] == errs[k - 1]) --k;
+                if (k > 0) applyLevel_ = errs[k - 1];
+            }
+            t_.stats.host_select_ms += nowMs() - tSel0;
+        }
+
+        // One applied refinement: the body of the reference's output-drain loop (Octree.cpp:245-297) for a popped leaf.
+        void Builder::applyJob(uint64_t idx, double err)
+        {
+            Job& j = jobs_[jobOf_[idx]];
+            jobOf_[idx] = -1;
+            const uint32_t p = nodes_[idx].degree, depth = nodes_[idx].depth;
+            if (!j.coarse)
+            {
+                if (j.doH)
+                {
+                    double maxNew = 0.0;
+                    for (int i = 0; i < 8; ++i) maxNew = std::max<double>(maxNew, j.hErr[i]);       // Octree.cpp:821
+                    j.hImp = (1.0 / (7.0 * coeffCount(p))) * (err - 8.0 * maxNew);                  // Octree.cpp:825
+                }
+                if (j.doP) j.pImp = (1.0 / (coeffCount(p + 1) - coeffCount(p))) * (err - 8.0 * j.pErr);   // Octree.cpp:854
+            }
+            // Octree.cpp:600-601 with BASIS_MAX_DEGREE-1 -> max_degree, TREE_MAX_DEPTH -> max_depth. A coarse cell always
+            // takes its degree-2 fit (the reference is undefined if that fit's error is exactly 0).
+            const bool refineP = j.coarse || (p < o_.max_degree && (depth == o_.max_depth || j.pImp > j.hImp));
+            const bool refineH = depth < o_.max_depth && !refineP;
+
+            if (!j.coarse && j.doH && j.doP)
+            {
+                const double mag = std::max(std::fabs(j.pImp), std::fabs(j.hImp));
+                const double margin = mag > 0.0 ? std::fabs(j.pImp - j.hImp) / mag : 0.0;
+                if (margin <= 1e-9)
+                {
+                    hpsdf_decision_log_entry e{};
+                    e.node_idx = idx; e.depth = depth; e.degree = p; e.chose_p = refineP; e.kind = 0;
+                    for (int a = 0; a < 3; ++a) e.centre[a] = (nodes_[idx].mn[a] + nodes_[idx].mx[a]) / 2.0f;
+                    e.p_improvement = j.pImp; e.h_improvement = j.hImp; e.relative_margin = margin;
+                    t_.decisionLog.push_back(e);
+                    t_.stats.near_tie_decisions++;
+                }
+            }
+
+            if (refineP)
+            {
+                total_ += (j.pErr - err);                                                            // Octree.cpp:257
+                if (j.coarse) unfitted_--; else exactSum_ -= (long double)err;
+                exactSum_ += (long double)j.pErr;
+                nodes_[idx].slot   = j.pSlot;                                                        // Octree.cpp:286
+                nodes_[idx].degree = (uint8_t)(j.coarse ? kCoarseDegree : p + 1);
+                errOf_[idx] = j.pErr;
+                qPush(idx, j.pErr);                                                                  // Octree.cpp:289-290
+                pending_.push_back(idx);
+                t_.stats.jobs_applied_p++;
+                t_.applyLog.push_back({ idx, 0u, p, err, j.pErr, j.pImp, j.hImp, checkValue() });
+            }
+            else if (refineH)
+            {
+                nodes_[idx].degree = kInternalTag;                                                   // Octree.cpp:265-272
+                subdivide(idx);
+                total_ -= err;
+                exactSum_ -= (long double)err;
+                jobOf_.resize(nodes_.size(), -1);
+                errOf_.resize(nodes_.size(), 0.0);
+                inQueue_.resize(nodes_.size(), 0);
+                double mx = 0.0;
+                for (uint32_t i = 0; i < 8; ++i)
+                {
+                    const uint64_t c = nodes_[idx].child + i;                                        // Octree.cpp:275-290
+                    total_ += j.hErr[i];
+                    exactSum_ += (long double)j.hErr[i];
+                    nodes_[c].slot = j.hSlot[i];
+                    nodes_[c].degree = (uint8_t)p;
+                    errOf_[c] = j.hErr[i];
+                    qPush(c, j.hErr[i]);
+                    pending_.push_back(c);
+                    mx = std::max(mx, j.hErr[i]);
+                }
+                t_.stats.jobs_applied_h++;
+                t_.applyLog.push_back({ idx, 1u, p, err, mx, j.pImp, j.hImp, checkValue() });
+            }
+            // else: degree and depth both at their maximum — the node leaves the queue (Octree.cpp:643-655)
+
+            if (refineP || refineH)
+            {
+                lastApplied_.node_idx = idx; lastApplied_.depth = depth; lastApplied_.degree = p; lastApplied_.chose_p = refineP;
+                lastApplied_.kind = 1; lastApplied_.p_improvement = j.pImp; lastApplied_.h_improvement = j.hImp;
+                for (int a = 0; a < 3; ++a) lastApplied_.centre[a] = (nodes_[idx].mn[a] + nodes_[idx].mx[a]) / 2.0f;
+                totalBeforeLast_ = lastTotal_; lastTotal_ = checkValue();
+            }
+            if (cfg_.enable_logging)                                                                 // Octree.cpp:292-296
+                printf("\n%.11f\t%zu\t%f, %f, %f", total_, nodes_.size(), (double)(nodes_[idx].mn[0] + nodes_[idx].mx[0]) / 2.0,
+                       (double)(nodes_[idx].mn[1] + nodes_[idx].mx[1]) / 2.0, (double)(nodes_[idx].mn[2] + nodes_[idx].mx[2]) / 2.0);
+        }
+
+        // The reference's scheduler loop (Octree.cpp:213-302) driven by cached job results. Entries at or above the
+        // guaranteed level are applied as soon as their result is cached, stepping over uncached ones (which wait for the
+        // next batch); below the level the loop is the strict one: termination check, then pop the top if it is cached.
+        // Every time the strict part is reached the state is one the sequential greedy loop also passes through.
         bool Builder::replay()
         {
             const double thr = cfg_.target_error_threshold;
+            deferred_.clear();
+            bool done = false;
             for (;;)
             {
-                if (checkValue() < thr || queue_.empty()) return true;                                   // Octree.cpp:216
+                if (queue_.empty()) { done = deferred_.empty(); break; }
                 const std::pair<uint64_t, double> top = queue_.top();                                    // Octree.cpp:231
                 const uint64_t idx = top.first;
-                if (idx >= jobOf_.size() || jobOf_[idx] < 0) return false;                               // no cached result: next round
-                queue_.pop();
-                inQueue_[idx] = 0;
-                Job& j = jobs_[jobOf_[idx]];
-                jobOf_[idx] = -1;
-                const double err = top.second;
-                const uint32_t p = nodes_[idx].degree, depth = nodes_[idx].depth;
-                if (!j.coarse)
+                const bool cached = idx < jobOf_.size() && jobOf_[idx] >= 0;
+                if (top.second >= applyLevel_)
                 {
-                    if (j.doH)
-                    {
-                        double maxNew = 0.0;
-                        for (int i = 0; i < 8; ++i) maxNew = std::max<double>(maxNew, j.hErr[i]);       // Octree.cpp:821
-                        j.hImp = (1.0 / (7.0 * coeffCount(p))) * (err - 8.0 * maxNew);                  // Octree.cpp:825
-                    }
-                    if (j.doP) j.pImp = (1.0 / (coeffCount(p + 1) - coeffCount(p))) * (err - 8.0 * j.pErr);   // Octree.cpp:854
+                    qPop();
+                    if (cached) applyJob(idx, top.second); else deferred_.push_back(top);
+                    continue;
                 }
-                // Octree.cpp:600-601 with BASIS_MAX_DEGREE-1 -> max_degree, TREE_MAX_DEPTH -> max_depth. A coarse cell always
-                // takes its degree-2 fit (the reference is undefined if that fit's error is exactly 0).
-                const bool refineP = j.coarse || (p < o_.max_degree && (depth == o_.max_depth || j.pImp > j.hImp));
-                const bool refineH = depth < o_.max_depth && !refineP;
-
-                if (!j.coarse && j.doH && j.doP)
-                {
-                    const double mag = std::max(std::fabs(j.pImp), std::fabs(j.hImp));
-                    const double margin = mag > 0.0 ? std::fabs(j.pImp - j.hImp) / mag : 0.0;
-                    if (margin <= 1e-9)
-                    {
-                        hpsdf_decision_log_entry e{};
-                        e.node_idx = idx; e.depth = depth; e.degree = p; e.chose_p = refineP; e.kind = 0;
-                        for (int a = 0; a < 3; ++a) e.centre[a] = (nodes_[idx].mn[a] + nodes_[idx].mx[a]) / 2.0f;
-                        e.p_improvement = j.pImp; e.h_improvement = j.hImp; e.relative_margin = margin;
-                        t_.decisionLog.push_back(e);
-                        t_.stats.near_tie_decisions++;
-                    }
-                }
-
-                if (refineP)
-                {
-                    total_ += (j.pErr - err);                                                            // Octree.cpp:257
-                    if (j.coarse) unfitted_--; else exactSum_ -= (long double)err;
-                    exactSum_ += (long double)j.pErr;
-                    nodes_[idx].slot   = j.pSlot;                                                        // Octree.cpp:286
-                    nodes_[idx].degree = (uint8_t)(j.coarse ? kCoarseDegree : p + 1);
-                    errOf_[idx] = j.pErr;
-                    queue_.push({ idx, j.pErr });                                                        // Octree.cpp:289-290
-                    inQueue_[idx] = 1;
-                    pending_.push_back(idx);
-                    t_.stats.jobs_applied_p++;
-                    t_.applyLog.push_back({ idx, 0u, p, err, j.pErr, j.pImp, j.hImp, checkValue() });
-                }
-                else if (refineH)
-                {
-                    nodes_[idx].degree = kInternalTag;                                                   // Octree.cpp:265-272
-                    subdivide(idx);
-                    total_ -= err;
-                    exactSum_ -= (long double)err;
-                    jobOf_.resize(nodes_.size(), -1);
-                    errOf_.resize(nodes_.size(), 0.0);
-                    inQueue_.resize(nodes_.size(), 0);
-                    for (uint32_t i = 0; i < 8; ++i)
-                    {
-                        const uint64_t c = nodes_[idx].child + i;                                        // Octree.cpp:275-290
-                        total_ += j.hErr[i];
-                        exactSum_ += (long double)j.hErr[i];
-                        nodes_[c].slot = j.hSlot[i];
-                        nodes_[c].degree = (uint8_t)p;
-                        errOf_[c] = j.hErr[i];
-                        queue_.push({ c, j.hErr[i] });
-                        inQueue_[c] = 1;
-                        pending_.push_back(c);
-                    }
-                    t_.stats.jobs_applied_h++;
-                    double mx = 0.0;
-                    for (int i = 0; i < 8; ++i) mx = std::max(mx, j.hErr[i]);
-                    t_.applyLog.push_back({ idx, 1u, p, err, mx, j.pImp, j.hImp, checkValue() });
-                }
-                // else: degree and depth both at their maximum — the node leaves the queue (Octree.cpp:643-655)
-
-                if (refineP || refineH)
-                {
-                    lastApplied_.node_idx = idx; lastApplied_.depth = depth; lastApplied_.degree = p; lastApplied_.chose_p = refineP;
-                    lastApplied_.kind = 1; lastApplied_.p_improvement = j.pImp; lastApplied_.h_improvement = j.hImp;
-                    for (int a = 0; a < 3; ++a) lastApplied_.centre[a] = (nodes_[idx].mn[a] + nodes_[idx].mx[a]) / 2.0f;
-                    totalBeforeLast_ = lastTotal_; lastTotal_ = checkValue();
-                }
-                if (cfg_.enable_logging)                                                                 // Octree.cpp:292-296
-                    printf("\n%.11f\t%zu\t%f, %f, %f", total_, nodes_.size(), (double)(nodes_[idx].mn[0] + nodes_[idx].mx[0]) / 2.0,
-                           (double)(nodes_[idx].mn[1] + nodes_[idx].mx[1]) / 2.0, (double)(nodes_[idx].mn[2] + nodes_[idx].mx[2]) / 2.0);
+                if (!deferred_.empty()) break;            // entries above the level still wait for their results
+                if (checkValue() < thr) { done = true; break; }                                          // Octree.cpp:216
+                if (!cached) break;                       // no cached result: next round
+                qPop();
+                applyJob(idx, top.second);                // strict step; the state after it is a sequential-greedy state
+                computeLevel();
             }
+            for (const auto& d : deferred_) qPush(d.first, d.second);
+            if (!done && deferred_.empty() && queue_.empty()) done = true;
+            return done;
         }
 
         // Near-threshold divergence log (BASELINE north_star): the greedy loop stops in the middle of a run of leaves whose
@@ -413,7 +496,9 @@ namespace hpsdf
         void Builder::logCutTies()
         {
             if (t_.applyLog.empty() || queue_.empty()) return;
-            const double eLast = t_.applyLog.back().initial_err;
+            // the sequential loop's last pop is the smallest-error entry applied since the last sequential state
+            double eLast = t_.applyLog.back().initial_err;
+            for (size_t k = std::min(levelLogStart_, t_.applyLog.size() - 1); k < t_.applyLog.size(); ++k) eLast = std::min(eLast, t_.applyLog[k].initial_err);
             if (!(eLast > 0.0) || std::abs(eLast - kInitialErr) < 1e-9) return;
             const double band = 1e-9 * eLast;
             auto entry = [&](uint64_t idx, uint32_t degree, uint32_t kind, double err)
@@ -425,10 +510,10 @@ namespace hpsdf
                 t_.decisionLog.push_back(e);
             };
             size_t refined = 0, unrefined = 0;
-            for (size_t k = t_.applyLog.size(); k-- > 0;)
+            for (size_t k = t_.applyLog.size(); k-- > std::min(levelLogStart_, t_.applyLog.size() - 1);)
             {
                 const hpsdf_apply_log_entry& a = t_.applyLog[k];
-                if (std::fabs(a.initial_err - eLast) > band) break;
+                if (std::fabs(a.initial_err - eLast) > band) continue;
                 entry(a.node_idx, a.degree, 2u, a.initial_err);
                 t_.decisionLog.back().chose_p = a.kind == 0;
                 ++refined;
@@ -501,10 +586,11 @@ namespace hpsdf
             errOf_.assign(nodes_.size(), kInitialErr);
             jobOf_.assign(nodes_.size(), -1);
             inQueue_.assign(nodes_.size(), 0);
-            for (uint64_t idx : pending_) inQueue_[idx] = 1;
+            for (uint64_t idx : pending_) qPush(idx, kInitialErr);                                      // Octree.cpp:176-177
             total_ = std::pow(8, 4) * kInitialErr;                                                      // Octree.cpp:212
             unfitted_ = (long)queue_.size();
             lastTotal_ = totalBeforeLast_ = total_;
+            computeLevel();
 
             double replayMs = 0.0;
             for (;;)
@@ -517,7 +603,9 @@ namespace hpsdf
                 if (done) break;
                 if (pending_.empty()) { setLastError("internal: replay stalled with nothing to evaluate"); st = HPSDF_ERR_CUDA; break; }
             }
+            const double tPack0 = nowMs();
             if (st == HPSDF_OK) st = pack();
+            t_.stats.pack_ms = nowMs() - tPack0;
             if (st == HPSDF_OK)
             {
                 t_.stats.total_error = o_.total_mode == HPSDF_TOTAL_EXACT_SUM ? (double)exactSum_ : total_;
@@ -539,7 +627,9 @@ namespace hpsdf
                     t_.stats.continuity_ms = nowMs() - c0;
                 }
             }
+            const double tFin0 = nowMs();
             if (st == HPSDF_OK) st = finalizeQueryStructures(t_, stream_);
+            t_.stats.finalize_ms = nowMs() - tFin0;
             if (st == HPSDF_OK)
             {
                 uint64_t leaves = 0;

@@ -18,7 +18,7 @@
  * fallback: every compute entry point fails with HPSDF_ERR_NO_DEVICE when no CUDA device is present.
  *
  * The C++ facade with the reference's names (SDF::Config, SDF::Octree, MemoryBlock) is
- * include/HP/Octree.h of THIS repository; it forwards to these functions.
+ * include/hpsdf.hpp of THIS repository; it forwards to these functions.
  */
 #ifndef HPSDF_H
 #define HPSDF_H
@@ -113,7 +113,9 @@ typedef struct hpsdf_build_opts
     uint32_t cg_max_iterations;   /* 0 = 2n, Eigen's default */
     double   cg_tolerance;        /* relative residual; 0 = the reference's (double)1e-6f (Octree.cpp:1754) */
     int32_t  device;              /* CUDA device ordinal; -1 = current device */
-    uint32_t speculate;           /* 0 = one job per leaf per round; 1 = also pre-evaluate the follow-up job of the chosen branch */
+    uint32_t speculate;           /* octaves (factors of 8 in error) below the guaranteed level whose jobs are pre-evaluated */
+    uint32_t strict_order;        /* 1 = apply jobs in exactly the sequential greedy order (node numbering = the CPU checker's);
+                                     0 = entries certain to be refined are applied as soon as their results are cached */
     hpsdf_comm* comm;             /* NULL = single GPU; else frontier jobs are sharded over the communicator's ranks */
     void*    stream;              /* cudaStream_t to run on; NULL = an internal non-blocking stream */
 } hpsdf_build_opts;
@@ -224,6 +226,10 @@ typedef struct hpsdf_build_stats
     double   fit_kernel_ms;       /* device time in fit kernels (CUDA events on the build stream) */
     double   continuity_ms;       /* device time of face assembly + CG */
     double   host_replay_ms;      /* host time in the greedy replay */
+    double   host_select_ms;      /* host time choosing which leaves to evaluate each round */
+    double   host_tasks_ms;       /* host time building fit task lists */
+    double   device_wait_ms;      /* host time blocked on the build stream (kernels + copies) */
+    double   pack_ms, finalize_ms;/* ReallocCoeffs gather; Query structures */
     double   total_ms;            /* wall time of hpsdf_create */
     uint64_t cg_iterations;
     double   cg_relative_residual;

@@ -1,0 +1,128 @@
+// facade_test.cpp — the reference's own unit tests (Source/Tests/HPUnitTests.cpp:46-316) re-expressed against the C++
+// facade include/hpsdf.hpp: same workloads, same acceptance tolerances (|Query - analytic| <= 0.01, <= 0.05 for the SDF
+// operations). The lambdas of the reference become SDF::Program objects (the device SDF evaluator).
+// Build: g++ -std=c++17 -I include tests/cpp/facade_test.cpp -L <pkg>/lib -lhpsdf ; run on a GPU box.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <random>
+#include <vector>
+#include "hpsdf.hpp"
+
+using SDF::Vec3d;
+
+static double sphere(const Vec3d& p, double cx, double cy, double cz, double r)
+{
+    return std::sqrt((p.x() - cx) * (p.x() - cx) + (p.y() - cy) * (p.y() - cy) + (p.z() - cz) * (p.z() - cz)) - r;
+}
+
+static std::vector<double> samples(size_t n, double lo, double hi, unsigned seed)
+{
+    std::mt19937_64 g(seed);
+    std::uniform_real_distribution<double> u(lo, hi);
+    std::vector<double> v(3 * n);
+    for (double& x : v) x = u(g);
+    return v;
+}
+
+template <class F>
+static bool within(const SDF::Octree& t, const std::vector<double>& pts, F truth, double tol)
+{
+    std::vector<double> out(pts.size() / 3);
+    t.Query(pts.data(), out.size(), out.data());
+    for (size_t i = 0; i < out.size(); ++i)
+    {
+        const Vec3d p{ { pts[3 * i], pts[3 * i + 1], pts[3 * i + 2] } };
+        if (std::abs(out[i] - truth(p)) > tol) { std::printf("  point %zu: got %.6f want %.6f\n", i, out[i], truth(p)); return false; }
+    }
+    return true;
+}
+
+static SDF::Config baseConfig(bool continuity)
+{
+    SDF::Config c;
+    c.targetErrorThreshold       = std::pow(10, -8);
+    c.nearnessWeighting.type     = SDF::Config::NearnessWeighting::Polynomial;
+    c.nearnessWeighting.strength = 3.0;
+    c.continuity.enforce         = continuity;
+    c.continuity.strength        = 8.0;
+    c.threadCount                = std::thread::hardware_concurrency() ? std::thread::hardware_concurrency() : 1;
+    return c;
+}
+
+int main()
+{
+    const auto pts = samples(1000000, -0.5, 0.5, 1);
+    auto sphereF = [](const Vec3d& p) { return sphere(p, 0.25, 0, 0, 0.5); };
+    SDF::Program sphereProg;
+    sphereProg.Sphere(0.25, 0, 0, 0.5);
+    int failed = 0;
+    auto report = [&](const char* name, bool ok) { std::printf("%s: %s\n", name, ok ? "Passed" : "Failed"); failed += !ok; };
+
+    {   // TestOctreeCreation (HPUnitTests.cpp:46-77)
+        SDF::Octree t;
+        t.Create(baseConfig(false), sphereProg);
+        report("Octree Creation", within(t, pts, sphereF, 0.01));
+    }
+    {   // TestOctreeContinuity (:80-112)
+        SDF::Octree t;
+        t.Create(baseConfig(true), sphereProg);
+        report("Octree Continuity", within(t, pts, sphereF, 0.01));
+    }
+    {   // TestOctreeSerialisation (:115-154): Create -> ToMemoryBlock -> destroy -> FromMemoryBlock -> free block
+        MemoryBlock b;
+        {
+            SDF::Octree t;
+            t.Create(baseConfig(true), sphereProg);
+            b = t.ToMemoryBlock();
+        }
+        SDF::Octree t2;
+        t2.FromMemoryBlock(b);
+        free(b.ptr);
+        report("Octree Serialisation", within(t2, pts, sphereF, 0.01));
+    }
+    {   // TestOctreeCopying (:157-204): copy-construct, then move-assign
+        SDF::Octree t;
+        t.Create(baseConfig(false), sphereProg);
+        SDF::Octree copy(t);
+        t.Clear();
+        bool ok = within(copy, pts, sphereF, 0.01);
+        SDF::Octree moved;
+        moved = std::move(copy);
+        ok = ok && within(moved, pts, sphereF, 0.01);
+        report("Octree Copying", ok);
+    }
+    {   // TestOctreeSDFOperations (:207-282): nearness None, second sphere, tolerance 0.05
+        SDF::Config c = baseConfig(false);
+        c.nearnessWeighting.type = SDF::Config::NearnessWeighting::None;
+        SDF::Program other;
+        other.Sphere(-0.25, 0, 0, 0.3);
+        auto otherF = [](const Vec3d& p) { return sphere(p, -0.25, 0, 0, 0.3); };
+        bool ok = true;
+        { SDF::Octree t; t.Create(c, sphereProg); t.UnionSDF(other);     ok = ok && within(t, pts, [&](const Vec3d& p) { return std::min(sphereF(p), otherF(p)); }, 0.05); }
+        { SDF::Octree t; t.Create(c, sphereProg); t.IntersectSDF(other); ok = ok && within(t, pts, [&](const Vec3d& p) { return std::max(sphereF(p), otherF(p)); }, 0.05); }
+        { SDF::Octree t; t.Create(c, sphereProg); t.SubtractSDF(other);  ok = ok && within(t, pts, [&](const Vec3d& p) { return std::max(-sphereF(p), otherF(p)); }, 0.05); }
+        report("SDF Operations", ok);
+    }
+    {   // TestOctreeCustomDomains (:285-316): root [-0.25,5]^3, radius 0.75, continuity on
+        SDF::Config c = baseConfig(true);
+        for (int i = 0; i < 3; ++i) { c.root.lo[i] = -0.25f; c.root.hi[i] = 5.0f; }
+        SDF::Program p;
+        p.Sphere(2.0, 2.0, 2.0, 0.75);
+        SDF::Octree t;
+        t.Create(c, p);
+        const auto big = samples(1000000, -0.25, 5.0, 2);
+        report("Custom Domains", within(t, big, [](const Vec3d& q) { return sphere(q, 2.0, 2.0, 2.0, 0.75); }, 0.01));
+        const SDF::Box3f root = t.GetRootAABB();
+        report("GetRootAABB", root.lo[0] == -0.25f && root.hi[2] == 5.0f);
+    }
+    {   // error behaviour: out-of-domain Query is DBL_MAX (Octree.cpp:668-671); the std::function Create is refused
+        SDF::Octree t;
+        t.Create(baseConfig(false), sphereProg);
+        bool ok = t.Query(Vec3d{ { 0.75, 0, 0 } }) == std::numeric_limits<double>::max();
+        try { t.Create(baseConfig(false), [](const Vec3d&, unsigned long) { return 0.0; }); ok = false; } catch (const SDF::Error& e) { ok = ok && e.status == HPSDF_ERR_UNSUPPORTED; }
+        report("Error behaviour", ok);
+    }
+    std::printf(failed ? "Some tests failed!\n" : "All tests passed!\n");
+    return failed;
+}
