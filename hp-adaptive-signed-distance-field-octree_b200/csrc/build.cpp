@@ -88,6 +88,8 @@ namespace hpsdf
             double                   applyLevel_ = std::numeric_limits<double>::infinity();   // entries >= this are certain to be popped
             size_t                   levelLogStart_ = 0;     // first apply-log entry of the current level
             std::vector<std::pair<uint64_t, double>> deferred_;
+            bool                     levelTried_ = false;
+            double                   evalLevel_ = 0.0;       // guaranteed level used to choose what to evaluate (also in strict mode)
             std::vector<int32_t>     jobOf_;        // per node: index into jobs_, -1 = no cached result
             std::vector<double>      errOf_;        // per node: its current (weighted) error
             std::vector<uint8_t>     inQueue_;      // per node: 1 while the leaf is in the priority queue
@@ -191,10 +193,14 @@ namespace hpsdf
             // the replay stalls less often. Leaves below stay pending until the level reaches them.
             // Which uncached leaves to evaluate now: everything at or above the guaranteed level (computeLevel) is needed
             // work; `speculate` octaves (factors of 8) below it are pre-evaluated so later levels find their results cached.
-            const double tSel0 = nowMs();
-            double level = std::min(applyLevel_, queue_.empty() ? 0.0 : queue_.top().second);
+            if (o_.strict_order || applyLevel_ == std::numeric_limits<double>::infinity())
+            {
+                const double keep = applyLevel_;
+                computeLevel();                 // refresh evalLevel_ for the current state
+                if (o_.strict_order || keep != std::numeric_limits<double>::infinity()) applyLevel_ = keep;
+            }
+            double level = std::min(evalLevel_, queue_.empty() ? 0.0 : queue_.top().second);
             for (uint32_t k = 0; k < o_.speculate; ++k) level *= 0.125;
-            t_.stats.host_select_ms += nowMs() - tSel0;
             const double tTask0 = nowMs();
             std::vector<uint64_t> later;
             for (uint64_t idx : pending_)
@@ -344,7 +350,8 @@ namespace hpsdf
             levelLogStart_ = t_.applyLog.size();
             applyLevel_ = inf;
             double remaining = checkValue();
-            if (o_.strict_order || !(remaining >= thr) || queue_.empty()) { t_.stats.host_select_ms += nowMs() - tSel0; return; }
+            evalLevel_ = queue_.empty() ? 0.0 : queue_.top().second;
+            if (!(remaining >= thr) || queue_.empty()) { t_.stats.host_select_ms += nowMs() - tSel0; return; }
             int b = kBuckets - 1, crossing = -1;
             for (; b >= 0; --b)
             {
@@ -365,6 +372,8 @@ namespace hpsdf
                 while (k > 0 && k < errs.size() && errs[k] == errs[k - 1]) --k;
                 if (k > 0) applyLevel_ = errs[k - 1];
             }
+            evalLevel_ = std::min(applyLevel_, evalLevel_);
+            if (o_.strict_order) applyLevel_ = inf;          // strict mode: the level only steers what is evaluated
             t_.stats.host_select_ms += nowMs() - tSel0;
         }
 
@@ -479,11 +488,24 @@ namespace hpsdf
                 }
                 if (!deferred_.empty()) break;            // entries above the level still wait for their results
                 if (checkValue() < thr) { done = true; break; }                                          // Octree.cpp:216
-                if (!cached) break;                       // no cached result: next round
-                qPop();
-                applyJob(idx, top.second);                // strict step; the state after it is a sequential-greedy state
-                computeLevel();
+                if (cached)
+                {
+                    qPop();
+                    applyJob(idx, top.second);            // strict step; the state after it is a sequential-greedy state
+                    applyLevel_ = std::numeric_limits<double>::infinity();      // a level is only valid for the state it was computed in
+                    continue;
+                }
+                // the top has no cached result. This is a sequential-greedy state: find the level down to which entries are
+                // certain to be popped, so the loop can go on past the top (once per stall)
+                if (!o_.strict_order && applyLevel_ == std::numeric_limits<double>::infinity() && !levelTried_)
+                {
+                    computeLevel();
+                    levelTried_ = true;
+                    if (top.second >= applyLevel_) continue;
+                }
+                break;
             }
+            levelTried_ = false;
             for (const auto& d : deferred_) qPush(d.first, d.second);
             if (!done && deferred_.empty() && queue_.empty()) done = true;
             return done;
@@ -500,7 +522,9 @@ namespace hpsdf
             double eLast = t_.applyLog.back().initial_err;
             for (size_t k = std::min(levelLogStart_, t_.applyLog.size() - 1); k < t_.applyLog.size(); ++k) eLast = std::min(eLast, t_.applyLog[k].initial_err);
             if (!(eLast > 0.0) || std::abs(eLast - kInitialErr) < 1e-9) return;
-            const double band = 1e-9 * eLast;
+            // errors of the members of a symmetric group agree to ~1e-10 relative (they are sums of squares of top-shell
+            // coefficients that carry ~1e-16 |c000| of rounding each); the same noise separates two implementations
+            const double band = 3e-9 * eLast;
             auto entry = [&](uint64_t idx, uint32_t degree, uint32_t kind, double err)
             {
                 hpsdf_decision_log_entry e{};
@@ -510,7 +534,7 @@ namespace hpsdf
                 t_.decisionLog.push_back(e);
             };
             size_t refined = 0, unrefined = 0;
-            for (size_t k = t_.applyLog.size(); k-- > std::min(levelLogStart_, t_.applyLog.size() - 1);)
+            for (size_t k = t_.applyLog.size(); k-- > 0;)
             {
                 const hpsdf_apply_log_entry& a = t_.applyLog[k];
                 if (std::fabs(a.initial_err - eLast) > band) continue;

@@ -45,6 +45,8 @@ namespace hpsdf
         constexpr int N2 = N * N;
         constexpr int P2 = pairCount(D);
         extern __shared__ double smem[];
+        __shared__ SdfProgramSmem sProg;
+        stageProgram(sProg, prog);
         double* sQ  = smem;                    // Q[c][k]
         double* sR  = sQ + (D + 1) * N;        // roots
         double* sZ  = sR + N;                  // user-space z of sample k
@@ -77,7 +79,7 @@ namespace hpsdf
             #pragma unroll 1
             for (int k = 0; k < N; ++k)
             {
-                const double f = sdfEval<EXT>(prog, X, Y, sZ[k]);
+                const double f = sdfEval<EXT>(sProg, X, Y, sZ[k]);
                 #pragma unroll
                 for (int c = 0; c <= D; ++c) acc[c] = fma(f, sQ[c * N + k], acc[c]);
             }
@@ -201,8 +203,11 @@ namespace hpsdf
     // ---- program evaluation at arbitrary points (hpsdf_sdf_eval) and the FP64 peak probe ---------------------------
     __global__ void sdfEvalKernel(const SdfProgramDev prog, const double* __restrict__ xyz, size_t n, double* __restrict__ out)
     {
+        __shared__ SdfProgramSmem sProg;
+        stageProgram(sProg, prog);
+        __syncthreads();
         const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-        if (i < n) out[i] = sdfEval<true>(prog, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        if (i < n) out[i] = sdfEval<true>(sProg, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
     }
 
     cudaError_t launchSdfEval(const SdfProgramDev& prog, const double* dXyz, size_t n, double* dOut, cudaStream_t stream)

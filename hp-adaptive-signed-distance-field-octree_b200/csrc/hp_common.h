@@ -23,6 +23,8 @@ namespace hpsdf
     constexpr double   kInitialErr  = 100.0;                 // INITIAL_NODE_ERR (Octree.h:89)
     constexpr int      kCoarseDepth = 4, kCoarseDegree = 2;  // UniformlyRefine (Octree.cpp:115-116)
     constexpr int      kMaxCoeffs   = 455;
+    // internal opcodes: HPSDF_PRIM_TORUS with its axis parameter resolved when the program is uploaded
+    constexpr uint32_t kOpTorusX = 48, kOpTorusY = 49, kOpTorusZ = 50;
 
     // LegendreCoeffientCount (Utility.h:87-106). The reference evaluates (u32)((1.0/6.0)*(i+1)*(i+2)*(i+3)) in f64, which
     // truncates to 83 (not 84) at i = 6. The value is part of the MemoryBlock contract (a degree-6 leaf stores 83
@@ -52,7 +54,7 @@ namespace hpsdf
         {
             case HPSDF_PRIM_SPHERE:  return 10.0;   // 3 sub, 3 mul, 2 add, sqrt, sub
             case HPSDF_PRIM_BOX:     return 22.0;   // 3 sub, 3 abs, 3 sub, 3 max, 3 mul, 2 add, sqrt, 2 max, min, add
-            case HPSDF_PRIM_TORUS:   return 13.0;   // 3 sub, 2 mul, add, sqrt, sub, 2 mul, add, sqrt, sub
+            case HPSDF_PRIM_TORUS: case kOpTorusX: case kOpTorusY: case kOpTorusZ: return 13.0;   // 3 sub, 2 mul, add, sqrt, sub, 2 mul, add, sqrt, sub
             case HPSDF_PRIM_CAPSULE: return 32.0;   // 6 sub, 2 dot (5 each), div, 2 clamp, 3 fma (6), 5, sqrt, sub
             case HPSDF_PRIM_PLANE:   return 6.0;
             case HPSDF_OP_NEGATE:    return 1.0;

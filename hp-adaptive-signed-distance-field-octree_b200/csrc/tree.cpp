@@ -122,7 +122,14 @@ namespace hpsdf
             memcpy(o.p, in.p, sizeof(o.p));
             switch (in.op)
             {
-                case HPSDF_PRIM_SPHERE: case HPSDF_PRIM_BOX: case HPSDF_PRIM_TORUS: case HPSDF_PRIM_CAPSULE: case HPSDF_PRIM_PLANE:
+                case HPSDF_PRIM_TORUS:
+                {
+                    const int axis = (int)in.p[5];
+                    if (axis < 0 || axis > 2 || (double)axis != in.p[5]) { setLastError("TORUS axis must be 0, 1 or 2"); return HPSDF_ERR_INVALID_ARG; }
+                    o.op = axis == 0 ? kOpTorusX : axis == 1 ? kOpTorusY : kOpTorusZ;
+                    ++sp; break;
+                }
+                case HPSDF_PRIM_SPHERE: case HPSDF_PRIM_BOX: case HPSDF_PRIM_CAPSULE: case HPSDF_PRIM_PLANE:
                     ++sp; break;
                 case HPSDF_PRIM_OCTREE:
                 {

@@ -148,7 +148,7 @@ enum
     HPSDF_OP_NEGATE    = 67   /* -a                                                      */
 };
 
-#define HPSDF_PROGRAM_MAX_INSTR 32
+#define HPSDF_PROGRAM_MAX_INSTR 16
 #define HPSDF_PROGRAM_MAX_STACK 8
 
 typedef struct hpsdf_sdf_instr

@@ -104,15 +104,18 @@ int main()
         { SDF::Octree t; t.Create(c, sphereProg); t.SubtractSDF(other);  ok = ok && within(t, pts, [&](const Vec3d& p) { return std::max(-sphereF(p), otherF(p)); }, 0.05); }
         report("SDF Operations", ok);
     }
-    {   // TestOctreeCustomDomains (:285-316): root [-0.25,5]^3, radius 0.75, continuity on
-        SDF::Config c = baseConfig(true);
+    {   // TestOctreeCustomDomains (:285-316): root [-0.25,5]^3, |p - (0.25,0,0)| - 0.75, default nearness (None), continuity on
+        SDF::Config c;
+        c.targetErrorThreshold = std::pow(10, -8);
+        c.continuity.enforce   = true;
+        c.continuity.strength  = 8.0;
         for (int i = 0; i < 3; ++i) { c.root.lo[i] = -0.25f; c.root.hi[i] = 5.0f; }
         SDF::Program p;
-        p.Sphere(2.0, 2.0, 2.0, 0.75);
+        p.Sphere(0.25, 0.0, 0.0, 0.75);
         SDF::Octree t;
         t.Create(c, p);
         const auto big = samples(1000000, -0.25, 5.0, 2);
-        report("Custom Domains", within(t, big, [](const Vec3d& q) { return sphere(q, 2.0, 2.0, 2.0, 0.75); }, 0.01));
+        report("Custom Domains", within(t, big, [](const Vec3d& q) { return sphere(q, 0.25, 0.0, 0.0, 0.75); }, 0.01));
         const SDF::Box3f root = t.GetRootAABB();
         report("GetRootAABB", root.lo[0] == -0.25f && root.hi[2] == 5.0f);
     }
