@@ -230,6 +230,41 @@ class SdfProgram:
         return out
 
 
+class Mesh:
+    """Device-resident triangle mesh + BVH as an SDF source (replaces Meshing::Mesh + Meshing::BVH under Create).
+    verts: (n,3) float32, tris: (m,3) uint32, counter-clockwise seen from outside; raises if an edge has no twin."""
+
+    def __init__(self, verts, tris, device=-1):
+        v = np.ascontiguousarray(verts, np.float32)
+        t = np.ascontiguousarray(tris, np.uint32)
+        h = C.c_void_p()
+        _check(lib().hpsdf_mesh_create(v.ctypes.data, len(v), t.ctypes.data, len(t), device, C.byref(h)))
+        self._h = h.value
+
+    def SignedDistanceAtPt(self, pts):
+        """Mesh::SignedDistanceAtPt (Source/Meshing/Mesh.cpp:54-63), batched, float32."""
+        p = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+        out = np.empty(len(p), np.float32)
+        _check(lib().hpsdf_mesh_signed_distance(self._h, p.ctypes.data, len(p), out.ctypes.data))
+        return out
+
+    def CalculateMeshAABB(self):
+        mn, mx = (C.c_float * 3)(), (C.c_float * 3)()
+        _check(lib().hpsdf_mesh_aabb(self._h, mn, mx))
+        return np.array(mn[:], np.float32), np.array(mx[:], np.float32)
+
+    def close(self):
+        if self._h:
+            lib().hpsdf_mesh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class MemoryBlock:
     """MemoryBlock {size, ptr} (Include/Utility/MemoryBlock.h:5-9). `ptr` is malloc()ed by ToMemoryBlock and owned by
     the caller (the reference's callers free() it, README.md:41-53); free() here does that."""

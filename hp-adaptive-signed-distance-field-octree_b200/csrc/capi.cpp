@@ -413,22 +413,4 @@ extern "C"
         return HPSDF_OK;
     }
 
-    // ---- meshes: see mesh.cpp (round 1: not yet available) -------------------------------------------------
-    HPSDF_API hpsdf_status hpsdf_mesh_create(const float*, size_t, const uint32_t*, size_t, int, hpsdf_mesh** out)
-    {
-        if (out) *out = nullptr;
-        setLastError("device meshes are not available in this build");
-        return HPSDF_ERR_UNSUPPORTED;
-    }
-    HPSDF_API hpsdf_status hpsdf_mesh_signed_distance(const hpsdf_mesh*, const float*, size_t, float*)
-    {
-        setLastError("device meshes are not available in this build");
-        return HPSDF_ERR_UNSUPPORTED;
-    }
-    HPSDF_API hpsdf_status hpsdf_mesh_aabb(const hpsdf_mesh*, float*, float*)
-    {
-        setLastError("device meshes are not available in this build");
-        return HPSDF_ERR_UNSUPPORTED;
-    }
-    HPSDF_API void hpsdf_mesh_destroy(hpsdf_mesh*) {}
 }

@@ -109,8 +109,24 @@ namespace hpsdf
         double c0;
     };
 
+    // Device mesh (mesh.cpp builds it, mesh_eval.cuh traverses it)
+    struct BvhNode            // 32 bytes
+    {
+        float    mn[3];
+        uint32_t a;           // internal: left child index; leaf: first triangle slot
+        float    mx[3];
+        uint32_t b;           // internal: right child index; leaf: 0x80000000 | triangle count
+    };
+
+    struct DeviceMeshView
+    {
+        const BvhNode*  nodes;
+        const void*     triVerts;     // 3 float4 per triangle SLOT (BVH order): a, b, c; .w of a = original triangle index (bits)
+        const float*    pseudo;       // 21 floats per ORIGINAL triangle: face normal, 3 edge normals (AB, BC, CA), 3 vertex normals (A, B, C)
+        uint32_t        nTris, nNodes;
+    };
+
     // Device SDF program (hpsdf_sdf_program with handles resolved to device pointers). Passed by value as a kernel parameter.
-    struct DeviceMeshView;
     struct DeviceTreeView;
     struct SdfInstrDev
     {

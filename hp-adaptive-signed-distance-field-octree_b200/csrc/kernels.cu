@@ -154,4 +154,11 @@ namespace hpsdf
         cudaFree(scratch);
         return e;
     }
+
+    cudaError_t launchMeshDistance(const DeviceMeshView* dView, const float* dXyz, size_t n, float* dOut, cudaStream_t stream)
+    {
+        if (!n) return cudaSuccess;
+        meshDistanceKernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(dView, dXyz, n, dOut);
+        return cudaGetLastError();
+    }
 }

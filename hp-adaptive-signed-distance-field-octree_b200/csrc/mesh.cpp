@@ -1,0 +1,275 @@
+// mesh.cpp — device-resident triangle mesh as an SDF source: what replaces Meshing::Mesh + Meshing::BVH
+// (Include/Meshing/Mesh.h, Include/Meshing/BVH.h) under Octree::Create.
+//
+// Host side, at hpsdf_mesh_create:
+//   * half-edge twins            Mesh::CreateHalfEdges (Source/Meshing/Mesh.cpp:87-131); an unpaired edge -> HPSDF_ERR_MESH
+//   * pseudonormals, float32     PseudoNormalFace / Edge / Vertex (Mesh.cpp:185-242), precomputed for every face, every
+//                                half-edge and every triangle corner with the reference's formulas and operation order
+//                                (this file is compiled with -ffp-contract=off; acosf is the host libm's, as in the reference)
+//   * BVH                        top-down median split on the longest axis of the centroid bounds, <= 4 triangles per leaf.
+//                                The reference's bottom-up pairing through an NNOctree (BVH.cpp:26-260) is not reproduced:
+//                                any BVH gives the same closest triangle.
+// Device side: mesh_eval.cuh.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <vector>
+#include "octree.h"
+
+struct hpsdf_mesh
+{
+    int      device = 0;
+    void*    blob = nullptr;                  // nodes | triVerts | pseudo | view
+    hpsdf::DeviceMeshView  view{};
+    hpsdf::DeviceMeshView* dView = nullptr;
+    float    mn[3] = { 0, 0, 0 }, mx[3] = { 0, 0, 0 };
+    uint32_t nTris = 0, nVerts = 0;
+};
+
+namespace hpsdf
+{
+    cudaError_t launchMeshDistance(const DeviceMeshView* dView, const float* dXyz, size_t n, float* dOut, cudaStream_t stream);   // kernels.cu
+
+    const DeviceMeshView* meshDeviceView(const hpsdf_mesh* m) { return m ? m->dView : nullptr; }
+    int meshDevice(const hpsdf_mesh* m) { return m ? m->device : -1; }
+
+    namespace
+    {
+        struct V3 { float x, y, z; };
+        inline V3 sub(const V3& a, const V3& b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+        inline V3 add(const V3& a, const V3& b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
+        inline V3 mul(const V3& a, float s) { return { a.x * s, a.y * s, a.z * s }; }
+        inline float dot(const V3& a, const V3& b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }           // a0 + (a1 + a2)
+        inline V3 cross(const V3& a, const V3& b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+        inline V3 normalized(const V3& a)
+        {
+            const float z = dot(a, a);
+            if (z > 0.0f) { const float n = std::sqrt(z); return { a.x / n, a.y / n, a.z / n }; }
+            return a;
+        }
+
+        struct Builder
+        {
+            const std::vector<V3>& v;
+            const std::vector<uint32_t>& tri;
+            std::vector<uint32_t> he;
+
+            V3 vert(uint32_t t, uint32_t k) const { return v[tri[3 * t + k]]; }
+            // PseudoNormalFace, Mesh.cpp:185-193
+            V3 faceNormal(uint32_t t) const
+            {
+                const V3 ab = sub(vert(t, 1), vert(t, 0)), ac = sub(vert(t, 2), vert(t, 0));
+                return normalized(cross(ab, ac));
+            }
+            // PseudoNormalEdge, Mesh.cpp:196-213: n = nA * PI + nB * PI (PI converted to float), normalised
+            V3 edgeNormal(uint32_t t, uint32_t s) const
+            {
+                const uint32_t adjEdge = he[3 * t + s];
+                const uint32_t adjTri = (adjEdge - (adjEdge % 3)) / 3;
+                const float PI = (float)3.14159265359;
+                return normalized(add(mul(faceNormal(t), PI), mul(faceNormal(adjTri), PI)));
+            }
+            // PseudoNormalVertex, Mesh.cpp:216-242: walk the fan he -> next(twin(he)) until back at the start triangle
+            V3 vertexNormal(uint32_t t, uint32_t s) const
+            {
+                V3 n = { 0.0f, 0.0f, 0.0f };
+                uint32_t curHE = 3 * t + s, curTri = t;
+                size_t guard = 0;
+                do
+                {
+                    const V3 c0 = vert(curTri, curHE % 3), c1 = vert(curTri, (curHE + 1) % 3), c2 = vert(curTri, (curHE + 2) % 3);
+                    const V3 ab = sub(c1, c0), ac = sub(c2, c0);
+                    const float ang = acosf(dot(normalized(ab), normalized(ac)));
+                    n = add(n, mul(faceNormal(curTri), ang));
+                    curHE = he[curHE];
+                    curHE = ((curHE % 3) == 2) ? (curHE - 2) : (curHE + 1);
+                    curTri = (curHE - (curHE % 3)) / 3;
+                } while (curTri != t && ++guard < 100000);
+                return normalized(n);
+            }
+        };
+
+        struct BuildNode { float mn[3], mx[3]; uint32_t a, b; };
+
+        void triBounds(const std::vector<V3>& v, const std::vector<uint32_t>& tri, uint32_t t, float mn[3], float mx[3])
+        {
+            for (int k = 0; k < 3; ++k)
+            {
+                const V3& p = v[tri[3 * t + k]];
+                const float c[3] = { p.x, p.y, p.z };
+                for (int d = 0; d < 3; ++d) { mn[d] = k ? std::min(mn[d], c[d]) : c[d]; mx[d] = k ? std::max(mx[d], c[d]) : c[d]; }
+            }
+        }
+
+        uint32_t buildBvh(std::vector<BuildNode>& nodes, std::vector<uint32_t>& order, const std::vector<float>& cen,
+                          const std::vector<float>& tmn, const std::vector<float>& tmx, uint32_t begin, uint32_t end)
+        {
+            const uint32_t idx = (uint32_t)nodes.size();
+            nodes.push_back({});
+            float mn[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, mx[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
+            float cmn[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, cmx[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
+            for (uint32_t i = begin; i < end; ++i)
+            {
+                const uint32_t t = order[i];
+                for (int d = 0; d < 3; ++d)
+                {
+                    mn[d] = std::min(mn[d], tmn[3 * t + d]); mx[d] = std::max(mx[d], tmx[3 * t + d]);
+                    cmn[d] = std::min(cmn[d], cen[3 * t + d]); cmx[d] = std::max(cmx[d], cen[3 * t + d]);
+                }
+            }
+            memcpy(nodes[idx].mn, mn, 12); memcpy(nodes[idx].mx, mx, 12);
+            if (end - begin <= 4)
+            {
+                nodes[idx].a = begin; nodes[idx].b = 0x80000000u | (end - begin);
+                return idx;
+            }
+            int axis = 0;
+            if (cmx[1] - cmn[1] > cmx[axis] - cmn[axis]) axis = 1;
+            if (cmx[2] - cmn[2] > cmx[axis] - cmn[axis]) axis = 2;
+            const uint32_t mid = (begin + end) / 2;
+            std::nth_element(order.begin() + begin, order.begin() + mid, order.begin() + end,
+                             [&](uint32_t x, uint32_t y) { return cen[3 * x + axis] < cen[3 * y + axis] || (cen[3 * x + axis] == cen[3 * y + axis] && x < y); });
+            const uint32_t l = buildBvh(nodes, order, cen, tmn, tmx, begin, mid);
+            const uint32_t r = buildBvh(nodes, order, cen, tmn, tmx, mid, end);
+            nodes[idx].a = l; nodes[idx].b = r;
+            return idx;
+        }
+    }
+}
+
+using namespace hpsdf;
+
+extern "C"
+{
+    HPSDF_API hpsdf_status hpsdf_mesh_create(const float* vertices, size_t n_vertices, const uint32_t* tri_indices, size_t n_tris,
+                                             int device, hpsdf_mesh** out)
+    {
+        if (!out) { setLastError("out is null"); return HPSDF_ERR_INVALID_ARG; }
+        *out = nullptr;
+        if (!vertices || !tri_indices || n_vertices == 0 || n_tris == 0 || n_tris >= 0x2AAAAAAAull)
+        { setLastError("mesh arrays are null, empty or too large"); return HPSDF_ERR_INVALID_ARG; }
+        std::string err;
+        DeviceCtx* ctx = getDeviceCtx(device, err);
+        if (!ctx) { setLastError(err); return HPSDF_ERR_NO_DEVICE; }
+
+        std::vector<V3> v(n_vertices);
+        memcpy(v.data(), vertices, n_vertices * 12);
+        std::vector<uint32_t> tri(tri_indices, tri_indices + 3 * n_tris);
+        for (uint32_t i : tri) if (i >= n_vertices) { setLastError("triangle index out of range"); return HPSDF_ERR_INVALID_ARG; }
+
+        // CreateHalfEdges (Mesh.cpp:87-131): twin of the directed edge (a, b) is the edge (b, a); first occurrence wins
+        Builder b{ v, tri, std::vector<uint32_t>(3 * n_tris, 0xFFFFFFFFu) };
+        {
+            std::map<std::pair<uint32_t, uint32_t>, uint32_t> edgeMap;
+            for (uint32_t i = 0; i < 3 * n_tris; ++i)
+            {
+                const std::pair<uint32_t, uint32_t> edge(tri[i], (i % 3 == 2) ? tri[i - 2] : tri[i + 1]);
+                const auto f = edgeMap.find({ edge.second, edge.first });
+                if (f != edgeMap.end()) { b.he[f->second] = i; b.he[i] = f->second; }
+                else edgeMap.insert({ edge, i });
+            }
+            for (uint32_t h : b.he)
+                if (h == 0xFFFFFFFFu) { setLastError("mesh has an edge without a twin: not a closed manifold (Mesh.cpp:121-128)"); return HPSDF_ERR_MESH; }
+        }
+
+        // pseudonormals: 21 floats per triangle
+        std::vector<float> pseudo(21 * n_tris);
+        for (uint32_t t = 0; t < n_tris; ++t)
+        {
+            float* p = pseudo.data() + 21 * (size_t)t;
+            const V3 f = b.faceNormal(t);
+            p[0] = f.x; p[1] = f.y; p[2] = f.z;
+            for (uint32_t s = 0; s < 3; ++s)
+            {
+                const V3 e = b.edgeNormal(t, s), w = b.vertexNormal(t, s);
+                p[3 + 3 * s] = e.x; p[4 + 3 * s] = e.y; p[5 + 3 * s] = e.z;
+                p[12 + 3 * s] = w.x; p[13 + 3 * s] = w.y; p[14 + 3 * s] = w.z;
+            }
+        }
+
+        // BVH
+        std::vector<float> cen(3 * n_tris), tmn(3 * n_tris), tmx(3 * n_tris);
+        for (uint32_t t = 0; t < n_tris; ++t)
+        {
+            triBounds(v, tri, t, &tmn[3 * t], &tmx[3 * t]);
+            for (int d = 0; d < 3; ++d) cen[3 * t + d] = 0.5f * (tmn[3 * t + d] + tmx[3 * t + d]);
+        }
+        std::vector<uint32_t> order(n_tris);
+        std::iota(order.begin(), order.end(), 0u);
+        std::vector<BuildNode> bn;
+        bn.reserve(n_tris);
+        buildBvh(bn, order, cen, tmn, tmx, 0, (uint32_t)n_tris);
+        std::vector<BvhNode> nodes(bn.size());
+        for (size_t i = 0; i < bn.size(); ++i)
+        {
+            memcpy(nodes[i].mn, bn[i].mn, 12); memcpy(nodes[i].mx, bn[i].mx, 12);
+            nodes[i].a = bn[i].a; nodes[i].b = bn[i].b;
+        }
+        std::vector<float> tv(12 * n_tris);
+        for (uint32_t slot = 0; slot < n_tris; ++slot)
+        {
+            const uint32_t t = order[slot];
+            for (int k = 0; k < 3; ++k)
+            {
+                const V3 p = v[tri[3 * t + k]];
+                float* o = &tv[12 * (size_t)slot + 4 * k];
+                o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = 0.0f;
+            }
+            memcpy(&tv[12 * (size_t)slot + 3], &t, 4);          // original triangle index rides in a.w
+        }
+
+        hpsdf_mesh* m = new hpsdf_mesh();
+        m->device = ctx->device; m->nTris = (uint32_t)n_tris; m->nVerts = (uint32_t)n_vertices;
+        memcpy(m->mn, bn[0].mn, 12); memcpy(m->mx, bn[0].mx, 12);          // CalculateMeshAABB (Mesh.cpp:66-84)
+        auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        const size_t bNodes = align(nodes.size() * sizeof(BvhNode)), bTv = align(tv.size() * 4), bPs = align(pseudo.size() * 4);
+        cudaError_t e = cudaMalloc(&m->blob, bNodes + bTv + bPs + 256);
+        if (e != cudaSuccess) { delete m; return failCuda(e, "mesh allocation"); }
+        char* p = (char*)m->blob;
+        m->view.nodes = (const BvhNode*)p;
+        m->view.triVerts = (const void*)(p + bNodes);
+        m->view.pseudo = (const float*)(p + bNodes + bTv);
+        m->view.nTris = (uint32_t)n_tris; m->view.nNodes = (uint32_t)nodes.size();
+        m->dView = (DeviceMeshView*)(p + bNodes + bTv + bPs);
+        e = cudaMemcpy(p, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(p + bNodes, tv.data(), tv.size() * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(p + bNodes + bTv, pseudo.data(), pseudo.size() * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(m->dView, &m->view, sizeof(DeviceMeshView), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(m->blob); delete m; return failCuda(e, "mesh upload"); }
+        *out = m;
+        return HPSDF_OK;
+    }
+
+    HPSDF_API hpsdf_status hpsdf_mesh_signed_distance(const hpsdf_mesh* mesh, const float* xyz, size_t n, float* out)
+    {
+        if (!mesh || (n && (!xyz || !out))) { setLastError("null pointer"); return HPSDF_ERR_INVALID_ARG; }
+        if (!n) return HPSDF_OK;
+        HPSDF_CUDA(cudaSetDevice(mesh->device));
+        float *dIn = nullptr, *dOut = nullptr;
+        HPSDF_CUDA(cudaMalloc((void**)&dIn, n * 12));
+        cudaError_t e = cudaMalloc((void**)&dOut, n * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(dIn, xyz, n * 12, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = launchMeshDistance(mesh->dView, dIn, n, dOut, nullptr);
+        if (e == cudaSuccess) e = cudaMemcpy(out, dOut, n * 4, cudaMemcpyDeviceToHost);
+        cudaFree(dIn); cudaFree(dOut);
+        if (e != cudaSuccess) return failCuda(e, "hpsdf_mesh_signed_distance");
+        return HPSDF_OK;
+    }
+
+    HPSDF_API hpsdf_status hpsdf_mesh_aabb(const hpsdf_mesh* mesh, float mn[3], float mx[3])
+    {
+        if (!mesh || !mn || !mx) { setLastError("null pointer"); return HPSDF_ERR_INVALID_ARG; }
+        memcpy(mn, mesh->mn, 12); memcpy(mx, mesh->mx, 12);
+        return HPSDF_OK;
+    }
+
+    HPSDF_API void hpsdf_mesh_destroy(hpsdf_mesh* mesh)
+    {
+        if (!mesh) return;
+        cudaSetDevice(mesh->device);
+        cudaFree(mesh->blob);
+        delete mesh;
+    }
+}

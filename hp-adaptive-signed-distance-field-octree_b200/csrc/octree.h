@@ -83,6 +83,8 @@ namespace hpsdf
     hpsdf_status  fromMemoryBlock(hpsdf_octree& t, const void* ptr, size_t size);
     hpsdf_status  queryHost(hpsdf_octree& t, const double* xyz, size_t n, double* out);
     const std::string& lastError();
+    const DeviceMeshView* meshDeviceView(const hpsdf_mesh* m);      // mesh.cpp
+    int           meshDevice(const hpsdf_mesh* m);
     // CornerAABB (Octree.cpp:1096-1112)
     void          cornerAabb(const HostNode& parent, uint32_t i, float mn[3], float mx[3]);
     double        nowMs();

@@ -138,8 +138,11 @@ namespace hpsdf
                     o.handle = src->dView; ++sp; break;
                 }
                 case HPSDF_PRIM_MESH:
-                    setLastError("MESH primitives are not available in this build");
-                    return HPSDF_ERR_UNSUPPORTED;
+                {
+                    const hpsdf_mesh* src = (const hpsdf_mesh*)in.handle;
+                    if (!src || meshDevice(src) != device) { setLastError("MESH primitive needs a mesh created on the same device"); return HPSDF_ERR_INVALID_ARG; }
+                    o.handle = meshDeviceView(src); ++sp; break;
+                }
                 case HPSDF_OP_NEGATE:
                     if (sp < 1) { setLastError("SDF program: operator without operand"); return HPSDF_ERR_INVALID_ARG; }
                     break;

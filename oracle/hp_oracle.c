@@ -39,6 +39,7 @@
 #include "../include/hpsdf.h"
 #include "sdf_cpu.h"
 #include "hp_oracle_tables.h"
+#include "hp_oracle_mesh.h"
 
 #define MAXDEG 12           /* BASIS_MAX_DEGREE, Consts.h:7 */
 #define MAXDEPTH 10         /* TREE_MAX_DEPTH,  Consts.h:8 */
@@ -820,6 +821,33 @@ static void continuity_post_process(Tree* t, double tol, int threads)
     free(b); free(x); free(r); free(p); free(z); free(tmp); free(invDiag); free(m.rowPtr); free(m.col); free(m.val);
 }
 
+/* MESH primitives of a program: handle = OMesh* (hporacle_mesh_create); the f64 point is cast to f32 and the f32 distance
+ * widened, the glue the reference implies (Include/Meshing/Mesh.h:53-54). OCTREE primitives: handle = Tree*. */
+static double query_one(const Tree* t, const double x[3]);
+static double builtin_ext(uint32_t op, const void* handle, const double x[3])
+{
+    if (op == HPSDF_PRIM_MESH)
+    {
+        const mv3 p = { (float)x[0], (float)x[1], (float)x[2] };
+        return (double)omesh_signed_distance((const OMesh*)handle, p, 1);
+    }
+    if (op == HPSDF_PRIM_OCTREE) return query_one((const Tree*)handle, x);
+    return NAN;
+}
+
+void* hporacle_mesh_create(const float* verts, size_t nv, const uint32_t* tris, size_t nt) { return omesh_create(verts, nv, tris, nt); }
+void  hporacle_mesh_destroy(void* m) { omesh_free((OMesh*)m); }
+void  hporacle_mesh_sdf(void* m, const float* xyz, size_t n, float* out, int useBvh, int threads)
+{
+    (void)threads;
+    #pragma omp parallel for schedule(dynamic, 64) num_threads(threads) if (threads > 1)
+    for (long i = 0; i < (long)n; ++i)
+    {
+        const mv3 p = { xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2] };
+        out[i] = omesh_signed_distance((const OMesh*)m, p, useBvh);
+    }
+}
+
 /* ---- public entry points (ctypes) ------------------------------------------------------------------------ */
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
@@ -829,7 +857,7 @@ static Tree* tree_new(const hpsdf_config* cfg, const hpsdf_sdf_instr* prog, uint
     Tree* t = (Tree*)calloc(1, sizeof(Tree));
     t->cfg = *cfg;
     if (n) { t->prog = (hpsdf_sdf_instr*)malloc(sizeof(hpsdf_sdf_instr) * n); memcpy(t->prog, prog, sizeof(hpsdf_sdf_instr) * n); }
-    t->nprog = n; t->ext = ext;
+    t->nprog = n; t->ext = ext ? ext : builtin_ext;
     set_root_mapping(t);
     return t;
 }
@@ -954,7 +982,7 @@ double hporacle_fit(const hpsdf_config* cfg, const hpsdf_sdf_instr* prog, uint32
 /* SDF program at n points in USER space (the argument of F_, Octree.cpp:327). */
 void hporacle_sdf_eval_batch(const hpsdf_sdf_instr* prog, uint32_t n, const double* xyz, size_t npts, double* out, hporacle_ext_eval ext)
 {
-    for (size_t i = 0; i < npts; ++i) out[i] = hporacle_sdf_eval(prog, n, xyz + 3 * i, ext);
+    for (size_t i = 0; i < npts; ++i) out[i] = hporacle_sdf_eval(prog, n, xyz + 3 * i, ext ? ext : builtin_ext);
 }
 
 /* Continuity matrix M (withDiagonal = 0) or M + lambda I as CSR; two-call protocol (rowPtr == NULL returns nnz). */

@@ -53,6 +53,10 @@ def lib():
     L.hporacle_n_nodes.restype = C.c_size_t
     L.hporacle_n_nodes.argtypes = [C.c_void_p]
     L.hporacle_tables.argtypes = [C.c_void_p] * 7
+    L.hporacle_mesh_create.restype = C.c_void_p
+    L.hporacle_mesh_create.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    L.hporacle_mesh_destroy.argtypes = [C.c_void_p]
+    L.hporacle_mesh_sdf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
     _lib = L
     return L
 
@@ -127,6 +131,28 @@ class OracleTree:
             self.close()
         except Exception:
             pass
+
+
+class OracleMesh:
+    """Float32 mesh signed distance (Mesh::SignedDistanceAtPt restated); `h` can be the handle of a ("mesh", [], h) item."""
+
+    def __init__(self, verts, tris):
+        self.v = np.ascontiguousarray(verts, np.float32)
+        self.t = np.ascontiguousarray(tris, np.uint32)
+        self.h = lib().hporacle_mesh_create(self.v.ctypes.data, len(self.v), self.t.ctypes.data, len(self.t))
+        if not self.h:
+            raise ValueError("mesh is not a closed manifold")
+
+    def sdf(self, pts, use_bvh=True, threads=1):
+        p = np.ascontiguousarray(pts, np.float32)
+        out = np.empty(len(p), np.float32)
+        lib().hporacle_mesh_sdf(self.h, p.ctypes.data, len(p), out.ctypes.data, 1 if use_bvh else 0, threads)
+        return out
+
+    def close(self):
+        if self.h:
+            lib().hporacle_mesh_destroy(self.h)
+            self.h = None
 
 
 def oracle_fit(cfg, prog, aabb_min, aabb_max, degree, depth, degree_in=0, coeffs_in=None):

@@ -76,8 +76,20 @@ def fit_golden():
     print("fits", k)
 
 
+def mesh_golden():
+    """Reference Mesh::SignedDistanceAtPt (through its own BVH) on the procedural bumpy torus at seeded points."""
+    from meshgen import bumpy_torus, mesh_root
+    v, t = bumpy_torus(60, 40)
+    rm = hpref.RefMesh.create(v, t, bvh=True)
+    lo, hi = mesh_root(v)
+    pts = np.random.default_rng(42).uniform(lo, hi, (20000, 3)).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "mesh_torus.npz"), pts=pts, sdf=rm.sdf(pts, True, 8))
+    print("mesh", len(t))
+
+
 if __name__ == "__main__":
     assert hpref.available(), "build oracle/_ref first: make -C oracle ref"
     fit_golden()
+    mesh_golden()
     for n in TREE_CASES:
         tree_golden(n)
