@@ -87,7 +87,10 @@ namespace hpsdf
             std::vector<uint32_t>    bucketCount_ = std::vector<uint32_t>(kBuckets, 0u);
             double                   applyLevel_ = std::numeric_limits<double>::infinity();   // entries >= this are certain to be popped
             size_t                   levelLogStart_ = 0;     // first apply-log entry of the current level
-            std::vector<std::pair<uint64_t, double>> deferred_;
+            double                   pendingMax_ = 0.0;      // largest error among pending_ (uncached) leaves
+            std::vector<FitTask>     tasksD_[kMaxDegree + 1];
+            std::vector<uint32_t>    ownerD_[kMaxDegree + 1]; // per task: job index << 4 | child slot (8 = the p-fit)
+            std::vector<uint64_t>    evaluated_;
             bool                     levelTried_ = false;
             double                   evalLevel_ = 0.0;       // guaranteed level used to choose what to evaluate (also in strict mode)
             std::vector<int32_t>     jobOf_;        // per node: index into jobs_, -1 = no cached result
@@ -125,14 +128,16 @@ namespace hpsdf
                 if (e > 0.0) std::frexp(e, &ex);
                 return std::min(std::max(ex + 1100, 0), kBuckets - 1);
             }
+            // a new / changed leaf enters the conceptual queue: histogram + pending list (it reaches the heap once evaluated)
             void qPush(uint64_t idx, double err)
             {
-                queue_.push({ idx, err });
                 inQueue_[idx] = 1;
                 const int b = bucketOf(err);
                 bucketSum_[b] += err; bucketCount_[b]++;
+                pending_.push_back(idx);
+                pendingMax_ = std::max(pendingMax_, err);
             }
-            void qPop()
+            void hPop()
             {
                 const std::pair<uint64_t, double> t = queue_.top();
                 queue_.pop();
@@ -140,7 +145,12 @@ namespace hpsdf
                 const int b = bucketOf(t.second);
                 if (--bucketCount_[b] == 0) bucketSum_[b] = 0.0; else bucketSum_[b] -= t.second;
             }
-            double       checkValue() const
+            double conceptualTop() const
+            {
+                const double h = queue_.empty() ? 0.0 : queue_.top().second;
+                return pending_.empty() ? h : std::max(h, pendingMax_);
+            }
+            double checkValue() const
             {
                 return o_.total_mode == HPSDF_TOTAL_EXACT_SUM
                      ? (unfitted_ > 0 ? std::numeric_limits<double>::infinity() : (double)exactSum_) : total_;
@@ -177,61 +187,83 @@ namespace hpsdf
             }
         }
 
-        // One batch: the refinement jobs of every pending leaf.
+        // One batch: the refinement jobs of the pending (not yet evaluated) leaves at or above the evaluation level.
         hpsdf_status Builder::evaluateRound()
         {
-            // ---- 1. jobs and fit tasks, grouped by fit degree ------------------------------------------------------
-            struct Proto { uint64_t node; uint8_t child; bool isP; };     // child 0..7 for h-fits
-            std::vector<Proto> byDegree[kMaxDegree + 1];
-            const size_t firstJob = jobs_.size();
-            jobOf_.resize(nodes_.size(), -1);
-            errOf_.resize(nodes_.size(), 0.0);
-            // Which uncached leaves to evaluate now. A leaf is certainly popped by the strict greedy loop if, taking the
-            // queue in decreasing error order, the total minus the errors before it is still >= the threshold (popping
-            // an entry and any of its descendants lowers the total by at most that entry's error). Everything down to
-            // that guaranteed level L is needed work; entries down to L / 8^speculate are pre-evaluated speculatively so
-            // the replay stalls less often. Leaves below stay pending until the level reaches them.
-            // Which uncached leaves to evaluate now: everything at or above the guaranteed level (computeLevel) is needed
-            // work; `speculate` octaves (factors of 8) below it are pre-evaluated so later levels find their results cached.
+            // ---- 1. which leaves: everything at or above the guaranteed level (computeLevel) is needed work; `speculate`
+            //         octaves (factors of 8) below it are pre-evaluated so later levels find their results cached -------------
             if (o_.strict_order || applyLevel_ == std::numeric_limits<double>::infinity())
             {
                 const double keep = applyLevel_;
-                computeLevel();                 // refresh evalLevel_ for the current state
+                computeLevel();                 // refresh evalLevel_ for the current (sequential) state
                 if (o_.strict_order || keep != std::numeric_limits<double>::infinity()) applyLevel_ = keep;
             }
-            double level = std::min(evalLevel_, queue_.empty() ? 0.0 : queue_.top().second);
+            double level = std::min(evalLevel_, conceptualTop());
             for (uint32_t k = 0; k < o_.speculate; ++k) level *= 0.125;
+
             const double tTask0 = nowMs();
-            std::vector<uint64_t> later;
-            for (uint64_t idx : pending_)
+            for (int d = 0; d <= kMaxDegree; ++d) { tasksD_[d].clear(); ownerD_[d].clear(); }
+            const size_t firstJob = jobs_.size();
+            evaluated_.clear();
+            size_t keepN = 0;
+            pendingMax_ = 0.0;
+            for (size_t k = 0; k < pending_.size(); ++k)
             {
+                const uint64_t idx = pending_[k];
+                if (errOf_[idx] < level) { pending_[keepN++] = idx; pendingMax_ = std::max(pendingMax_, errOf_[idx]); continue; }
                 const HostNode& n = nodes_[idx];
-                if (errOf_[idx] < level) { later.push_back(idx); continue; }
-                Job j;
+                const uint32_t jobIdx = (uint32_t)jobs_.size();
+                jobs_.emplace_back();
+                Job& j = jobs_.back();
                 j.coarse = std::abs(errOf_[idx] - kInitialErr) < std::numeric_limits<double>::epsilon() && n.degree == 0;   // Octree.cpp:806, 831
-                if (j.coarse) { j.doP = true; byDegree[kCoarseDegree].push_back({ idx, 0, true }); }
+                FitTask t;
+                t.pad = 0; t.rec = 0; t.out = 0;
+                if (j.coarse)
+                {
+                    j.doP = true;
+                    t.cx = (n.mn[0] + n.mx[0]) / 2.0f; t.cy = (n.mn[1] + n.mx[1]) / 2.0f; t.cz = (n.mn[2] + n.mx[2]) / 2.0f;   // AlignedBox::center() in f32
+                    t.half = (n.mx[0] - n.mn[0]) * 0.5f;
+                    t.depth = n.depth; t.degree = (uint8_t)kCoarseDegree; t.degreeIn = 0; t.src = kNoSrc;
+                    tasksD_[kCoarseDegree].push_back(t); ownerD_[kCoarseDegree].push_back(jobIdx << 4 | 8u);
+                }
                 else
                 {
                     j.doH = n.depth < o_.max_depth;             // child fits at depth > TREE_MAX_DEPTH are never used (Octree.cpp:600-601)
                     j.doP = n.degree < o_.max_degree;           // nor is the p-fit of a max-degree node
-                    if (j.doH) for (uint8_t c = 0; c < 8; ++c) byDegree[n.degree].push_back({ idx, c, false });
-                    if (j.doP) byDegree[n.degree + 1].push_back({ idx, 0, true });
+                    if (j.doH)
+                        for (uint32_t c = 0; c < 8; ++c)
+                        {
+                            float mn[3], mx[3];
+                            cornerAabb(n, c, mn, mx);                                                          // Octree.cpp:820
+                            t.cx = (mn[0] + mx[0]) / 2.0f; t.cy = (mn[1] + mx[1]) / 2.0f; t.cz = (mn[2] + mx[2]) / 2.0f;
+                            t.half = (mx[0] - mn[0]) * 0.5f;
+                            t.depth = (uint8_t)(n.depth + 1); t.degree = n.degree; t.degreeIn = 0; t.src = kNoSrc;
+                            tasksD_[n.degree].push_back(t); ownerD_[n.degree].push_back(jobIdx << 4 | c);
+                        }
+                    if (j.doP)
+                    {
+                        t.cx = (n.mn[0] + n.mx[0]) / 2.0f; t.cy = (n.mn[1] + n.mx[1]) / 2.0f; t.cz = (n.mn[2] + n.mx[2]) / 2.0f;
+                        t.half = (n.mx[0] - n.mn[0]) * 0.5f;
+                        t.depth = n.depth; t.degree = (uint8_t)(n.degree + 1); t.degreeIn = n.degree; t.src = n.slot;        // Octree.cpp:846-851
+                        tasksD_[n.degree + 1].push_back(t); ownerD_[n.degree + 1].push_back(jobIdx << 4 | 8u);
+                    }
                 }
-                jobOf_[idx] = (int32_t)jobs_.size();
-                jobs_.push_back(j);
+                jobOf_[idx] = (int32_t)jobIdx;
+                evaluated_.push_back(idx);
             }
-            pending_.swap(later);
+            pending_.resize(keepN);
 
             size_t nTasks = 0, poolNeed = poolUsed_;
-            for (int d = 1; d <= kMaxDegree; ++d) { nTasks += byDegree[d].size(); poolNeed += byDegree[d].size() * (size_t)coeffCount(d); }
-            if (nTasks == 0) return HPSDF_OK;
+            for (int d = 1; d <= kMaxDegree; ++d) { nTasks += tasksD_[d].size(); poolNeed += tasksD_[d].size() * (size_t)coeffCount(d); }
             if (poolNeed >= 0xFFFFFFF0ull) { setLastError("coefficient pool exceeds 2^32 doubles"); return HPSDF_ERR_OOM; }
-            HPSDF_CUDA(pool_.reserve(poolNeed + 1024, stream_, poolUsed_));
-            HPSDF_CUDA(dTasks_.reserve(nTasks));
-            HPSDF_CUDA(dRecs_.reserve(nTasks));
-            HPSDF_CUDA(hTasks_.reserve(nTasks));
-            HPSDF_CUDA(hRecs_.reserve(nTasks));
-
+            if (nTasks)
+            {
+                HPSDF_CUDA(pool_.reserve(poolNeed + 1024, stream_, poolUsed_));
+                HPSDF_CUDA(dTasks_.reserve(nTasks));
+                HPSDF_CUDA(dRecs_.reserve(nTasks));
+                HPSDF_CUDA(hTasks_.reserve(nTasks));
+                HPSDF_CUDA(hRecs_.reserve(nTasks));
+            }
             // Tasks in degree order; task index == record index; slots allocated in task order (contiguous per degree,
             // so a rank's shard of a degree group is one contiguous pool range).
             size_t ti = 0;
@@ -241,98 +273,95 @@ namespace hpsdf
             for (int d = 1; d <= kMaxDegree; ++d)
             {
                 groupBegin[d] = ti; groupPool[d] = poolUsed_;
-                for (const Proto& p : byDegree[d])
+                const size_t nd = tasksD_[d].size();
+                const uint32_t cc = (uint32_t)coeffCount(d);
+                for (size_t k = 0; k < nd; ++k)
                 {
-                    const HostNode& n = nodes_[p.node];
-                    Job& j = jobs_[jobOf_[p.node]];
-                    FitTask& t = hTasks_.p[ti];
-                    float mn[3], mx[3];
-                    uint8_t depth = n.depth;
-                    if (p.isP) { memcpy(mn, n.mn, 12); memcpy(mx, n.mx, 12); }
-                    else { cornerAabb(n, p.child, mn, mx); depth = (uint8_t)(n.depth + 1); }
-                    t.cx = (mn[0] + mx[0]) / 2.0f; t.cy = (mn[1] + mx[1]) / 2.0f; t.cz = (mn[2] + mx[2]) / 2.0f;   // AlignedBox::center() in f32
-                    t.half = (mx[0] - mn[0]) * 0.5f;
-                    t.out = (uint32_t)poolUsed_;
-                    t.depth = depth; t.degree = (uint8_t)d; t.pad = 0;
-                    t.rec = (uint32_t)ti;
-                    if (p.isP && !j.coarse) { t.src = n.slot; t.degreeIn = n.degree; }
-                    else { t.src = kNoSrc; t.degreeIn = 0; }
-                    if (p.isP) j.pSlot = t.out; else j.hSlot[p.child] = t.out;
-                    poolUsed_ += (size_t)coeffCount(d);
-                    ++ti;
+                    FitTask& t = tasksD_[d][k];
+                    t.out = (uint32_t)poolUsed_; t.rec = (uint32_t)ti;
+                    Job& j = jobs_[ownerD_[d][k] >> 4];
+                    const uint32_t which = ownerD_[d][k] & 15u;
+                    if (which == 8u) j.pSlot = t.out; else j.hSlot[which] = t.out;
+                    poolUsed_ += cc; ++ti;
                 }
+                if (nd) memcpy(hTasks_.p + groupBegin[d], tasksD_[d].data(), nd * sizeof(FitTask));
             }
             groupBegin[kMaxDegree + 1] = ti;
-
             t_.stats.host_tasks_ms += nowMs() - tTask0;
+
             // ---- 2. upload, launch one kernel per degree present (this rank's shard), gather across ranks ----------
-            HPSDF_CUDA(cudaMemcpyAsync(dTasks_.p, hTasks_.p, nTasks * sizeof(FitTask), cudaMemcpyHostToDevice, stream_));
-            HPSDF_CUDA(cudaEventRecord(ev0_, stream_));
-            for (int d = 1; d <= kMaxDegree; ++d)
+            if (nTasks)
             {
-                const size_t n = byDegree[d].size();
-                if (!n) continue;
-                size_t b = 0, e = n;
-                if (world_ > 1) hpsdf_shard_range(n, rank_, world_, &b, &e);
-                if (e > b)
-                {
-                    HPSDF_CUDA(launchFitKernel(d, dTasks_.p + groupBegin[d] + b, (int)(e - b), pool_.p, dRecs_.p, prog_, t_.map, t_.ctx->fitTab, stream_));
-                    t_.stats.kernel_launches++;
-                }
-                t_.stats.fits_evaluated += n;
-                roundFlops += (double)n * (fitFlops(d) + sdfFlops_ * fitRule(d) * fitRule(d) * fitRule(d));
-                roundEvals += (uint64_t)n * fitRule(d) * fitRule(d) * fitRule(d);
-            }
-            HPSDF_CUDA(cudaEventRecord(ev1_, stream_));
-            if (world_ > 1)
-            {
-                // every rank receives every other rank's shard: coefficients and records (replicated pool, identical replay)
-                std::vector<CommSegment> segs;
+                HPSDF_CUDA(cudaMemcpyAsync(dTasks_.p, hTasks_.p, nTasks * sizeof(FitTask), cudaMemcpyHostToDevice, stream_));
+                HPSDF_CUDA(cudaEventRecord(ev0_, stream_));
                 for (int d = 1; d <= kMaxDegree; ++d)
                 {
-                    const size_t n = byDegree[d].size();
+                    const size_t n = tasksD_[d].size();
                     if (!n) continue;
-                    for (int r = 0; r < world_; ++r)
+                    size_t b = 0, e = n;
+                    if (world_ > 1) hpsdf_shard_range(n, rank_, world_, &b, &e);
+                    if (e > b)
                     {
-                        size_t b, e;
-                        hpsdf_shard_range(n, r, world_, &b, &e);
-                        if (e <= b) continue;
-                        segs.push_back({ pool_.p + groupPool[d] + b * (size_t)coeffCount(d), (e - b) * (size_t)coeffCount(d), r });
-                        segs.push_back({ (double*)(dRecs_.p + groupBegin[d] + b), (e - b) * 2, r });
+                        HPSDF_CUDA(launchFitKernel(d, dTasks_.p + groupBegin[d] + b, (int)(e - b), pool_.p, dRecs_.p, prog_, t_.map, t_.ctx->fitTab, stream_));
+                        t_.stats.kernel_launches++;
                     }
+                    t_.stats.fits_evaluated += n;
+                    roundFlops += (double)n * (fitFlops(d) + sdfFlops_ * fitRule(d) * fitRule(d) * fitRule(d));
+                    roundEvals += (uint64_t)n * fitRule(d) * fitRule(d) * fitRule(d);
                 }
-                hpsdf_status cs = commBroadcastSegments(o_.comm, segs, stream_);
-                if (cs != HPSDF_OK) return cs;
+                HPSDF_CUDA(cudaEventRecord(ev1_, stream_));
+                if (world_ > 1)
+                {
+                    // every rank receives every other rank's shard: coefficients and records (replicated pool, identical replay)
+                    std::vector<CommSegment> segs;
+                    for (int d = 1; d <= kMaxDegree; ++d)
+                    {
+                        const size_t n = tasksD_[d].size();
+                        if (!n) continue;
+                        for (int r = 0; r < world_; ++r)
+                        {
+                            size_t b, e;
+                            hpsdf_shard_range(n, r, world_, &b, &e);
+                            if (e <= b) continue;
+                            segs.push_back({ pool_.p + groupPool[d] + b * (size_t)coeffCount(d), (e - b) * (size_t)coeffCount(d), r });
+                            segs.push_back({ (double*)(dRecs_.p + groupBegin[d] + b), (e - b) * 2, r });
+                        }
+                    }
+                    hpsdf_status cs = commBroadcastSegments(o_.comm, segs, stream_);
+                    if (cs != HPSDF_OK) return cs;
+                }
+                HPSDF_CUDA(cudaMemcpyAsync(hRecs_.p, dRecs_.p, nTasks * sizeof(FitRecord), cudaMemcpyDeviceToHost, stream_));
+                const double tWait0 = nowMs();
+                HPSDF_CUDA(cudaStreamSynchronize(stream_));
+                t_.stats.device_wait_ms += nowMs() - tWait0;
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, ev0_, ev1_);
+                t_.stats.fit_kernel_ms += ms;
+                t_.stats.algorithmic_flops += roundFlops;
+                t_.stats.sdf_evals += roundEvals;
+                t_.stats.rounds++;
             }
-            HPSDF_CUDA(cudaMemcpyAsync(hRecs_.p, dRecs_.p, nTasks * sizeof(FitRecord), cudaMemcpyDeviceToHost, stream_));
-            const double tWait0 = nowMs();
-            HPSDF_CUDA(cudaStreamSynchronize(stream_));
-            t_.stats.device_wait_ms += nowMs() - tWait0;
-            float ms = 0.0f;
-            cudaEventElapsedTime(&ms, ev0_, ev1_);
-            t_.stats.fit_kernel_ms += ms;
-            t_.stats.algorithmic_flops += roundFlops;
-            t_.stats.sdf_evals += roundEvals;
-            t_.stats.rounds++;
             t_.stats.jobs_evaluated += jobs_.size() - firstJob;
 
-            // ---- 3. errors, improvements (host, same expressions and libm as the CPU checker) ------------------------
-            // walk the tasks again in the same order to attach records to jobs
+            // ---- 3. errors (host, same expressions and libm as the CPU checker); the evaluated leaves enter the heap ------
+            const double tRec0 = nowMs();
             ti = 0;
             for (int d = 1; d <= kMaxDegree; ++d)
-                for (const Proto& p : byDegree[d])
-                {
-                    const HostNode& n = nodes_[p.node];
-                    Job& j = jobs_[jobOf_[p.node]];
-                    const FitRecord& r = hRecs_.p[ti++];
-                    if (p.isP) j.pErr = r.rawErr * nearnessWeight(cfg_, r.c0, n.depth);
-                    else       j.hErr[p.child] = r.rawErr * nearnessWeight(cfg_, r.c0, n.depth + 1u);
-                }
-            for (size_t k = firstJob; k < jobs_.size(); ++k)
             {
-                Job& j = jobs_[k];
-                if (j.coarse) { j.hImp = 0.0; j.pImp = j.pErr; }                                         // Octree.cpp:806-810, 836-843
+                const size_t nd = tasksD_[d].size();
+                for (size_t k = 0; k < nd; ++k, ++ti)
+                {
+                    Job& j = jobs_[ownerD_[d][k] >> 4];
+                    const uint32_t which = ownerD_[d][k] & 15u;
+                    const FitRecord& r = hRecs_.p[ti];
+                    const double e = r.rawErr * nearnessWeight(cfg_, r.c0, tasksD_[d][k].depth);
+                    if (which == 8u) j.pErr = e; else j.hErr[which] = e;
+                }
             }
+            for (size_t k = firstJob; k < jobs_.size(); ++k)
+                if (jobs_[k].coarse) { jobs_[k].hImp = 0.0; jobs_[k].pImp = jobs_[k].pErr; }             // Octree.cpp:806-810, 836-843
+            for (uint64_t idx : evaluated_) queue_.push({ idx, errOf_[idx] });
+            t_.stats.host_tasks_ms += nowMs() - tRec0;
             return HPSDF_OK;
         }
 
@@ -350,8 +379,8 @@ namespace hpsdf
             levelLogStart_ = t_.applyLog.size();
             applyLevel_ = inf;
             double remaining = checkValue();
-            evalLevel_ = queue_.empty() ? 0.0 : queue_.top().second;
-            if (!(remaining >= thr) || queue_.empty()) { t_.stats.host_select_ms += nowMs() - tSel0; return; }
+            evalLevel_ = conceptualTop();
+            if (!(remaining >= thr) || (queue_.empty() && pending_.empty())) { t_.stats.host_select_ms += nowMs() - tSel0; return; }
             int b = kBuckets - 1, crossing = -1;
             for (; b >= 0; --b)
             {
@@ -365,6 +394,7 @@ namespace hpsdf
             {
                 std::vector<double> errs;
                 for (const auto& e : queue_.entries()) if (bucketOf(e.second) == crossing) errs.push_back(e.second);
+                for (uint64_t idx : pending_) if (bucketOf(errOf_[idx]) == crossing) errs.push_back(errOf_[idx]);
                 std::sort(errs.begin(), errs.end(), std::greater<double>());
                 size_t k = 0;
                 for (; k < errs.size() && remaining >= thr; ++k) remaining -= errs[k] * (1.0 + 1e-9);
@@ -422,7 +452,6 @@ namespace hpsdf
                 nodes_[idx].degree = (uint8_t)(j.coarse ? kCoarseDegree : p + 1);
                 errOf_[idx] = j.pErr;
                 qPush(idx, j.pErr);                                                                  // Octree.cpp:289-290
-                pending_.push_back(idx);
                 t_.stats.jobs_applied_p++;
                 t_.applyLog.push_back({ idx, 0u, p, err, j.pErr, j.pImp, j.hImp, checkValue() });
             }
@@ -445,7 +474,6 @@ namespace hpsdf
                     nodes_[c].degree = (uint8_t)p;
                     errOf_[c] = j.hErr[i];
                     qPush(c, j.hErr[i]);
-                    pending_.push_back(c);
                     mx = std::max(mx, j.hErr[i]);
                 }
                 t_.stats.jobs_applied_h++;
@@ -465,49 +493,48 @@ namespace hpsdf
                        (double)(nodes_[idx].mn[1] + nodes_[idx].mx[1]) / 2.0, (double)(nodes_[idx].mn[2] + nodes_[idx].mx[2]) / 2.0);
         }
 
-        // The reference's scheduler loop (Octree.cpp:213-302) driven by cached job results. Entries at or above the
-        // guaranteed level are applied as soon as their result is cached, stepping over uncached ones (which wait for the
-        // next batch); below the level the loop is the strict one: termination check, then pop the top if it is cached.
-        // Every time the strict part is reached the state is one the sequential greedy loop also passes through.
+        // The reference's scheduler loop (Octree.cpp:213-302) driven by cached job results. The heap holds only leaves whose
+        // job is cached; leaves still waiting for a batch sit in pending_ (pendingMax_ = their largest error), so the
+        // conceptual queue of the reference = heap + pending. Entries at or above the guaranteed level are applied as soon
+        // as they are cached; below the level the loop is the strict one: termination check, then pop the overall maximum
+        // if it is cached. Every time the strict part is reached the state is one the sequential greedy loop passes through.
         bool Builder::replay()
         {
             const double thr = cfg_.target_error_threshold;
-            deferred_.clear();
+            const double inf = std::numeric_limits<double>::infinity();
             bool done = false;
+            levelTried_ = false;
             for (;;)
             {
-                if (queue_.empty()) { done = deferred_.empty(); break; }
-                const std::pair<uint64_t, double> top = queue_.top();                                    // Octree.cpp:231
-                const uint64_t idx = top.first;
-                const bool cached = idx < jobOf_.size() && jobOf_[idx] >= 0;
-                if (top.second >= applyLevel_)
+                if (queue_.empty() && pending_.empty()) { done = true; break; }                          // nodeQueue.empty(), Octree.cpp:216
+                if (!queue_.empty() && queue_.top().second >= applyLevel_)
                 {
-                    qPop();
-                    if (cached) applyJob(idx, top.second); else deferred_.push_back(top);
+                    const std::pair<uint64_t, double> top = queue_.top();
+                    hPop();
+                    applyJob(top.first, top.second);
                     continue;
                 }
-                if (!deferred_.empty()) break;            // entries above the level still wait for their results
+                if (pendingMax_ >= applyLevel_ && !pending_.empty()) break;     // entries above the level still wait for their results
                 if (checkValue() < thr) { done = true; break; }                                          // Octree.cpp:216
-                if (cached)
+                if (!queue_.empty() && (pending_.empty() || queue_.top().second >= pendingMax_))
                 {
-                    qPop();
-                    applyJob(idx, top.second);            // strict step; the state after it is a sequential-greedy state
-                    applyLevel_ = std::numeric_limits<double>::infinity();      // a level is only valid for the state it was computed in
+                    const std::pair<uint64_t, double> top = queue_.top();                                // Octree.cpp:231: the overall maximum
+                    hPop();
+                    applyJob(top.first, top.second);          // strict step; the state after it is a sequential-greedy state
+                    applyLevel_ = inf;                        // a level is only valid for the state it was computed in
+                    levelTried_ = false;
                     continue;
                 }
-                // the top has no cached result. This is a sequential-greedy state: find the level down to which entries are
-                // certain to be popped, so the loop can go on past the top (once per stall)
-                if (!o_.strict_order && applyLevel_ == std::numeric_limits<double>::infinity() && !levelTried_)
+                // the overall maximum has no cached result. This is a sequential-greedy state: find the level down to which
+                // entries are certain to be popped, so the loop can go on past it (once per state)
+                if (!o_.strict_order && applyLevel_ == inf && !levelTried_)
                 {
                     computeLevel();
                     levelTried_ = true;
-                    if (top.second >= applyLevel_) continue;
+                    if (!queue_.empty() && queue_.top().second >= applyLevel_) continue;
                 }
                 break;
             }
-            levelTried_ = false;
-            for (const auto& d : deferred_) qPush(d.first, d.second);
-            if (!done && deferred_.empty() && queue_.empty()) done = true;
             return done;
         }
 
@@ -517,7 +544,7 @@ namespace hpsdf
         // other members of the group. Log the whole group: kind 2 = refined before the cut, kind 3 = left unrefined.
         void Builder::logCutTies()
         {
-            if (t_.applyLog.empty() || queue_.empty()) return;
+            if (t_.applyLog.empty() || (queue_.empty() && pending_.empty())) return;
             // the sequential loop's last pop is the smallest-error entry applied since the last sequential state
             double eLast = t_.applyLog.back().initial_err;
             for (size_t k = std::min(levelLogStart_, t_.applyLog.size() - 1); k < t_.applyLog.size(); ++k) eLast = std::min(eLast, t_.applyLog[k].initial_err);
@@ -610,13 +637,18 @@ namespace hpsdf
             errOf_.assign(nodes_.size(), kInitialErr);
             jobOf_.assign(nodes_.size(), -1);
             inQueue_.assign(nodes_.size(), 0);
-            for (uint64_t idx : pending_) qPush(idx, kInitialErr);                                      // Octree.cpp:176-177
+            {
+                std::vector<uint64_t> coarse;
+                coarse.swap(pending_);
+                for (uint64_t idx : coarse) qPush(idx, kInitialErr);                                    // Octree.cpp:176-177
+            }
             total_ = std::pow(8, 4) * kInitialErr;                                                      // Octree.cpp:212
-            unfitted_ = (long)queue_.size();
+            unfitted_ = (long)pending_.size();
             lastTotal_ = totalBeforeLast_ = total_;
             computeLevel();
 
             double replayMs = 0.0;
+            size_t stallGuard = 0;
             for (;;)
             {
                 st = evaluateRound();
@@ -626,6 +658,7 @@ namespace hpsdf
                 replayMs += nowMs() - r0;
                 if (done) break;
                 if (pending_.empty()) { setLastError("internal: replay stalled with nothing to evaluate"); st = HPSDF_ERR_CUDA; break; }
+                if (++stallGuard > 100000) { setLastError("internal: build does not converge"); st = HPSDF_ERR_CUDA; break; }
             }
             const double tPack0 = nowMs();
             if (st == HPSDF_OK) st = pack();
