@@ -91,6 +91,7 @@ namespace hpsdf
             std::vector<FitTask>     tasksD_[kMaxDegree + 1];
             std::vector<uint32_t>    ownerD_[kMaxDegree + 1]; // per task: job index << 4 | child slot (8 = the p-fit)
             std::vector<uint64_t>    evaluated_;
+            std::vector<uint64_t>    coarseReady_;           // coarse cells whose degree-2 fit is cached
             bool                     levelTried_ = false;
             double                   evalLevel_ = 0.0;       // guaranteed level used to choose what to evaluate (also in strict mode)
             std::vector<int32_t>     jobOf_;        // per node: index into jobs_, -1 = no cached result
@@ -360,7 +361,11 @@ namespace hpsdf
             }
             for (size_t k = firstJob; k < jobs_.size(); ++k)
                 if (jobs_[k].coarse) { jobs_[k].hImp = 0.0; jobs_[k].pImp = jobs_[k].pErr; }             // Octree.cpp:806-810, 836-843
-            for (uint64_t idx : evaluated_) queue_.push({ idx, errOf_[idx] });
+            for (uint64_t idx : evaluated_)
+            {
+                if (jobs_[jobOf_[idx]].coarse) coarseReady_.push_back(idx);      // applied in the reference's pop order, see replay()
+                else queue_.push({ idx, errOf_[idx] });
+            }
             t_.stats.host_tasks_ms += nowMs() - tRec0;
             return HPSDF_OK;
         }
@@ -504,6 +509,34 @@ namespace hpsdf
             const double inf = std::numeric_limits<double>::infinity();
             bool done = false;
             levelTried_ = false;
+            if (!coarseReady_.empty())
+            {
+                // Coarse stage (Octree.cpp:112-191, 228-238): all 16^3 cells sit in the reference's queue with err = 100; each is
+                // popped, fitted and pushed back with its real error. The ORDER in which the equal keys pop is a property of
+                // the heap algorithm and of the re-pushed entries, and it matters: totalCoeffError starts at 8^4 * 100, so
+                // the first errors added are rounded at ulp(4e5) = 5.8e-11 and the running total depends on the order at
+                // the 1e-9 level. Replay the same push/pop sequence on a scratch std::priority_queue.
+                std::priority_queue<std::pair<uint64_t, double>, std::vector<std::pair<uint64_t, double>>, QueuePredicate> sim;
+                for (uint64_t idx : coarseReady_) sim.push({ idx, kInitialErr });                         // visiting order, Octree.cpp:176-177
+                std::vector<uint64_t> order;
+                order.reserve(coarseReady_.size());
+                for (size_t k = 0; k < coarseReady_.size(); ++k)
+                {
+                    const std::pair<uint64_t, double> top = sim.top();
+                    sim.pop();
+                    order.push_back(top.first);
+                    sim.push({ top.first, jobs_[jobOf_[top.first]].pErr });
+                }
+                for (uint64_t idx : order)
+                {
+                    inQueue_[idx] = 0;
+                    const int b = bucketOf(kInitialErr);
+                    if (--bucketCount_[b] == 0) bucketSum_[b] = 0.0; else bucketSum_[b] -= kInitialErr;
+                    applyJob(idx, kInitialErr);
+                }
+                coarseReady_.clear();
+                applyLevel_ = inf;
+            }
             for (;;)
             {
                 if (queue_.empty() && pending_.empty()) { done = true; break; }                          // nodeQueue.empty(), Octree.cpp:216

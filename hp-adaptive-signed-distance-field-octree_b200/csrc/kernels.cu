@@ -39,19 +39,21 @@ namespace hpsdf
         cudaMemcpyToSymbol(c_lm1, lm1, sizeof(lm1));
     }
 
+    static const uint32_t* g_bidxDev[16] = { nullptr };
+    void setBidxDev(int device, const uint32_t* p) { g_bidxDev[device & 15] = p; }
+
     cudaError_t launchQuery(const DeviceTreeView& view, const double* dXyz, size_t n, double* dOut, int smCount, cudaStream_t stream)
     {
         if (!n) return cudaSuccess;
         const size_t tiles = (n + kQueryThreads - 1) / kQueryThreads;
         // persistent grid: 8 CTAs of 256 threads per SM (22 KB shared memory each), fewer if the batch is small
-        size_t grid = (size_t)(smCount > 0 ? smCount : 148) * 8;
+        size_t grid = (size_t)(smCount > 0 ? smCount : 148) * 3;
         if (grid > tiles) grid = tiles;
-        queryKernel<<<(unsigned)grid, kQueryThreads, 0, stream>>>(view, dXyz, n, dOut);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        queryKernel<<<(unsigned)grid, kQueryThreads, 0, stream>>>(view, dXyz, n, dOut, g_bidxDev[dev & 15]);
         return cudaGetLastError();
     }
-
-    static const uint32_t* g_bidxDev[16] = { nullptr };
-    void setBidxDev(int device, const uint32_t* p) { g_bidxDev[device & 15] = p; }
 
     cudaError_t launchQueryGradient(const DeviceTreeView& view, const double* dXyz, size_t n, double* dOut, double* dGrad, cudaStream_t stream)
     {

@@ -12,37 +12,42 @@ namespace hpsdf
 {
     constexpr int kQueryThreads = 256;
 
-    __global__ void __launch_bounds__(kQueryThreads)
-    queryKernel(const DeviceTreeView view, const double* __restrict__ xyz, size_t n, double* __restrict__ out)
+    __global__ void __launch_bounds__(kQueryThreads, 3)
+    queryKernel(const DeviceTreeView view, const double* __restrict__ xyz, size_t n, double* __restrict__ out,
+                const uint32_t* __restrict__ bidx)
     {
         __shared__ uint32_t sTop[4096];
-        __shared__ __align__(16) double sPts[kQueryThreads * 3];
+        __shared__ __align__(16) double sPts[kQueryThreads / 32][96];          // per warp: 32 points x 3 doubles
         const bool useTop = view.top != nullptr;
         if (useTop)
+        {
             for (int i = threadIdx.x; i < 1024; i += kQueryThreads)
                 reinterpret_cast<uint4*>(sTop)[i] = __ldg(reinterpret_cast<const uint4*>(view.top) + i);
-
-        const size_t nTiles = (n + kQueryThreads - 1) / kQueryThreads;
-        for (size_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x)
+            __syncthreads();                        // the only block-wide barrier: the table is read-only afterwards
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const size_t nGroups = (n + 31) / 32;                                   // a warp handles 32 consecutive points
+        const size_t warpsTotal = (size_t)gridDim.x * (kQueryThreads / 32);
+        double* sp = sPts[warp];
+        for (size_t g = (size_t)blockIdx.x * (kQueryThreads / 32) + warp; g < nGroups; g += warpsTotal)
         {
-            const size_t base = tile * kQueryThreads;
-            const size_t cnt  = n - base < (size_t)kQueryThreads ? n - base : (size_t)kQueryThreads;
-            __syncthreads();                       // previous tile's reads of sPts are done (and sTop is ready)
-            const double* src = xyz + 3 * base;    // 3 * 256 * 8 B = 6144 B per tile: base of a tile is 16-byte aligned
-            if (cnt == (size_t)kQueryThreads)
+            const size_t base = g * 32;
+            const size_t cnt = n - base < 32 ? n - base : 32;
+            const double* src = xyz + 3 * base;                                 // 32 * 24 B = 768 B: 16-byte aligned
+            if (cnt == 32)
             {
-                for (int v = threadIdx.x; v < kQueryThreads * 3 / 2; v += kQueryThreads)
-                    reinterpret_cast<double2*>(sPts)[v] = __ldcs(reinterpret_cast<const double2*>(src) + v);
+                reinterpret_cast<double2*>(sp)[lane] = __ldcs(reinterpret_cast<const double2*>(src) + lane);
+                if (lane < 16) reinterpret_cast<double2*>(sp)[32 + lane] = __ldcs(reinterpret_cast<const double2*>(src) + 32 + lane);
             }
             else
-                for (size_t v = threadIdx.x; v < 3 * cnt; v += kQueryThreads) sPts[v] = src[v];
-            __syncthreads();
-            if (threadIdx.x < cnt)
-            {
-                const double x = sPts[3 * threadIdx.x], y = sPts[3 * threadIdx.x + 1], z = sPts[3 * threadIdx.x + 2];
-                const double v = queryPoint(view.nodes, view.coeffs, useTop ? sTop : nullptr, view.map, x, y, z);
-                __stcs(out + base + threadIdx.x, v);
-            }
+                for (size_t v = lane; v < 3 * cnt; v += 32) sp[v] = src[v];
+            __syncwarp();
+            LeafHit h;
+            h.coeffs = view.coeffs; h.ux = h.uy = h.uz = 0.0; h.degree = -1; h.depth = 0;
+            if ((size_t)lane < cnt) h = findLeaf(view.nodes, view.coeffs, useTop ? sTop : nullptr, view.map, sp[3 * lane], sp[3 * lane + 1], sp[3 * lane + 2]);
+            __syncwarp();                           // sp is overwritten by the next group
+            const double v = evalWarp(h, bidx);
+            if ((size_t)lane < cnt) __stcs(out + base + lane, v);
         }
     }
 
