@@ -18,7 +18,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libhpsdf.so")
+LIB_PATH = os.environ.get("HPSDF_LIB", os.path.join(HERE, "lib", "libhpsdf.so"))
 
 # ---- enums (include/hpsdf.h) ---------------------------------------------------------------------------------------
 OK, ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_BAD_BLOCK, ERR_UNSUPPORTED, ERR_COMM, ERR_OOM, ERR_MESH = range(9)

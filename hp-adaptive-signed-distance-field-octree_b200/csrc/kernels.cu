@@ -46,8 +46,8 @@ namespace hpsdf
     {
         if (!n) return cudaSuccess;
         const size_t tiles = (n + kQueryThreads - 1) / kQueryThreads;
-        // persistent grid: 8 CTAs of 256 threads per SM (22 KB shared memory each), fewer if the batch is small
-        size_t grid = (size_t)(smCount > 0 ? smCount : 148) * 3;
+        // persistent grid: as many CTAs of 256 threads per SM as the register budget allows, fewer if the batch is small
+        size_t grid = (size_t)(smCount > 0 ? smCount : 148) * kQueryBlocksPerSm;
         if (grid > tiles) grid = tiles;
         int dev = 0;
         cudaGetDevice(&dev);

@@ -11,8 +11,12 @@
 namespace hpsdf
 {
     constexpr int kQueryThreads = 256;
+#ifndef HPSDF_QUERY_MINBLOCKS
+#define HPSDF_QUERY_MINBLOCKS 4
+#endif
+    constexpr int kQueryBlocksPerSm = HPSDF_QUERY_MINBLOCKS;
 
-    __global__ void __launch_bounds__(kQueryThreads, 3)
+    __global__ void __launch_bounds__(kQueryThreads, kQueryBlocksPerSm)
     queryKernel(const DeviceTreeView view, const double* __restrict__ xyz, size_t n, double* __restrict__ out,
                 const uint32_t* __restrict__ bidx)
     {
