@@ -88,8 +88,7 @@ namespace hpsdf
             double                   applyLevel_ = std::numeric_limits<double>::infinity();   // entries >= this are certain to be popped
             size_t                   levelLogStart_ = 0;     // first apply-log entry of the current level
             double                   pendingMax_ = 0.0;      // largest error among pending_ (uncached) leaves
-            std::vector<FitTask>     tasksD_[kMaxDegree + 1];
-            std::vector<uint32_t>    ownerD_[kMaxDegree + 1]; // per task: job index << 4 | child slot (8 = the p-fit)
+            std::vector<uint32_t>    owner_;                 // per task: job index << 4 | child slot (8 = the p-fit)
             std::vector<uint64_t>    evaluated_;
             std::vector<uint64_t>    coarseReady_;           // coarse cells whose degree-2 fit is cached
             bool                     levelTried_ = false;
@@ -203,9 +202,10 @@ namespace hpsdf
             for (uint32_t k = 0; k < o_.speculate; ++k) level *= 0.125;
 
             const double tTask0 = nowMs();
-            for (int d = 0; d <= kMaxDegree; ++d) { tasksD_[d].clear(); ownerD_[d].clear(); }
+            // pass A: select, create the jobs, count fits per degree
             const size_t firstJob = jobs_.size();
             evaluated_.clear();
+            size_t cnt[kMaxDegree + 2] = { 0 };
             size_t keepN = 0;
             pendingMax_ = 0.0;
             for (size_t k = 0; k < pending_.size(); ++k)
@@ -213,49 +213,32 @@ namespace hpsdf
                 const uint64_t idx = pending_[k];
                 if (errOf_[idx] < level) { pending_[keepN++] = idx; pendingMax_ = std::max(pendingMax_, errOf_[idx]); continue; }
                 const HostNode& n = nodes_[idx];
-                const uint32_t jobIdx = (uint32_t)jobs_.size();
                 jobs_.emplace_back();
                 Job& j = jobs_.back();
                 j.coarse = std::abs(errOf_[idx] - kInitialErr) < std::numeric_limits<double>::epsilon() && n.degree == 0;   // Octree.cpp:806, 831
-                FitTask t;
-                t.pad = 0; t.rec = 0; t.out = 0;
-                if (j.coarse)
-                {
-                    j.doP = true;
-                    t.cx = (n.mn[0] + n.mx[0]) / 2.0f; t.cy = (n.mn[1] + n.mx[1]) / 2.0f; t.cz = (n.mn[2] + n.mx[2]) / 2.0f;   // AlignedBox::center() in f32
-                    t.half = (n.mx[0] - n.mn[0]) * 0.5f;
-                    t.depth = n.depth; t.degree = (uint8_t)kCoarseDegree; t.degreeIn = 0; t.src = kNoSrc;
-                    tasksD_[kCoarseDegree].push_back(t); ownerD_[kCoarseDegree].push_back(jobIdx << 4 | 8u);
-                }
+                if (j.coarse) { j.doP = true; cnt[kCoarseDegree]++; }
                 else
                 {
                     j.doH = n.depth < o_.max_depth;             // child fits at depth > TREE_MAX_DEPTH are never used (Octree.cpp:600-601)
                     j.doP = n.degree < o_.max_degree;           // nor is the p-fit of a max-degree node
-                    if (j.doH)
-                        for (uint32_t c = 0; c < 8; ++c)
-                        {
-                            float mn[3], mx[3];
-                            cornerAabb(n, c, mn, mx);                                                          // Octree.cpp:820
-                            t.cx = (mn[0] + mx[0]) / 2.0f; t.cy = (mn[1] + mx[1]) / 2.0f; t.cz = (mn[2] + mx[2]) / 2.0f;
-                            t.half = (mx[0] - mn[0]) * 0.5f;
-                            t.depth = (uint8_t)(n.depth + 1); t.degree = n.degree; t.degreeIn = 0; t.src = kNoSrc;
-                            tasksD_[n.degree].push_back(t); ownerD_[n.degree].push_back(jobIdx << 4 | c);
-                        }
-                    if (j.doP)
-                    {
-                        t.cx = (n.mn[0] + n.mx[0]) / 2.0f; t.cy = (n.mn[1] + n.mx[1]) / 2.0f; t.cz = (n.mn[2] + n.mx[2]) / 2.0f;
-                        t.half = (n.mx[0] - n.mn[0]) * 0.5f;
-                        t.depth = n.depth; t.degree = (uint8_t)(n.degree + 1); t.degreeIn = n.degree; t.src = n.slot;        // Octree.cpp:846-851
-                        tasksD_[n.degree + 1].push_back(t); ownerD_[n.degree + 1].push_back(jobIdx << 4 | 8u);
-                    }
+                    if (j.doH) cnt[n.degree] += 8;
+                    if (j.doP) cnt[n.degree + 1]++;
                 }
-                jobOf_[idx] = (int32_t)jobIdx;
+                jobOf_[idx] = (int32_t)(jobs_.size() - 1);
                 evaluated_.push_back(idx);
             }
             pending_.resize(keepN);
 
+            // Tasks in degree order; task index == record index; slots allocated in task order (contiguous per degree,
+            // so a rank's shard of a degree group is one contiguous pool range).
             size_t nTasks = 0, poolNeed = poolUsed_;
-            for (int d = 1; d <= kMaxDegree; ++d) { nTasks += tasksD_[d].size(); poolNeed += tasksD_[d].size() * (size_t)coeffCount(d); }
+            size_t groupBegin[kMaxDegree + 2] = { 0 }, groupPool[kMaxDegree + 2] = { 0 }, cursor[kMaxDegree + 2] = { 0 };
+            for (int d = 1; d <= kMaxDegree; ++d)
+            {
+                groupBegin[d] = cursor[d] = nTasks; groupPool[d] = poolNeed;
+                nTasks += cnt[d]; poolNeed += cnt[d] * (size_t)coeffCount(d);
+            }
+            groupBegin[kMaxDegree + 1] = nTasks;
             if (poolNeed >= 0xFFFFFFF0ull) { setLastError("coefficient pool exceeds 2^32 doubles"); return HPSDF_ERR_OOM; }
             if (nTasks)
             {
@@ -265,29 +248,40 @@ namespace hpsdf
                 HPSDF_CUDA(hTasks_.reserve(nTasks));
                 HPSDF_CUDA(hRecs_.reserve(nTasks));
             }
-            // Tasks in degree order; task index == record index; slots allocated in task order (contiguous per degree,
-            // so a rank's shard of a degree group is one contiguous pool range).
-            size_t ti = 0;
-            size_t groupBegin[kMaxDegree + 2] = { 0 };
-            size_t groupPool[kMaxDegree + 2] = { 0 };
-            double roundFlops = 0.0; uint64_t roundEvals = 0;
-            for (int d = 1; d <= kMaxDegree; ++d)
+            owner_.resize(nTasks);
+            // pass B: write the 32-byte task descriptors straight into pinned memory. Cells are dyadic, so centre and half size
+            // of a child follow exactly (in f32) from the parent's: c +- h/2, h/2 — the values CornerAABB + center() give.
+            FitTask* T = hTasks_.p;
+            auto emit = [&](int d, float cx, float cy, float cz, float half, uint8_t depth, uint8_t degreeIn, uint32_t src, uint32_t own) -> uint32_t
             {
-                groupBegin[d] = ti; groupPool[d] = poolUsed_;
-                const size_t nd = tasksD_[d].size();
-                const uint32_t cc = (uint32_t)coeffCount(d);
-                for (size_t k = 0; k < nd; ++k)
+                const size_t pos = cursor[d]++;
+                FitTask& t = T[pos];
+                t.cx = cx; t.cy = cy; t.cz = cz; t.half = half;
+                t.out = (uint32_t)(groupPool[d] + (pos - groupBegin[d]) * (size_t)coeffCount(d));
+                t.src = src; t.depth = depth; t.degree = (uint8_t)d; t.degreeIn = degreeIn; t.pad = 0; t.rec = (uint32_t)pos;
+                owner_[pos] = own;
+                return t.out;
+            };
+            for (size_t k = 0; k < evaluated_.size(); ++k)
+            {
+                const uint64_t idx = evaluated_[k];
+                const HostNode& n = nodes_[idx];
+                const uint32_t jobIdx = (uint32_t)(firstJob + k);
+                Job& j = jobs_[jobIdx];
+                const float cx = (n.mn[0] + n.mx[0]) / 2.0f, cy = (n.mn[1] + n.mx[1]) / 2.0f, cz = (n.mn[2] + n.mx[2]) / 2.0f;   // AlignedBox::center() in f32
+                const float half = (n.mx[0] - n.mn[0]) * 0.5f;
+                if (j.coarse) { j.pSlot = emit(kCoarseDegree, cx, cy, cz, half, n.depth, 0, kNoSrc, jobIdx << 4 | 8u); continue; }   // Octree.cpp:840
+                if (j.doH)
                 {
-                    FitTask& t = tasksD_[d][k];
-                    t.out = (uint32_t)poolUsed_; t.rec = (uint32_t)ti;
-                    Job& j = jobs_[ownerD_[d][k] >> 4];
-                    const uint32_t which = ownerD_[d][k] & 15u;
-                    if (which == 8u) j.pSlot = t.out; else j.hSlot[which] = t.out;
-                    poolUsed_ += cc; ++ti;
+                    const float q = half * 0.5f;
+                    for (uint32_t c = 0; c < 8; ++c)                                                                 // Octree.cpp:820
+                        j.hSlot[c] = emit(n.degree, cx + ((c & 1) ? q : -q), cy + ((c & 2) ? q : -q), cz + ((c & 4) ? q : -q), q,
+                                          (uint8_t)(n.depth + 1), 0, kNoSrc, jobIdx << 4 | c);
                 }
-                if (nd) memcpy(hTasks_.p + groupBegin[d], tasksD_[d].data(), nd * sizeof(FitTask));
+                if (j.doP) j.pSlot = emit(n.degree + 1, cx, cy, cz, half, n.depth, n.degree, n.slot, jobIdx << 4 | 8u);   // Octree.cpp:846-851
             }
-            groupBegin[kMaxDegree + 1] = ti;
+            poolUsed_ = poolNeed;
+            double roundFlops = 0.0; uint64_t roundEvals = 0;
             t_.stats.host_tasks_ms += nowMs() - tTask0;
 
             // ---- 2. upload, launch one kernel per degree present (this rank's shard), gather across ranks ----------
@@ -297,7 +291,7 @@ namespace hpsdf
                 HPSDF_CUDA(cudaEventRecord(ev0_, stream_));
                 for (int d = 1; d <= kMaxDegree; ++d)
                 {
-                    const size_t n = tasksD_[d].size();
+                    const size_t n = cnt[d];
                     if (!n) continue;
                     size_t b = 0, e = n;
                     if (world_ > 1) hpsdf_shard_range(n, rank_, world_, &b, &e);
@@ -317,7 +311,7 @@ namespace hpsdf
                     std::vector<CommSegment> segs;
                     for (int d = 1; d <= kMaxDegree; ++d)
                     {
-                        const size_t n = tasksD_[d].size();
+                        const size_t n = cnt[d];
                         if (!n) continue;
                         for (int r = 0; r < world_; ++r)
                         {
@@ -346,18 +340,14 @@ namespace hpsdf
 
             // ---- 3. errors (host, same expressions and libm as the CPU checker); the evaluated leaves enter the heap ------
             const double tRec0 = nowMs();
-            ti = 0;
-            for (int d = 1; d <= kMaxDegree; ++d)
+            const bool weighted = cfg_.nearness_type != HPSDF_NEARNESS_NONE;
+            for (size_t ti = 0; ti < nTasks; ++ti)
             {
-                const size_t nd = tasksD_[d].size();
-                for (size_t k = 0; k < nd; ++k, ++ti)
-                {
-                    Job& j = jobs_[ownerD_[d][k] >> 4];
-                    const uint32_t which = ownerD_[d][k] & 15u;
-                    const FitRecord& r = hRecs_.p[ti];
-                    const double e = r.rawErr * nearnessWeight(cfg_, r.c0, tasksD_[d][k].depth);
-                    if (which == 8u) j.pErr = e; else j.hErr[which] = e;
-                }
+                Job& j = jobs_[owner_[ti] >> 4];
+                const uint32_t which = owner_[ti] & 15u;
+                const FitRecord& r = hRecs_.p[ti];
+                const double e = weighted ? r.rawErr * nearnessWeight(cfg_, r.c0, hTasks_.p[ti].depth) : r.rawErr;
+                if (which == 8u) j.pErr = e; else j.hErr[which] = e;
             }
             for (size_t k = firstJob; k < jobs_.size(); ++k)
                 if (jobs_[k].coarse) { jobs_[k].hImp = 0.0; jobs_[k].pImp = jobs_[k].pErr; }             // Octree.cpp:806-810, 836-843

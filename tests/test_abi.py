@@ -84,11 +84,12 @@ def test_compute_fails_loudly_without_a_gpu(hp):
 
 
 def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package may import, link or call it."""
     pkg = os.path.join(ROOT, "hp-adaptive-signed-distance-field-octree_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f)).read()
-                assert "oracle/" not in text.replace("under oracle/", "").replace("anything oracle/", "") or f == "__init__.py" and "import" not in [l for l in text.splitlines() if "oracle" in l and l.strip().startswith(("import", "from"))], f
-                assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
-                assert "hp_oracle" not in text and "hpref" not in text, f
+                assert not re.search(r"^\s*(from|import)\s+\.*oracle", text, re.M), f
+                assert "hp_oracle" not in text and "hpref" not in text and "libhporacle" not in text, f
+                assert not re.search(r'#include\s+"[^"]*oracle', text), f

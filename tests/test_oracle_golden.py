@@ -89,3 +89,16 @@ def test_query_gradient_is_unit_and_matches_finite_difference(oracle):
     # sphere: gradient points away from the centre
     n = pts / np.linalg.norm(pts, axis=1)[:, None]
     assert (np.einsum("ij,ij->i", n, g) > 0.99).all()
+
+
+def test_mesh_distance_matches_reference_golden(oracle):
+    """Float32 mesh signed distance restatement (oracle/hp_oracle_mesh.h) against Mesh::SignedDistanceAtPt of the
+    reference (golden generated through its own BVH): bit-exact."""
+    from meshgen import bumpy_torus
+    v, t = bumpy_torus(60, 40)
+    m = oracle.OracleMesh(v, t)
+    g = golden("mesh_torus")
+    assert np.array_equal(m.sdf(g["pts"], True, 8), g["sdf"])
+    assert np.array_equal(m.sdf(g["pts"][:1500], False, 8), g["sdf"][:1500])          # brute force == BVH (MeshingUnitTests.cpp:92-138)
+    with pytest.raises(ValueError):
+        oracle.OracleMesh(v, t[:-1])                                                  # open mesh: an edge has no twin

@@ -80,3 +80,27 @@ def test_literal_reference_create_agrees_within_its_own_test_tolerance(ref, orac
     assert np.abs(lit.query(pts, 8) - truth).max() <= 0.01
     assert np.abs(det.query(pts, 8) - truth).max() <= 0.01
     assert ref.parse_block(lit.block())["n_nodes"] == ref.parse_block(det.block())["n_nodes"]
+
+
+def test_mesh_distance_bit_identical(ref, oracle):
+    """Mesh::SignedDistanceAtPt through the reference's own BVH and by brute force == the restatement, bit for bit; also on
+    the one mesh the reference ships (Resources/halfedge_fail.obj) where /root/reference is present."""
+    import os
+    from meshgen import bumpy_torus, mesh_root
+    v, t = bumpy_torus(48, 32)
+    rm, om = ref.RefMesh.create(v, t, bvh=True), oracle.OracleMesh(v, t)
+    lo, hi = mesh_root(v)
+    pts = np.random.default_rng(0).uniform(lo, hi, (20000, 3)).astype(np.float32)
+    a = rm.sdf(pts, True, 8)
+    assert np.array_equal(a, om.sdf(pts, True, 8))
+    assert np.array_equal(rm.sdf(pts[:1000], False, 8), om.sdf(pts[:1000], False, 8))
+    assert np.array_equal(a[:1000], rm.sdf(pts[:1000], False, 8))                     # the reference's own BVH-vs-brute-force test
+    assert ref.RefMesh.create(v, t[:-1]) is None                                     # CreateHalfEdges fails on an open mesh
+    obj = "/root/reference/Resources/halfedge_fail.obj"
+    if os.path.exists(obj):
+        rm2 = ref.RefMesh.load_obj(obj, bvh=True)
+        v2, t2 = rm2.arrays()
+        om2 = oracle.OracleMesh(v2, t2)
+        lo2, hi2 = mesh_root(v2)
+        p2 = np.random.default_rng(1).uniform(lo2, hi2, (4000, 3)).astype(np.float32)
+        assert np.array_equal(rm2.sdf(p2, True, 8), om2.sdf(p2, True, 8))
