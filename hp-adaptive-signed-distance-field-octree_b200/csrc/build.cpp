@@ -91,6 +91,7 @@ namespace hpsdf
             std::vector<uint32_t>    owner_;                 // per task: job index << 4 | child slot (8 = the p-fit)
             std::vector<uint64_t>    evaluated_;
             std::vector<uint64_t>    coarseReady_;           // coarse cells whose degree-2 fit is cached
+            std::vector<uint64_t>    ready_;                 // freshly evaluated leaves not yet in the heap
             bool                     levelTried_ = false;
             double                   evalLevel_ = 0.0;       // guaranteed level used to choose what to evaluate (also in strict mode)
             std::vector<int32_t>     jobOf_;        // per node: index into jobs_, -1 = no cached result
@@ -354,7 +355,7 @@ namespace hpsdf
             for (uint64_t idx : evaluated_)
             {
                 if (jobs_[jobOf_[idx]].coarse) coarseReady_.push_back(idx);      // applied in the reference's pop order, see replay()
-                else queue_.push({ idx, errOf_[idx] });
+                else ready_.push_back(idx);                                       // enters the heap only if it is below the level
             }
             t_.stats.host_tasks_ms += nowMs() - tRec0;
             return HPSDF_OK;
@@ -527,6 +528,21 @@ namespace hpsdf
                 coarseReady_.clear();
                 applyLevel_ = inf;
             }
+            // freshly evaluated leaves at or above the level need no ordering at all: apply them directly; the rest go to the heap
+            for (size_t k = 0; k < ready_.size(); ++k)
+            {
+                const uint64_t idx = ready_[k];
+                const double err = errOf_[idx];
+                if (err >= applyLevel_)
+                {
+                    inQueue_[idx] = 0;
+                    const int b = bucketOf(err);
+                    if (--bucketCount_[b] == 0) bucketSum_[b] = 0.0; else bucketSum_[b] -= err;
+                    applyJob(idx, err);
+                }
+                else queue_.push({ idx, err });
+            }
+            ready_.clear();
             for (;;)
             {
                 if (queue_.empty() && pending_.empty()) { done = true; break; }                          // nodeQueue.empty(), Octree.cpp:216

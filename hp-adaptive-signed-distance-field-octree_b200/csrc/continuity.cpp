@@ -111,28 +111,42 @@ namespace hpsdf
         }
         if (cur >= 0x7FFFFFFFull) { setLastError("continuity: COO exceeds 2^31 entries"); return HPSDF_ERR_UNSUPPORTED; }
 
-        FaceJobDev* dFaces = nullptr; uint64_t* keys = nullptr; double* vals = nullptr; double* b = nullptr;
+        // one arena from the persistent build workspace (grow-only): no allocation in steady state
+        BuildWorkspace& ws = t.ctx->ws;
+        const int grid = cgGridSize(n, t.ctx->smCount);
+        const size_t tmpBytes = cooToCsrTempBytes(cur, n);
+        auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t need = al(faces.size() * sizeof(FaceJobDev)) + 6 * al(cur * 8) + al(cur * 4) + al(((size_t)n + 1) * 4) + al((size_t)n * 8)
+                          + al((4 * (size_t)n + 3 * (size_t)grid + 2) * 8) + al(tmpBytes) + 512;
+        HPSDF_CUDA(ws.cont.reserve(need));
+        HPSDF_CUDA(ws.hFaces.reserve(faces.size() + 1));
+        memcpy(ws.hFaces.p, faces.data(), faces.size() * sizeof(FaceJobDev));
+        char* ap = ws.cont.p;
+        auto take = [&](size_t bytes) { char* r = ap; ap += al(bytes); return (void*)r; };
+        FaceJobDev* dFaces = (FaceJobDev*)take(faces.size() * sizeof(FaceJobDev));
+        uint64_t* keys = (uint64_t*)take(cur * 8); double* vals = (double*)take(cur * 8);
+        uint64_t* keysAlt = (uint64_t*)take(cur * 8); double* valsAlt = (double*)take(cur * 8);
+        uint64_t* uniq = (uint64_t*)take(cur * 8);
         CsrDev csr;
+        csr.val = (double*)take(cur * 8); csr.col = (uint32_t*)take(cur * 4); csr.rowPtr = (uint32_t*)take(((size_t)n + 1) * 4);
+        double* b = (double*)take((size_t)n * 8);
+        double* cgScratch = (double*)take((4 * (size_t)n + 3 * (size_t)grid + 2) * 8);
+        uint32_t* dNum = (uint32_t*)take(256);
+        void* tmp = take(tmpBytes);
         double result[2] = { 0.0, 0.0 };
-        cudaError_t e = cudaMalloc((void**)&dFaces, std::max<size_t>(faces.size(), 1) * sizeof(FaceJobDev));
-        if (e == cudaSuccess) e = cudaMalloc((void**)&keys, cur * 8);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&vals, cur * 8);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&b, (size_t)n * 8);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(dFaces, faces.data(), faces.size() * sizeof(FaceJobDev), cudaMemcpyHostToDevice, stream);
+        cudaError_t e = cudaMemcpyAsync(dFaces, ws.hFaces.p, faces.size() * sizeof(FaceJobDev), cudaMemcpyHostToDevice, stream);
         if (e == cudaSuccess) e = launchDiagEmit(keys, vals, n, t.cfg.continuity_strength, stream);
         if (e == cudaSuccess) e = launchFaceEmit(dFaces, (uint32_t)faces.size(), *t.ctx, keys, vals, stream);
-        if (e == cudaSuccess) e = cooToCsr(keys, vals, cur, n, csr, stream);
+        if (e == cudaSuccess) e = cooToCsr(keys, vals, keysAlt, valsAlt, uniq, dNum, tmp, tmpBytes, cur, n, csr, stream);
         // b = lambda * c, x0 = b (Octree.cpp:1738-1741, 1755: the scaled vector is also the initial guess)
         if (e == cudaSuccess) e = launchScale(t.dCoeffs, b, n, t.cfg.continuity_strength, stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(t.dCoeffs, b, (size_t)n * 8, cudaMemcpyDeviceToDevice, stream);
         const double tol = o.cg_tolerance > 0.0 ? o.cg_tolerance : (double)0.000001f;        // setTolerance(EPSILON_F32), :1754
         const uint32_t maxIt = o.cg_max_iterations ? o.cg_max_iterations : 2u * n;            // Eigen's default: 2n
-        if (e == cudaSuccess) e = launchCg(csr, b, t.dCoeffs, tol, maxIt, t.ctx->smCount, result, stream);   // coeffStore <- x (:1756)
+        if (e == cudaSuccess) e = launchCg(csr, b, t.dCoeffs, tol, maxIt, grid, cgScratch, result, stream);   // coeffStore <- x (:1756)
         t.stats.kernel_launches += 6 + 4;      // diag, faces, sort (~4 CUB kernels), reduce, rowptr, scale, cg
         t.stats.cg_iterations = (uint64_t)result[0];
         t.stats.cg_relative_residual = result[1];
-        cudaFree(dFaces); cudaFree(keys); cudaFree(vals); cudaFree(b);
-        cudaFree(csr.rowPtr); cudaFree(csr.col); cudaFree(csr.val);
         if (e != cudaSuccess) return failCuda(e, "continuityPostProcess");
         return HPSDF_OK;
     }

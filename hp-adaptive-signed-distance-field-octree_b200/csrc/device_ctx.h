@@ -15,6 +15,17 @@ namespace hpsdf
         const uint32_t* bidx;
     };
 
+    // One leaf-leaf shared face (ContinuityThreadPool::Input, ContinuityThreadPool.h:24-28) with everything
+    // EvaluateSharedFaceIntegral{Analytically,Numerically} derives from the two nodes precomputed on the host.
+    struct FaceJobDev
+    {
+        uint64_t cooOffset;                   // where this face's entries start in the COO arrays
+        uint32_t cstartA, cstartB;            // coeffsStart of the low-side (A) and high-side (B) leaf
+        uint8_t  degA, degB, depthA, depthB, dim, analytic, pad0, pad1;
+        double   faceScale;                   // sharedFaceScale(t1) * sharedFaceScale(t2)   (Octree.cpp:1265-1267, 1333)
+        double   invDist, invTr1, invTr2;     // 2^-depthDiff and the tangential translations (Octree.cpp:1275-1290)
+    };
+
     template <typename T>
     struct PinnedBuf
     {
@@ -59,6 +70,8 @@ namespace hpsdf
         PinnedBuf<FitTask>   hTasks;
         PinnedBuf<FitRecord> hRecs;
         PinnedBuf<uint32_t>  hSegs;
+        DeviceBuf<char>      cont;        // continuity: faces, COO, CSR, CG vectors, CUB temp
+        PinnedBuf<FaceJobDev> hFaces;
         cudaStream_t         stream = nullptr;
         cudaEvent_t          ev0 = nullptr, ev1 = nullptr;
     };
@@ -73,17 +86,6 @@ namespace hpsdf
         const double* glWeights = nullptr;
         BuildWorkspace ws;
         void*          wsMutex = nullptr;     // std::mutex*, serialises builds on this device
-    };
-
-    // One leaf-leaf shared face (ContinuityThreadPool::Input, ContinuityThreadPool.h:24-28) with everything
-    // EvaluateSharedFaceIntegral{Analytically,Numerically} derives from the two nodes precomputed on the host.
-    struct FaceJobDev
-    {
-        uint64_t cooOffset;                   // where this face's entries start in the COO arrays
-        uint32_t cstartA, cstartB;            // coeffsStart of the low-side (A) and high-side (B) leaf
-        uint8_t  degA, degB, depthA, depthB, dim, analytic, pad0, pad1;
-        double   faceScale;                   // sharedFaceScale(t1) * sharedFaceScale(t2)   (Octree.cpp:1265-1267, 1333)
-        double   invDist, invTr1, invTr2;     // 2^-depthDiff and the tangential translations (Octree.cpp:1275-1290)
     };
 
     struct CsrDev
@@ -106,10 +108,14 @@ namespace hpsdf
     // continuity (continuity_kernels.cuh)
     cudaError_t launchFaceEmit(const FaceJobDev* dFaces, uint32_t nFaces, const DeviceCtx& ctx, uint64_t* keys, double* vals, cudaStream_t stream);
     cudaError_t launchDiagEmit(uint64_t* keys, double* vals, uint32_t n, double lambda, cudaStream_t stream);
-    // sort COO by (row, col), sum duplicates, build CSR (allocates csr.*; the caller frees them)
-    cudaError_t cooToCsr(uint64_t* keys, double* vals, size_t nCoo, uint32_t n, CsrDev& csr, cudaStream_t stream);
-    // (A) x = b by preconditioned CG from the guess in x; result[0] = iterations, result[1] = relative residual
-    cudaError_t launchCg(const CsrDev& csr, const double* b, double* x, double tol, uint32_t maxIt, int smCount,
+    size_t      cooToCsrTempBytes(size_t nCoo, uint32_t n);
+    // sort COO by (row, col), sum duplicates, build CSR; every buffer comes from the caller (build workspace)
+    cudaError_t cooToCsr(uint64_t* keys, double* vals, uint64_t* keysAlt, double* valsAlt, uint64_t* uniq, uint32_t* dNum,
+                         void* tmp, size_t tmpBytes, size_t nCoo, uint32_t n, CsrDev& csr, cudaStream_t stream);
+    int         cgGridSize(uint32_t n, int smCount);
+    // (A) x = b by preconditioned CG from the guess in x; scratch: 4 n + 3 grid + 2 doubles;
+    // hostResult[0] = iterations, [1] = relative residual
+    cudaError_t launchCg(const CsrDev& csr, const double* b, double* x, double tol, uint32_t maxIt, int grid, double* scratch,
                          double* hostResult, cudaStream_t stream);
     cudaError_t launchScale(const double* in, double* out, uint32_t n, double s, cudaStream_t stream);
     // dst[dstOff[s] + i] = src[srcOff[s] + i], i < count[s], for nSeg segments (ReallocCoeffs, Octree.cpp:474-555, on device)

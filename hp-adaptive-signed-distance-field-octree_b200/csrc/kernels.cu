@@ -94,66 +94,69 @@ namespace hpsdf
         return cudaGetLastError();
     }
 
-    cudaError_t cooToCsr(uint64_t* keys, double* vals, size_t nCoo, uint32_t n, CsrDev& csr, cudaStream_t stream)
+    // temp-storage bytes CUB needs for the sort + reduce of nCoo entries
+    size_t cooToCsrTempBytes(size_t nCoo, uint32_t n)
     {
-        uint64_t* keysAlt = nullptr; double* valsAlt = nullptr; uint64_t* uniq = nullptr; uint32_t* dNum = nullptr; void* tmp = nullptr;
-        cudaError_t e = cudaMalloc((void**)&keysAlt, nCoo * 8);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&valsAlt, nCoo * 8);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&uniq, nCoo * 8);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&dNum, 4);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&csr.val, nCoo * 8);
         size_t tmpSort = 0, tmpRed = 0;
+        cub::DoubleBuffer<uint64_t> kb((uint64_t*)nullptr, (uint64_t*)nullptr);
+        cub::DoubleBuffer<double>   vb((double*)nullptr, (double*)nullptr);
+        int bits = 1; while (bits < 32 && (1ull << bits) < (uint64_t)n) ++bits;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmpSort, kb, vb, (int)nCoo, 0, 32 + bits, (cudaStream_t)0);
+        cub::DeviceReduce::ReduceByKey(nullptr, tmpRed, (uint64_t*)nullptr, (uint64_t*)nullptr, (double*)nullptr, (double*)nullptr,
+                                       (uint32_t*)nullptr, cub::Sum(), (int)nCoo, (cudaStream_t)0);
+        return (tmpSort > tmpRed ? tmpSort : tmpRed) + 256;
+    }
+
+    // Sort COO by (row, col), sum duplicates, build CSR. All buffers are caller-provided (the build workspace):
+    // keysAlt/valsAlt/uniq: nCoo entries each; csr.val, csr.col: nCoo entries; csr.rowPtr: n + 1; dNum: one uint32.
+    cudaError_t cooToCsr(uint64_t* keys, double* vals, uint64_t* keysAlt, double* valsAlt, uint64_t* uniq, uint32_t* dNum,
+                         void* tmp, size_t tmpBytes, size_t nCoo, uint32_t n, CsrDev& csr, cudaStream_t stream)
+    {
         cub::DoubleBuffer<uint64_t> kb(keys, keysAlt);
         cub::DoubleBuffer<double>   vb(vals, valsAlt);
         // keys are (row << 32 | col) with row, col < n: only the significant bits need sorting; radix sort is stable, so
         // duplicates keep their emission order and are summed in that order
         int bits = 1; while (bits < 32 && (1ull << bits) < (uint64_t)n) ++bits;
-        if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmpSort, kb, vb, (int)nCoo, 0, 32 + bits, stream);
-        if (e == cudaSuccess) e = cub::DeviceReduce::ReduceByKey(nullptr, tmpRed, keys, uniq, vals, csr.val, dNum, cub::Sum(), (int)nCoo, stream);
-        if (e == cudaSuccess) e = cudaMalloc(&tmp, tmpSort > tmpRed ? tmpSort : tmpRed);
-        if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmpSort, kb, vb, (int)nCoo, 0, 32 + bits, stream);
-        if (e == cudaSuccess) e = cub::DeviceReduce::ReduceByKey(tmp, tmpRed, kb.Current(), uniq, vb.Current(), csr.val, dNum, cub::Sum(), (int)nCoo, stream);
+        size_t tb = tmpBytes;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tb, kb, vb, (int)nCoo, 0, 32 + bits, stream);
+        tb = tmpBytes;
+        if (e == cudaSuccess) e = cub::DeviceReduce::ReduceByKey(tmp, tb, kb.Current(), uniq, vb.Current(), csr.val, dNum, cub::Sum(), (int)nCoo, stream);
         uint32_t nnz = 0;
         if (e == cudaSuccess) e = cudaMemcpyAsync(&nnz, dNum, 4, cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&csr.rowPtr, ((size_t)n + 1) * 4);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&csr.col, (size_t)(nnz ? nnz : 1) * 4);
         if (e == cudaSuccess)
         {
             rowPtrKernel<<<(nnz + 1 + 255) / 256, 256, 0, stream>>>(uniq, nnz, n, csr.rowPtr, csr.col);
             e = cudaGetLastError();
         }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         csr.n = n; csr.nnz = nnz;
-        cudaFree(keysAlt); cudaFree(valsAlt); cudaFree(uniq); cudaFree(dNum); cudaFree(tmp);
         return e;
     }
 
-    cudaError_t launchCg(const CsrDev& csr, const double* b, double* x, double tol, uint32_t maxIt, int smCount,
-                         double* hostResult, cudaStream_t stream)
+    int cgGridSize(uint32_t n, int smCount)
     {
         int perSm = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, cgKernel, kCgThreads, 0);
-        if (e != cudaSuccess) return e;
-        if (perSm < 1) return cudaErrorLaunchOutOfResources;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, cgKernel, kCgThreads, 0) != cudaSuccess || perSm < 1) return 0;
         // enough blocks for 4 lanes per row, at most 2 resident blocks per SM (grid syncs get dearer with more blocks)
-        int grid = (int)(((size_t)csr.n * kCgLanesPerRow + kCgThreads - 1) / kCgThreads);
+        int grid = (int)(((size_t)n * kCgLanesPerRow + kCgThreads - 1) / kCgThreads);
         const int cap = smCount * (perSm < 2 ? perSm : 2);
         if (grid > cap) grid = cap;
-        if (grid < 1) grid = 1;
-        double* scratch = nullptr;      // r, p, ap, invDiag (4n) + partial (3 grid) + result (2)
-        const size_t nd = 4 * (size_t)csr.n + 3 * (size_t)grid + 2;
-        e = cudaMalloc((void**)&scratch, nd * 8);
-        if (e != cudaSuccess) return e;
+        return grid < 1 ? 1 : grid;
+    }
+
+    // scratch: 4 n + 3 grid + 2 doubles
+    cudaError_t launchCg(const CsrDev& csr, const double* b, double* x, double tol, uint32_t maxIt, int grid, double* scratch,
+                         double* hostResult, cudaStream_t stream)
+    {
+        if (grid < 1) return cudaErrorLaunchOutOfResources;
         CgParams P;
         P.rowPtr = csr.rowPtr; P.col = csr.col; P.val = csr.val; P.n = csr.n; P.maxIt = maxIt; P.tol = tol; P.b = b; P.x = x;
         P.r = scratch; P.p = scratch + csr.n; P.ap = scratch + 2 * (size_t)csr.n; P.invDiag = scratch + 3 * (size_t)csr.n;
         P.partial = scratch + 4 * (size_t)csr.n; P.result = P.partial + 3 * (size_t)grid;
         void* args[] = { (void*)&P };
-        e = cudaLaunchCooperativeKernel((void*)cgKernel, dim3(grid), dim3(kCgThreads), args, 0, stream);
+        cudaError_t e = cudaLaunchCooperativeKernel((void*)cgKernel, dim3(grid), dim3(kCgThreads), args, 0, stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(hostResult, P.result, 16, cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        cudaFree(scratch);
         return e;
     }
 
