@@ -205,7 +205,6 @@ namespace hpsdf
     };
 
     constexpr int kCgThreads = 256;
-    constexpr int kCgLanesPerRow = 4;
 
     __device__ __forceinline__ double blockSum(double v, double* sRed)
     {
@@ -238,25 +237,28 @@ namespace hpsdf
         return r;
     }
 
-    // y[row] = sum_k val[k] * x[col[k]], 4 lanes per row; returns this thread's share of sum(y[row] * w[row]) (lane 0 of the group)
+    // y[row] = sum_k val[k] * x[col[k]], one thread per row: a row has ~20 entries whose x gathers are independent, so a
+    // single thread keeps ~20 loads in flight; the systems here (1e4..1e6 rows) have about as many rows as the grid has
+    // threads, and the kernel is bound by latency (grid syncs + one dependent gather), not by bandwidth.
     __device__ __forceinline__ void spmvRows(const CgParams& P, const double* __restrict__ x, double* __restrict__ y,
                                              const double* __restrict__ dotWith, double& dotAcc)
     {
-        const uint32_t groupsPerGrid = (gridDim.x * kCgThreads) / kCgLanesPerRow;
-        const uint32_t group = (blockIdx.x * kCgThreads + threadIdx.x) / kCgLanesPerRow;
-        const uint32_t sub = threadIdx.x % kCgLanesPerRow;
-        const uint32_t rows = (P.n + groupsPerGrid - 1) / groupsPerGrid * groupsPerGrid;     // keep whole warps converged for the shuffles
-        for (uint32_t row = group; row < rows; row += groupsPerGrid)
+        const uint32_t stride = gridDim.x * kCgThreads;
+        for (uint32_t row = blockIdx.x * kCgThreads + threadIdx.x; row < P.n; row += stride)
         {
-            double s = 0.0;
-            if (row < P.n)
+            const uint32_t b = P.rowPtr[row], e = P.rowPtr[row + 1];
+            double s0 = 0.0, s1 = 0.0;
+            uint32_t k = b;
+            #pragma unroll 4
+            for (; k + 1 < e; k += 2)
             {
-                const uint32_t e = P.rowPtr[row + 1];
-                for (uint32_t k = P.rowPtr[row] + sub; k < e; k += kCgLanesPerRow) s = fma(P.val[k], x[P.col[k]], s);
+                s0 = fma(P.val[k], x[P.col[k]], s0);
+                s1 = fma(P.val[k + 1], x[P.col[k + 1]], s1);
             }
-            s += __shfl_xor_sync(0xFFFFFFFFu, s, 1);
-            s += __shfl_xor_sync(0xFFFFFFFFu, s, 2);
-            if (sub == 0 && row < P.n) { y[row] = s; dotAcc = fma(s, dotWith[row], dotAcc); }
+            if (k < e) s0 = fma(P.val[k], x[P.col[k]], s0);
+            const double s = s0 + s1;
+            y[row] = s;
+            dotAcc = fma(s, dotWith[row], dotAcc);
         }
     }
 
