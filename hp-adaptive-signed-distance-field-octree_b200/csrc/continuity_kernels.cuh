@@ -178,6 +178,12 @@ namespace hpsdf
         if (i < n) { keys[i] = ((uint64_t)i << 32) | i; vals[i] = lambda; }                   // Octree.cpp:1724-1729
     }
 
+    __global__ void flagNonZeroKernel(const double* __restrict__ v, uint32_t n, uint8_t* __restrict__ flags)
+    {
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < n) flags[i] = v[i] != 0.0;
+    }
+
     // rowPtr from sorted unique keys: rowPtr[r] = first entry whose row >= r
     __global__ void rowPtrKernel(const uint64_t* __restrict__ keys, uint32_t nnz, uint32_t n, uint32_t* __restrict__ rowPtr,
                                  uint32_t* __restrict__ col)

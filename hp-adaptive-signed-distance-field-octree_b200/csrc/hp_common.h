@@ -155,8 +155,7 @@ namespace hpsdf
     {
         const QNode*    nodes;
         const double*   coeffs;      // padded store: every leaf starts at an even index
-        const uint2*    top;         // 4096 entries, cell x + 16 y + 256 z of the 16^3 grid: leaf -> {padded cstart, degree | depth << 8 | 1 << 31},
-                                     // internal -> {node index, 0}; nullptr when the tree is not complete to depth 4
+        const uint32_t* top;         // 4096 entries: node reached at depth <= 4 for each cell of the 16^3 grid (x + 16 y + 256 z)
         RootMap         map;
         uint32_t        nNodes;
     };

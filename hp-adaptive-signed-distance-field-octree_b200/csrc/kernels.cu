@@ -104,7 +104,11 @@ namespace hpsdf
         cub::DeviceRadixSort::SortPairs(nullptr, tmpSort, kb, vb, (int)nCoo, 0, 32 + bits, (cudaStream_t)0);
         cub::DeviceReduce::ReduceByKey(nullptr, tmpRed, (uint64_t*)nullptr, (uint64_t*)nullptr, (double*)nullptr, (double*)nullptr,
                                        (uint32_t*)nullptr, cub::Sum(), (int)nCoo, (cudaStream_t)0);
-        return (tmpSort > tmpRed ? tmpSort : tmpRed) + 256;
+        size_t tmpSel = 0;
+        cub::DeviceSelect::Flagged(nullptr, tmpSel, (uint64_t*)nullptr, (uint8_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (int)nCoo, (cudaStream_t)0);
+        size_t m = tmpSort > tmpRed ? tmpSort : tmpRed;
+        if (tmpSel > m) m = tmpSel;
+        return m + 256 + nCoo;          // + one flag byte per entry
     }
 
     // Sort COO by (row, col), sum duplicates, build CSR. All buffers are caller-provided (the build workspace):
@@ -121,12 +125,31 @@ namespace hpsdf
         cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tb, kb, vb, (int)nCoo, 0, 32 + bits, stream);
         tb = tmpBytes;
         if (e == cudaSuccess) e = cub::DeviceReduce::ReduceByKey(tmp, tb, kb.Current(), uniq, vb.Current(), csr.val, dNum, cub::Sum(), (int)nCoo, stream);
-        uint32_t nnz = 0;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&nnz, dNum, 4, cudaMemcpyDeviceToHost, stream);
+        uint32_t nUniq = 0;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&nUniq, dNum, 4, cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        // Drop entries whose summed value is exactly 0: the dense numeric blocks carry sub-threshold entries as explicit zeros
+        // (the reference never emits them, Octree.cpp:1336) and analytic low/high-face blocks cancel exactly; long rows of
+        // zeros would make one thread of the row-per-thread SpMV the straggler of every CG iteration.
+        uint8_t* flags = (uint8_t*)tmp + (tmpBytes - nCoo);
+        uint64_t* selKeys = kb.Alternate();          // both sort buffers are free once the reduction has run
+        double*   selVals = vb.Alternate();
+        uint32_t nnz = 0;
+        if (e == cudaSuccess && nUniq)
+        {
+            flagNonZeroKernel<<<(nUniq + 255) / 256, 256, 0, stream>>>(csr.val, nUniq, flags);
+            e = cudaGetLastError();
+            size_t tb2 = tmpBytes - nCoo;
+            if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(tmp, tb2, uniq, flags, selKeys, dNum, (int)nUniq, stream);
+            tb2 = tmpBytes - nCoo;
+            if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(tmp, tb2, csr.val, flags, selVals, dNum, (int)nUniq, stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&nnz, dNum, 4, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            csr.val = selVals;
+        }
         if (e == cudaSuccess)
         {
-            rowPtrKernel<<<(nnz + 1 + 255) / 256, 256, 0, stream>>>(uniq, nnz, n, csr.rowPtr, csr.col);
+            rowPtrKernel<<<(nnz + 1 + 255) / 256, 256, 0, stream>>>(selKeys, nnz, n, csr.rowPtr, csr.col);
             e = cudaGetLastError();
         }
         csr.n = n; csr.nnz = nnz;

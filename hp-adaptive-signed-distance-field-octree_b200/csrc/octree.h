@@ -48,7 +48,7 @@ struct hpsdf_octree
     double*             dCoeffsPad = nullptr;    // Query layout: every leaf starts at an even index
     size_t              nCoeffsPad = 0;
     hpsdf::QNode*       dNodes = nullptr;
-    uint2*              dTop = nullptr;          // 16^3 entry table (see DeviceTreeView::top)
+    uint32_t*           dTop = nullptr;          // 16^3 table, or nullptr when the tree is not complete to depth 4
     hpsdf::DeviceTreeView  view{};
     hpsdf::DeviceTreeView* dView = nullptr;      // device copy of `view` (handle of an OCTREE primitive)
 

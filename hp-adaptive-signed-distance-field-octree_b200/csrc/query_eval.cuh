@@ -165,7 +165,7 @@ namespace hpsdf
 
     // Octree::Query up to the leaf: root map, f32 containment test, descent (Octree.cpp:662-702).
     __device__ __forceinline__ LeafHit findLeaf(const QNode* __restrict__ nodes, const double* __restrict__ coeffs,
-                                                const uint2* top, const RootMap& map, double x, double y, double z)
+                                                const uint32_t* top, const RootMap& map, double x, double y, double z)
     {
         LeafHit h;
         h.coeffs = coeffs; h.ux = h.uy = h.uz = 0.0; h.degree = -1; h.depth = 0;
@@ -176,7 +176,6 @@ namespace hpsdf
         if (!(fx >= -0.5f && fx <= 0.5f && fy >= -0.5f && fy <= 0.5f && fz >= -0.5f && fz <= 0.5f)) return h;
         double cx = 0.0, cy = 0.0, cz = 0.0, q = 0.25;                    // centre of the current node, quarter of its size
         uint32_t cur = 0;
-        uint32_t cstart = 0, degree = kInternalTag, depth = 0;
         if (top)
         {
             uint32_t code = 0;
@@ -187,24 +186,18 @@ namespace hpsdf
                 cx += bx ? q : -q; cy += by ? q : -q; cz += bz ? q : -q; q *= 0.5;
                 code = (code << 1) | bx | (by << 4) | (bz << 8);
             }
-            const uint2 e = top[code & 0xFFF];
-            if (e.y & 0x80000000u) { cstart = e.x; degree = e.y & 0xFF; depth = (e.y >> 8) & 0xFF; }   // a depth-4 leaf: no node load at all
-            else cur = e.x;
+            cur = top[code & 0xFFF];
         }
-        if (degree == kInternalTag)
+        uint4 raw = __ldg(reinterpret_cast<const uint4*>(nodes) + cur);
+        while (raw.z == kInternalTag)                                               // Octree.cpp:687
         {
-            uint4 raw = __ldg(reinterpret_cast<const uint4*>(nodes) + cur);
-            while (raw.z == kInternalTag)                                               // Octree.cpp:687
-            {
-                const uint32_t bx = px >= cx, by = py >= cy, bz = pz >= cz;
-                cx += bx ? q : -q; cy += by ? q : -q; cz += bz ? q : -q; q *= 0.5;
-                cur = raw.x + bx + (by << 1) + (bz << 2);                               // Octree.cpp:685
-                raw = __ldg(reinterpret_cast<const uint4*>(nodes) + cur);
-            }
-            cstart = raw.y; degree = raw.z; depth = raw.w;
+            const uint32_t bx = px >= cx, by = py >= cy, bz = pz >= cz;
+            cx += bx ? q : -q; cy += by ? q : -q; cz += bz ? q : -q; q *= 0.5;
+            cur = raw.x + bx + (by << 1) + (bz << 2);                               // Octree.cpp:685
+            raw = __ldg(reinterpret_cast<const uint4*>(nodes) + cur);
         }
-        const double scale = (double)(2u << depth);                                     // Octree.cpp:862
-        h.coeffs = coeffs + cstart; h.degree = (int)degree; h.depth = (int)depth;
+        const double scale = (double)(2u << raw.w);                                 // Octree.cpp:862
+        h.coeffs = coeffs + raw.y; h.degree = (int)raw.z; h.depth = (int)raw.w;
         h.ux = (px - cx) * scale; h.uy = (py - cy) * scale; h.uz = (pz - cz) * scale;
         return h;
     }
@@ -268,6 +261,6 @@ namespace hpsdf
 
     __device__ __forceinline__ double treeQuery(const DeviceTreeView* tree, double x, double y, double z)
     {
-        return queryPoint(tree->nodes, tree->coeffs, nullptr, tree->map, x, y, z);     // from the root: not a hot path
+        return queryPoint(tree->nodes, tree->coeffs, tree->top, tree->map, x, y, z);
     }
 }

@@ -20,12 +20,12 @@ namespace hpsdf
     queryKernel(const DeviceTreeView view, const double* __restrict__ xyz, size_t n, double* __restrict__ out,
                 const uint32_t* __restrict__ bidx)
     {
-        __shared__ __align__(16) uint2 sTop[4096];                               // 32 KB: the 16^3 entry table incl. leaf records
+        __shared__ uint32_t sTop[4096];
         __shared__ __align__(16) double sPts[kQueryThreads / 32][96];          // per warp: 32 points x 3 doubles
         const bool useTop = view.top != nullptr;
         if (useTop)
         {
-            for (int i = threadIdx.x; i < 2048; i += kQueryThreads)
+            for (int i = threadIdx.x; i < 1024; i += kQueryThreads)
                 reinterpret_cast<uint4*>(sTop)[i] = __ldg(reinterpret_cast<const uint4*>(view.top) + i);
             __syncthreads();                        // the only block-wide barrier: the table is read-only afterwards
         }

@@ -34,7 +34,7 @@ namespace hpsdf
         const size_t nNodes = t.nodes.size();
         t.nCoeffsPad = paddedCoeffCount(t);
         const size_t bCoeffs = align(std::max<size_t>(t.nCoeffs, 1) * 8), bPad = align(std::max<size_t>(t.nCoeffsPad, 2) * 8);
-        const size_t bNodes = align(nNodes * sizeof(QNode)), bTop = align(4096 * 8), bView = align(sizeof(DeviceTreeView));
+        const size_t bNodes = align(nNodes * sizeof(QNode)), bTop = align(4096 * 4), bView = align(sizeof(DeviceTreeView));
         cudaFree(t.dBlob);
         t.dBlob = nullptr;
         HPSDF_CUDA(cudaMalloc(&t.dBlob, bCoeffs + bPad + bNodes + bTop + bView));
@@ -42,7 +42,7 @@ namespace hpsdf
         t.dCoeffs = (double*)p; p += bCoeffs;
         t.dCoeffsPad = (double*)p; p += bPad;
         t.dNodes = (QNode*)p; p += bNodes;
-        t.dTop = (uint2*)p; p += bTop;
+        t.dTop = (uint32_t*)p; p += bTop;
         t.dView = (DeviceTreeView*)p;
         return HPSDF_OK;
     }
@@ -54,7 +54,7 @@ namespace hpsdf
         // staging: [QNodes][top 4096][src|dst|count segments] in one pinned buffer, one H2D copy
         size_t nLeaves = 0;
         for (const HostNode& n : t.nodes) nLeaves += n.child == kNoChild;
-        const size_t wNodes = nNodes * 4, wTop = 8192, wSeg = 3 * nLeaves;
+        const size_t wNodes = nNodes * 4, wTop = 4096, wSeg = 3 * nLeaves;
         BuildWorkspace& ws = t.ctx->ws;
         HPSDF_CUDA(ws.hSegs.reserve(wNodes + wTop + wSeg + 16));
         HPSDF_CUDA(ws.segs.reserve(wSeg + 16));
@@ -88,17 +88,12 @@ namespace hpsdf
                 if (t.nodes[cur].child == kNoChild) { topOk = false; break; }
                 cur = t.nodes[cur].child + ((ix >> l) & 1) + 2 * ((iy >> l) & 1) + 4 * ((iz >> l) & 1);
             }
-            top[2 * code] = (uint32_t)cur; top[2 * code + 1] = 0;
-            if (topOk && t.nodes[cur].child == kNoChild)
-            {
-                top[2 * code] = q[cur].cstart;                                       // padded coefficient offset of the depth-4 leaf
-                top[2 * code + 1] = 0x80000000u | ((uint32_t)t.nodes[cur].depth << 8) | t.nodes[cur].degree;
-            }
+            top[code] = (uint32_t)cur;
         }
         if (padCur != t.nCoeffsPad || !t.dBlob) { setLastError("internal: tree blob not allocated for this tree"); return HPSDF_ERR_CUDA; }
 
         HPSDF_CUDA(cudaMemcpyAsync(t.dNodes, q, nNodes * sizeof(QNode), cudaMemcpyHostToDevice, stream));
-        HPSDF_CUDA(cudaMemcpyAsync(t.dTop, top, 4096 * 8, cudaMemcpyHostToDevice, stream));
+        HPSDF_CUDA(cudaMemcpyAsync(t.dTop, top, 4096 * 4, cudaMemcpyHostToDevice, stream));
         HPSDF_CUDA(cudaMemcpyAsync(ws.segs.p, srcOff, wSeg * 4, cudaMemcpyHostToDevice, stream));
         HPSDF_CUDA(cudaMemsetAsync(t.dCoeffsPad, 0, std::max<size_t>(padCur, 2) * 8, stream));
         HPSDF_CUDA(launchGatherSegments(t.dCoeffs, t.dCoeffsPad, ws.segs.p, ws.segs.p + nLeaves, ws.segs.p + 2 * nLeaves, (uint32_t)nLeaves, stream));
