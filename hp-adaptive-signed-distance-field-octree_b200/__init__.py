@@ -85,7 +85,8 @@ class BuildStats(C.Structure):
                 ("jobs_evaluated", C.c_uint64), ("jobs_applied_p", C.c_uint64), ("jobs_applied_h", C.c_uint64),
                 ("fits_evaluated", C.c_uint64), ("sdf_evals", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("algorithmic_flops", C.c_double), ("sdf_flops_per_eval", C.c_double), ("total_error", C.c_double), ("exact_total_error", C.c_double),
-                ("cut_margin", C.c_double), ("fit_kernel_ms", C.c_double), ("continuity_ms", C.c_double),
+                ("cut_margin", C.c_double), ("fit_kernel_ms", C.c_double), ("continuity_ms", C.c_double), ("continuity_enum_ms", C.c_double),
+                ("continuity_assembly_ms", C.c_double), ("continuity_cg_ms", C.c_double),
                 ("host_replay_ms", C.c_double), ("host_select_ms", C.c_double), ("host_tasks_ms", C.c_double),
                 ("device_wait_ms", C.c_double), ("pack_ms", C.c_double), ("finalize_ms", C.c_double), ("total_ms", C.c_double), ("cg_iterations", C.c_uint64),
                 ("cg_relative_residual", C.c_double), ("near_tie_decisions", C.c_uint64)]

@@ -21,6 +21,7 @@ namespace hpsdf
         {
             const std::vector<HostNode>& nodes;
             std::vector<FaceJobDev>&     out;
+            const Tables&                T = tables();
 
             // FaceProc (Octree.cpp:1574-1612)
             void faceProc(uint64_t a, uint64_t b, uint8_t dim)
@@ -29,8 +30,8 @@ namespace hpsdf
                 if (ac || bc)
                 {
                     for (int i = 0; i < 4; ++i)
-                        faceProc(ac ? nodes[a].child + tables().face[dim][i][1] : a,
-                                 bc ? nodes[b].child + tables().face[dim][i][0] : b, dim);
+                        faceProc(ac ? nodes[a].child + T.face[dim][i][1] : a,
+                                 bc ? nodes[b].child + T.face[dim][i][0] : b, dim);
                     return;
                 }
                 const bool aLow = nodes[a].mn[dim] < nodes[b].mn[dim];                       // Octree.cpp:1593-1594
@@ -53,7 +54,7 @@ namespace hpsdf
                     }
                     f.faceScale = fs[t1] * fs[t2];
                     const uint32_t depthDiff = A.depth > B.depth ? (uint32_t)(A.depth - B.depth) : (uint32_t)(B.depth - A.depth);
-                    f.invDist = 1.0 / std::pow(2.0, (double)depthDiff);                       // Octree.cpp:1275-1276
+                    f.invDist = 1.0 / (double)(1u << depthDiff);                              // 1 / pow(2, depthDiff), Octree.cpp:1275-1276
                     const HostNode& fine = A.depth > B.depth ? A : B;                        // translation of the finer cell's centre
                     const HostNode& coarse = A.depth > B.depth ? B : A;                      // in units of the finer cell's half size
                     auto centre = [](const HostNode& n, int k) { return (n.mn[k] + n.mx[k]) / 2.0f; };
@@ -71,7 +72,7 @@ namespace hpsdf
                 if (n.child == kNoChild) return;
                 for (int i = 0; i < 8; ++i) nodeProc(n.child + i);
                 for (uint8_t d = 0; d < 3; ++d)
-                    for (int j = 0; j < 4; ++j) faceProc(n.child + tables().face[d][j][0], n.child + tables().face[d][j][1], d);
+                    for (int j = 0; j < 4; ++j) faceProc(n.child + T.face[d][j][0], n.child + T.face[d][j][1], d);
             }
         };
 
@@ -96,7 +97,9 @@ namespace hpsdf
         const uint32_t n = (uint32_t)t.nCoeffs;
         if (!n) return HPSDF_OK;
         if (t.nCoeffs >= 0xFFFFFFFFull) { setLastError("continuity: more than 2^32 unknowns"); return HPSDF_ERR_UNSUPPORTED; }
+        const double tEnum0 = nowMs();
         std::vector<FaceJobDev> faces;
+        faces.reserve(4 * t.nodes.size());
         FaceEnumerator en{ t.nodes, faces };
         en.nodeProc(0);
 
@@ -111,6 +114,8 @@ namespace hpsdf
         }
         if (cur >= 0x7FFFFFFFull) { setLastError("continuity: COO exceeds 2^31 entries"); return HPSDF_ERR_UNSUPPORTED; }
 
+        t.stats.continuity_enum_ms = nowMs() - tEnum0;
+        const double tAsm0 = nowMs();
         // one arena from the persistent build workspace (grow-only): no allocation in steady state
         BuildWorkspace& ws = t.ctx->ws;
         const int grid = cgGridSize(n, t.ctx->smCount);
@@ -138,12 +143,15 @@ namespace hpsdf
         if (e == cudaSuccess) e = launchDiagEmit(keys, vals, n, t.cfg.continuity_strength, stream);
         if (e == cudaSuccess) e = launchFaceEmit(dFaces, (uint32_t)faces.size(), *t.ctx, keys, vals, stream);
         if (e == cudaSuccess) e = cooToCsr(keys, vals, keysAlt, valsAlt, uniq, dNum, tmp, tmpBytes, cur, n, csr, stream);
+        t.stats.continuity_assembly_ms = nowMs() - tAsm0;
+        const double tCg0 = nowMs();
         // b = lambda * c, x0 = b (Octree.cpp:1738-1741, 1755: the scaled vector is also the initial guess)
         if (e == cudaSuccess) e = launchScale(t.dCoeffs, b, n, t.cfg.continuity_strength, stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(t.dCoeffs, b, (size_t)n * 8, cudaMemcpyDeviceToDevice, stream);
         const double tol = o.cg_tolerance > 0.0 ? o.cg_tolerance : (double)0.000001f;        // setTolerance(EPSILON_F32), :1754
         const uint32_t maxIt = o.cg_max_iterations ? o.cg_max_iterations : 2u * n;            // Eigen's default: 2n
         if (e == cudaSuccess) e = launchCg(csr, b, t.dCoeffs, tol, maxIt, grid, cgScratch, result, stream);   // coeffStore <- x (:1756)
+        t.stats.continuity_cg_ms = nowMs() - tCg0;
         t.stats.kernel_launches += 6 + 4;      // diag, faces, sort (~4 CUB kernels), reduce, rowptr, scale, cg
         t.stats.cg_iterations = (uint64_t)result[0];
         t.stats.cg_relative_residual = result[1];

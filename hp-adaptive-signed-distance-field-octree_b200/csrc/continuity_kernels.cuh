@@ -243,9 +243,13 @@ namespace hpsdf
         return r;
     }
 
-    // y[row] = sum_k val[k] * x[col[k]], one thread per row: a row has ~20 entries whose x gathers are independent, so a
-    // single thread keeps ~20 loads in flight; the systems here (1e4..1e6 rows) have about as many rows as the grid has
-    // threads, and the kernel is bound by latency (grid syncs + one dependent gather), not by bandwidth.
+    // y[row] = sum_k val[k] * x[col[k]]. Rows are short (~20 entries) except next to mixed-depth faces, whose dense blocks
+    // give rows of several hundred entries. Pass 1: one thread per short row (its gathers are independent, ~20 loads in
+    // flight per thread). Pass 2: long rows, one warp per row with a shuffle reduction — otherwise a single thread walking
+    // a 500-entry row is the straggler every grid sync waits for. The assignment of rows to threads/warps is fixed, so
+    // the sums (and the fused dot product) are deterministic.
+    constexpr uint32_t kCgLongRow = 48;
+
     __device__ __forceinline__ void spmvRows(const CgParams& P, const double* __restrict__ x, double* __restrict__ y,
                                              const double* __restrict__ dotWith, double& dotAcc)
     {
@@ -253,6 +257,7 @@ namespace hpsdf
         for (uint32_t row = blockIdx.x * kCgThreads + threadIdx.x; row < P.n; row += stride)
         {
             const uint32_t b = P.rowPtr[row], e = P.rowPtr[row + 1];
+            if (e - b > kCgLongRow) continue;
             double s0 = 0.0, s1 = 0.0;
             uint32_t k = b;
             #pragma unroll 4
@@ -265,6 +270,25 @@ namespace hpsdf
             const double s = s0 + s1;
             y[row] = s;
             dotAcc = fma(s, dotWith[row], dotAcc);
+        }
+        const uint32_t lane = threadIdx.x & 31;
+        const uint32_t warpGlobal = (blockIdx.x * kCgThreads + threadIdx.x) >> 5, nWarps = stride >> 5;
+        for (uint32_t base = warpGlobal * 32; base < P.n; base += nWarps * 32)
+        {
+            const uint32_t row = base + lane;
+            const bool isLong = row < P.n && (P.rowPtr[row + 1] - P.rowPtr[row]) > kCgLongRow;
+            uint32_t mask = __ballot_sync(0xFFFFFFFFu, isLong);
+            while (mask)
+            {
+                const uint32_t r = base + (uint32_t)__ffs((int)mask) - 1u;
+                mask &= mask - 1u;
+                const uint32_t b = P.rowPtr[r], e = P.rowPtr[r + 1];
+                double s = 0.0;
+                for (uint32_t k = b + lane; k < e; k += 32) s = fma(P.val[k], x[P.col[k]], s);
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+                if (lane == 0) { y[r] = s; dotAcc = fma(s, dotWith[r], dotAcc); }
+            }
         }
     }
 

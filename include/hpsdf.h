@@ -224,7 +224,8 @@ typedef struct hpsdf_build_stats
     double   exact_total_error;   /* plain sum of leaf errors at termination */
     double   cut_margin;          /* (threshold - total)/threshold at termination: small = near-threshold stop */
     double   fit_kernel_ms;       /* device time in fit kernels (CUDA events on the build stream) */
-    double   continuity_ms;       /* device time of face assembly + CG */
+    double   continuity_ms;       /* wall time of the continuity post-process: face enumeration + assembly + CG */
+    double   continuity_enum_ms, continuity_assembly_ms, continuity_cg_ms;   /* its parts: host face walk; emit + sort + CSR; CG */
     double   host_replay_ms;      /* host time in the greedy replay */
     double   host_select_ms;      /* host time choosing which leaves to evaluate each round */
     double   host_tasks_ms;       /* host time building fit task lists */

@@ -9,7 +9,7 @@ spec = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 cfg, prog = product_cfg(hp, name)
 t = hp.Octree()
 keys = ["rounds", "fits_evaluated", "jobs_evaluated", "kernel_launches", "total_ms", "fit_kernel_ms", "device_wait_ms", "host_replay_ms",
-        "host_select_ms", "host_tasks_ms", "pack_ms", "finalize_ms", "continuity_ms", "cg_iterations", "n_nodes", "n_coeffs"]
+        "host_select_ms", "host_tasks_ms", "pack_ms", "finalize_ms", "continuity_ms", "continuity_enum_ms", "continuity_assembly_ms", "continuity_cg_ms", "cg_iterations", "n_nodes", "n_coeffs"]
 for i in range(4):
     t0 = time.perf_counter()
     t.Create(cfg, prog, hp.BuildOpts(speculate=spec))
