@@ -243,52 +243,32 @@ namespace hpsdf
         return r;
     }
 
-    // y[row] = sum_k val[k] * x[col[k]]. Rows are short (~20 entries) except next to mixed-depth faces, whose dense blocks
-    // give rows of several hundred entries. Pass 1: one thread per short row (its gathers are independent, ~20 loads in
-    // flight per thread). Pass 2: long rows, one warp per row with a shuffle reduction — otherwise a single thread walking
-    // a 500-entry row is the straggler every grid sync waits for. The assignment of rows to threads/warps is fixed, so
-    // the sums (and the fused dot product) are deterministic.
-    constexpr uint32_t kCgLongRow = 48;
+    // y[row] = sum_k val[k] * x[col[k]], 8 lanes per row. A row's columns come in contiguous runs (the coefficient ranges of
+    // the leaf itself and of each face neighbour), so 8 lanes reading 8 consecutive entries also gather 8 mostly consecutive
+    // x values: val / col are read as full 64 / 32-byte segments and the gathers coalesce into a few sectors. (One thread per
+    // row scatters every lane of a warp over a different row and quadruples the L2 sector traffic.) The row -> lane
+    // assignment is fixed, so the sums and the fused dot product are deterministic.
+    constexpr int kCgLanesPerRow = 8;
 
     __device__ __forceinline__ void spmvRows(const CgParams& P, const double* __restrict__ x, double* __restrict__ y,
                                              const double* __restrict__ dotWith, double& dotAcc)
     {
-        const uint32_t stride = gridDim.x * kCgThreads;
-        for (uint32_t row = blockIdx.x * kCgThreads + threadIdx.x; row < P.n; row += stride)
+        const uint32_t groupsPerGrid = (gridDim.x * kCgThreads) / kCgLanesPerRow;
+        const uint32_t group = (blockIdx.x * kCgThreads + threadIdx.x) / kCgLanesPerRow;
+        const uint32_t sub = threadIdx.x % kCgLanesPerRow;
+        const uint32_t rows = (P.n + groupsPerGrid - 1) / groupsPerGrid * groupsPerGrid;     // keep whole warps converged for the shuffles
+        for (uint32_t row = group; row < rows; row += groupsPerGrid)
         {
-            const uint32_t b = P.rowPtr[row], e = P.rowPtr[row + 1];
-            if (e - b > kCgLongRow) continue;
-            double s0 = 0.0, s1 = 0.0;
-            uint32_t k = b;
-            #pragma unroll 4
-            for (; k + 1 < e; k += 2)
+            double s = 0.0;
+            if (row < P.n)
             {
-                s0 = fma(P.val[k], x[P.col[k]], s0);
-                s1 = fma(P.val[k + 1], x[P.col[k + 1]], s1);
+                const uint32_t e = P.rowPtr[row + 1];
+                for (uint32_t k = P.rowPtr[row] + sub; k < e; k += kCgLanesPerRow) s = fma(P.val[k], x[P.col[k]], s);
             }
-            if (k < e) s0 = fma(P.val[k], x[P.col[k]], s0);
-            const double s = s0 + s1;
-            y[row] = s;
-            dotAcc = fma(s, dotWith[row], dotAcc);
-        }
-        const uint32_t lane = threadIdx.x & 31;
-        const uint32_t warpGlobal = (blockIdx.x * kCgThreads + threadIdx.x) >> 5, nWarps = stride >> 5;
-        for (uint32_t base = warpGlobal * 32; base < P.n; base += nWarps * 32)
-        {
-            const uint32_t row = base + lane;
-            const bool isLong = row < P.n && (P.rowPtr[row + 1] - P.rowPtr[row]) > kCgLongRow;
-            uint32_t mask = __ballot_sync(0xFFFFFFFFu, isLong);
-            while (mask)
-            {
-                const uint32_t r = base + (uint32_t)__ffs((int)mask) - 1u;
-                mask &= mask - 1u;
-                const uint32_t b = P.rowPtr[r], e = P.rowPtr[r + 1];
-                double s = 0.0;
-                for (uint32_t k = b + lane; k < e; k += 32) s = fma(P.val[k], x[P.col[k]], s);
-                #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-                if (lane == 0) { y[r] = s; dotAcc = fma(s, dotWith[r], dotAcc); }
-            }
+            s += __shfl_xor_sync(0xFFFFFFFFu, s, 1);
+            s += __shfl_xor_sync(0xFFFFFFFFu, s, 2);
+            s += __shfl_xor_sync(0xFFFFFFFFu, s, 4);
+            if (sub == 0 && row < P.n) { y[row] = s; dotAcc = fma(s, dotWith[row], dotAcc); }
         }
     }
 

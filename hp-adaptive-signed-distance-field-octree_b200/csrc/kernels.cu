@@ -160,8 +160,8 @@ namespace hpsdf
     {
         int perSm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, cgKernel, kCgThreads, 0) != cudaSuccess || perSm < 1) return 0;
-        // one thread per row; at most 4 resident blocks per SM (grid syncs get dearer with more blocks)
-        int grid = (int)(((size_t)n + kCgThreads - 1) / kCgThreads);
+        // 8 lanes per row; at most 4 resident blocks per SM (grid syncs get dearer with more blocks)
+        int grid = (int)(((size_t)n * kCgLanesPerRow + kCgThreads - 1) / kCgThreads);
         const int cap = smCount * (perSm < 4 ? perSm : 4);
         if (grid > cap) grid = cap;
         return grid < 1 ? 1 : grid;
