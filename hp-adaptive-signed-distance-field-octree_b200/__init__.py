@@ -63,7 +63,8 @@ class BuildOpts(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("max_degree", C.c_uint32), ("max_depth", C.c_uint32),
                 ("nearness_mode", C.c_uint32), ("total_mode", C.c_uint32), ("cg_max_iterations", C.c_uint32),
                 ("cg_tolerance", C.c_double), ("device", C.c_int32), ("speculate", C.c_uint32),
-                ("strict_order", C.c_uint32), ("comm", C.c_void_p), ("stream", C.c_void_p)]
+                ("strict_order", C.c_uint32), ("comm", C.c_void_p), ("stream", C.c_void_p),
+                ("jit", C.c_uint32), ("_reserved", C.c_uint32)]
 
     def __init__(self, **kw):
         super().__init__()
@@ -122,7 +123,7 @@ EXPORTS = [
     "hpsdf_query_device", "hpsdf_query_with_gradient", "hpsdf_to_memory_block", "hpsdf_from_memory_block", "hpsdf_clone",
     "hpsdf_get_root_aabb", "hpsdf_destroy", "hpsdf_get_build_stats", "hpsdf_get_decision_log", "hpsdf_get_apply_log", "hpsdf_fit_batch",
     "hpsdf_bench_frontier", "hpsdf_measure_fp64_peak", "hpsdf_comm_get_unique_id", "hpsdf_comm_init",
-    "hpsdf_comm_destroy", "hpsdf_shard_range",
+    "hpsdf_comm_destroy", "hpsdf_shard_range", "hpsdf_set_jit", "hpsdf_jit_compile_check",
 ]
 
 _lib = None
@@ -182,6 +183,9 @@ def lib():
     L.hpsdf_comm_destroy.argtypes = [vp]
     L.hpsdf_comm_destroy.restype = None
     L.hpsdf_shard_range.argtypes = [sz, i32, i32, C.POINTER(sz), C.POINTER(sz)]
+    L.hpsdf_jit_compile_check.argtypes = [C.POINTER(_Program), u32, vp, sz, C.POINTER(sz)]
+    L.hpsdf_set_jit.restype = None
+    L.hpsdf_set_jit.argtypes = [i32]
     L.hpsdf_shard_range.restype = None
     _lib = L
     return L
@@ -449,6 +453,19 @@ def bench_frontier(config, F, grid_depth, degree, repeats=3, device=-1, stream=N
     out = FrontierBench()
     _check(lib().hpsdf_bench_frontier(C.byref(config), C.byref(F._c), grid_depth, degree, repeats, device, stream, C.byref(out)))
     return {k: getattr(out, k) for k, _ in out._fields_}
+
+
+def set_jit(on):
+    """Process default for BuildOpts.jit == 0, fit_batch and bench_frontier: NVRTC-specialised fit kernels for closed-form programs."""
+    lib().hpsdf_set_jit(1 if on else 0)
+
+
+def jit_compile_check(F, degree):
+    """Generate + NVRTC-compile the specialised fit kernel of `degree` for program F (no GPU needed) -> (source, cubin bytes)."""
+    buf = C.create_string_buffer(1 << 16)
+    n = C.c_size_t()
+    _check(lib().hpsdf_jit_compile_check(C.byref(F._c), degree, buf, len(buf), C.byref(n)))
+    return buf.value.decode(), n.value
 
 
 def measure_fp64_peak(device=-1, stream=None):

@@ -253,6 +253,21 @@ extern "C"
         return n;
     }
 
+    HPSDF_API void hpsdf_set_jit(int on) { setJitDefault(on != 0); }
+
+    HPSDF_API hpsdf_status hpsdf_jit_compile_check(const hpsdf_sdf_program* prog, uint32_t degree, char* source_out, size_t source_cap, size_t* cubin_bytes)
+    {
+        if (degree < 1 || degree > (uint32_t)kMaxDegree) { setLastError("bad degree"); return HPSDF_ERR_INVALID_ARG; }
+        SdfProgramDev dp;
+        hpsdf_status st = resolveProgram(prog, -1, dp);
+        if (st != HPSDF_OK) return st;
+        std::string src, why;
+        const bool ok = jitCompileCheck(dp, (int)degree, &src, cubin_bytes, why);
+        if (source_out && source_cap) { const size_t k = std::min(source_cap - 1, src.size()); memcpy(source_out, src.data(), k); source_out[k] = 0; }
+        if (!ok) { setLastError("JIT fit kernel: " + why); return HPSDF_ERR_UNSUPPORTED; }
+        return HPSDF_OK;
+    }
+
     HPSDF_API hpsdf_status hpsdf_fit_batch(const hpsdf_config* cfg, const hpsdf_sdf_program* prog, const float* cells, const uint8_t* depth,
                                            size_t n, uint32_t degree, double* coeffs_out, double* raw_err_out, int device, float* elapsed_ms)
     {
@@ -284,7 +299,8 @@ extern "C"
         if (e == cudaSuccess) e = cudaEventCreate(&e0);
         if (e == cudaSuccess) e = cudaEventCreate(&e1);
         if (e == cudaSuccess) e = cudaEventRecord(e0, nullptr);
-        if (e == cudaSuccess) e = launchFitKernel((int)degree, dT, (int)n, dPool, dR, dp, map, ctx->fitTab, nullptr);
+        hpsdf_status ls = HPSDF_OK;
+        if (e == cudaSuccess) ls = launchFit(0, (int)degree, dT, (int)n, dPool, dR, dp, map, ctx->fitTab, nullptr);
         if (e == cudaSuccess) e = cudaEventRecord(e1, nullptr);
         if (e == cudaSuccess) e = cudaMemcpy(coeffs_out, dPool, n * nc * 8, cudaMemcpyDeviceToHost);
         std::vector<FitRecord> recs(n);
@@ -295,7 +311,7 @@ extern "C"
         if (e1) cudaEventDestroy(e1);
         cudaFree(dT); cudaFree(dPool); cudaFree(dR);
         if (e != cudaSuccess) return failCuda(e, "hpsdf_fit_batch");
-        return HPSDF_OK;
+        return ls;
     }
 
     // Synthetic frontier: all cells of a uniform grid at grid_depth as refinement jobs at degree p:
@@ -352,11 +368,12 @@ extern "C"
         if (e == cudaSuccess) e = cudaMemcpyAsync(dT, tasks.data(), tasks.size() * sizeof(FitTask), cudaMemcpyHostToDevice, stream);
         if (e == cudaSuccess) e = cudaEventCreate(&e0);
         if (e == cudaSuccess) e = cudaEventCreate(&e1);
-        for (uint32_t r = 0; r <= repeats && e == cudaSuccess; ++r)
+        hpsdf_status ls = HPSDF_OK;
+        for (uint32_t r = 0; r <= repeats && e == cudaSuccess && ls == HPSDF_OK; ++r)
         {
             if (r == 1) e = cudaEventRecord(e0, stream);          // launch 0 is the warm-up
-            if (e == cudaSuccess) e = launchFitKernel((int)degree, dT, (int)nH, dPool, dR, dp, map, ctx->fitTab, stream);
-            if (e == cudaSuccess) e = launchFitKernel((int)degree + 1, dT + nH, (int)nP, dPool, dR, dp, map, ctx->fitTab, stream);
+            if (e == cudaSuccess && ls == HPSDF_OK) ls = launchFit(0, (int)degree, dT, (int)nH, dPool, dR, dp, map, ctx->fitTab, stream);
+            if (e == cudaSuccess && ls == HPSDF_OK) ls = launchFit(0, (int)degree + 1, dT + nH, (int)nP, dPool, dR, dp, map, ctx->fitTab, stream);
         }
         if (e == cudaSuccess) e = cudaEventRecord(e1, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
@@ -368,6 +385,7 @@ extern "C"
         if (e1) cudaEventDestroy(e1);
         cudaFree(dT); cudaFree(dPool); cudaFree(dR);
         if (e != cudaSuccess) return failCuda(e, "hpsdf_bench_frontier");
+        if (ls != HPSDF_OK) return ls;
         memset(out, 0, sizeof(*out));
         out->ms_per_launch = (double)ms / repeats;
         out->jobs = jobs; out->fits = nH + nP;

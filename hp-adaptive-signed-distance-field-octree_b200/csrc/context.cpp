@@ -41,6 +41,50 @@ namespace hpsdf
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
     }
 
+    struct BlobCache
+    {
+        std::mutex m;
+        std::vector<std::pair<void*, size_t>> free;
+        size_t bytes = 0;
+    };
+
+    cudaError_t acquireBlob(DeviceCtx& ctx, size_t bytes, void** ptr, size_t* capacity)
+    {
+        BlobCache& c = *(BlobCache*)ctx.blobCache;
+        const size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        {
+            std::lock_guard<std::mutex> lock(c.m);
+            int best = -1;
+            for (int i = 0; i < (int)c.free.size(); ++i)
+                if (c.free[i].second >= want && c.free[i].second <= 4 * want && (best < 0 || c.free[i].second < c.free[best].second)) best = i;
+            if (best >= 0)
+            {
+                *ptr = c.free[best].first; *capacity = c.free[best].second;
+                c.bytes -= c.free[best].second;
+                c.free.erase(c.free.begin() + best);
+                return cudaSuccess;
+            }
+        }
+        *capacity = want;
+        return cudaMalloc(ptr, want);
+    }
+
+    void releaseBlob(DeviceCtx& ctx, void* ptr, size_t capacity)
+    {
+        if (!ptr) return;
+        BlobCache& c = *(BlobCache*)ctx.blobCache;
+        {
+            std::lock_guard<std::mutex> lock(c.m);
+            if (c.free.size() < 8 && c.bytes + capacity <= ((size_t)2 << 30))
+            {
+                c.free.emplace_back(ptr, capacity);
+                c.bytes += capacity;
+                return;
+            }
+        }
+        cudaFree(ptr);
+    }
+
     DeviceCtx* getDeviceCtx(int device, std::string& err)
     {
         std::lock_guard<std::mutex> lock(g_ctxMutex);
@@ -99,6 +143,7 @@ namespace hpsdf
         cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
         uploadConstants();
         ctx->wsMutex = new std::mutex();
+        ctx->blobCache = new BlobCache();
         cudaStreamCreateWithFlags(&ctx->ws.stream, cudaStreamNonBlocking);
         cudaEventCreate(&ctx->ws.ev0);
         cudaEventCreate(&ctx->ws.ev1);

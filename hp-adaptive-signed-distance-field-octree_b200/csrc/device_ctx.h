@@ -6,15 +6,6 @@
 
 namespace hpsdf
 {
-    // Per-degree projection tables in device memory: q[d][c*n + k] = w_k * P_c(xi_k) for the (4d+1)-point rule,
-    // roots[d][k] = xi_k; bidx[idx] = a | b << 8 | c << 16 (BasisIndexValues, Utility.h:133-160).
-    struct FitTablesDev
-    {
-        const double*   q[kMaxDegree + 1];
-        const double*   roots[kMaxDegree + 1];
-        const uint32_t* bidx;
-    };
-
     // One leaf-leaf shared face (ContinuityThreadPool::Input, ContinuityThreadPool.h:24-28) with everything
     // EvaluateSharedFaceIntegral{Analytically,Numerically} derives from the two nodes precomputed on the host.
     struct FaceJobDev
@@ -86,7 +77,15 @@ namespace hpsdf
         const double* glWeights = nullptr;
         BuildWorkspace ws;
         void*          wsMutex = nullptr;     // std::mutex*, serialises builds on this device
+        void*          blobCache = nullptr;   // released tree allocations kept for reuse (context.cpp)
     };
+
+    // Tree storage comes from a small per-device cache: cudaFree + cudaMalloc per Create cost 0.3-3 ms (cudaFree synchronises
+    // the device), a multiple of everything else pack does. Capacities are rounded up to 1 MiB so rebuilt trees of similar
+    // size reuse the same block. Released blocks are reused by later builds on the device's build stream; callers must not
+    // destroy / re-Create a tree while their own streams still run hpsdf_query_device on it (the rule of cudaFreeAsync).
+    cudaError_t acquireBlob(DeviceCtx& ctx, size_t bytes, void** ptr, size_t* capacity);
+    void        releaseBlob(DeviceCtx& ctx, void* ptr, size_t capacity);
 
     struct CsrDev
     {
@@ -101,6 +100,12 @@ namespace hpsdf
     void        uploadConstants();
     cudaError_t launchFitKernel(int degree, const FitTask* dTasks, int n, double* pool, FitRecord* recs,
                                 const SdfProgramDev& prog, const RootMap& map, const FitTablesDev& tab, cudaStream_t stream);
+    // jit.cpp: the fit launch the scheduler calls (interpreted kernels, or NVRTC-specialised ones; see hpsdf_build_opts.jit)
+    hpsdf_status launchFit(uint32_t jitMode, int degree, const FitTask* dTasks, int n, double* pool, FitRecord* recs,
+                           const SdfProgramDev& prog, const RootMap& map, const FitTablesDev& tab, cudaStream_t stream);
+    bool        jitCompileCheck(const SdfProgramDev& prog, int degree, std::string* source, size_t* cubinBytes, std::string& why);
+    void        setJitDefault(bool on);
+    bool        jitDefault();
     cudaError_t launchSdfEval(const SdfProgramDev& prog, const double* dXyz, size_t n, double* dOut, cudaStream_t stream);
     cudaError_t launchDfmaPeak(double* dOut, int blocks, cudaStream_t stream);
     cudaError_t launchQuery(const DeviceTreeView& view, const double* dXyz, size_t n, double* dOut, int smCount, cudaStream_t stream);

@@ -4,8 +4,15 @@
 // (SumToN, NormalisedLengths, LegendreCoeffientCount, LegendreCoefficent, BasisIndexValues, SharedFaceLookup).
 // The tables are rebuilt here from their definitions; nothing is copied from the reference.
 #pragma once
+#ifdef __CUDACC_RTC__
+// run-time compilation (NVRTC, jit.cpp): no system headers
+typedef unsigned char uint8_t; typedef unsigned short uint16_t; typedef unsigned int uint32_t; typedef unsigned long long uint64_t;
+typedef int int32_t; typedef long long int64_t; typedef unsigned long size_t;
+#define HPSDF_NO_SYSTEM_HEADERS 1
+#else
 #include <cstdint>
 #include <cstddef>
+#endif
 #include "../../include/hpsdf.h"
 
 #if defined(__CUDACC__)
@@ -37,7 +44,19 @@ namespace hpsdf
     HPSDF_HD constexpr int pairCount(int d) { return (d + 1) * (d + 2) / 2; }
     // Gauss-Legendre points per axis of a degree-d fit (Octree.cpp:1016-1017: rule 4d+1)
     HPSDF_HD constexpr int fitRule(int d) { return 4 * d + 1; }
+    // fit kernel geometry (fit_kernel_body.cuh): threads per CTA and dynamic shared memory per degree
+    HPSDF_HD constexpr int fitPasses(int d)  { return (fitRule(d) * fitRule(d) + 639) / 640; }
+    HPSDF_HD constexpr int fitThreads(int d)
+    {
+        return (((fitRule(d) * fitRule(d) + fitPasses(d) - 1) / fitPasses(d)) + 31) / 32 * 32;
+    }
+    // shared memory (doubles): Q (d+1)*n | roots n | user-space z n | T1 (d+1)*n*n | T2 pairCount*n ; coefficients alias T1
+    HPSDF_HD constexpr size_t fitSmemDoubles(int d)
+    {
+        return (size_t)(d + 1) * fitRule(d) + 2 * fitRule(d) + (size_t)(d + 1) * fitRule(d) * fitRule(d) + (size_t)pairCount(d) * fitRule(d);
+    }
 
+#ifndef __CUDACC_RTC__
     // Sum-factorised FLOPs of one full fit at degree d, SDF evaluation excluded:
     // 2(d+1)n^3 + 2 T2(d) n^2 + 2 N_d n + 4 n^3.
     inline double fitFlops(int d)
@@ -76,6 +95,7 @@ namespace hpsdf
     // Gauss-Legendre rule with n points (1..64), nodes ascending: pointers to n roots / n weights
     const double* glRoots(int n);
     const double* glWeights(int n);
+#endif   // !__CUDACC_RTC__
 
     // ---- device-side descriptors ------------------------------------------------------------------------------
     // Unit cube -> user space map of Octree::Create (Octree.cpp:322-328) and its f32-rounded inverse used by Query
@@ -107,6 +127,15 @@ namespace hpsdf
     {
         double rawErr;
         double c0;
+    };
+
+    // Per-degree projection tables in device memory: q[d][c*n + k] = w_k * P_c(xi_k) for the (4d+1)-point rule,
+    // roots[d][k] = xi_k; bidx[idx] = a | b << 8 | c << 16 (BasisIndexValues, Utility.h:133-160).
+    struct FitTablesDev
+    {
+        const double*   q[kMaxDegree + 1];
+        const double*   roots[kMaxDegree + 1];
+        const uint32_t* bidx;
     };
 
     // Device mesh (mesh.cpp builds it, mesh_eval.cuh traverses it)

@@ -43,6 +43,7 @@ struct hpsdf_octree
     std::vector<hpsdf::HostNode> nodes;
     size_t              nCoeffs = 0;
 
+    size_t              dBlobBytes = 0;          // capacity of dBlob (it comes from the device's blob cache)
     void*               dBlob = nullptr;         // one allocation: packed store | padded store | QNodes | top table | view
     double*             dCoeffs = nullptr;       // packed store, MemoryBlock order (DFS leaf order)
     double*             dCoeffsPad = nullptr;    // Query layout: every leaf starts at an even index

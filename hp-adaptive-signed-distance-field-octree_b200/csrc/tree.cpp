@@ -10,8 +10,8 @@
 
 hpsdf_octree::~hpsdf_octree()
 {
-    if (ctx) cudaSetDevice(device);
-    cudaFree(dBlob);
+    if (ctx) { cudaSetDevice(device); hpsdf::releaseBlob(*ctx, dBlob, dBlobBytes); }
+    else cudaFree(dBlob);
     for (int i = 0; i < 3; ++i)
     {
         cudaFree(dScratchIn[i]); cudaFree(dScratchOut[i]);
@@ -35,9 +35,13 @@ namespace hpsdf
         t.nCoeffsPad = paddedCoeffCount(t);
         const size_t bCoeffs = align(std::max<size_t>(t.nCoeffs, 1) * 8), bPad = align(std::max<size_t>(t.nCoeffsPad, 2) * 8);
         const size_t bNodes = align(nNodes * sizeof(QNode)), bTop = align(4096 * 4), bView = align(sizeof(DeviceTreeView));
-        cudaFree(t.dBlob);
-        t.dBlob = nullptr;
-        HPSDF_CUDA(cudaMalloc(&t.dBlob, bCoeffs + bPad + bNodes + bTop + bView));
+        const size_t need = bCoeffs + bPad + bNodes + bTop + bView;
+        if (!t.dBlob || t.dBlobBytes < need || t.dBlobBytes > 4 * need + ((size_t)1 << 20))
+        {
+            releaseBlob(*t.ctx, t.dBlob, t.dBlobBytes);
+            t.dBlob = nullptr; t.dBlobBytes = 0;
+            HPSDF_CUDA(acquireBlob(*t.ctx, need, &t.dBlob, &t.dBlobBytes));
+        }
         char* p = (char*)t.dBlob;
         t.dCoeffs = (double*)p; p += bCoeffs;
         t.dCoeffsPad = (double*)p; p += bPad;

@@ -23,8 +23,10 @@
 #ifndef HPSDF_H
 #define HPSDF_H
 
+#ifndef HPSDF_NO_SYSTEM_HEADERS   /* defined by the library's run-time (NVRTC) compilation units only */
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -118,9 +120,15 @@ typedef struct hpsdf_build_opts
                                      0 = entries certain to be refined are applied as soon as their results are cached */
     hpsdf_comm* comm;             /* NULL = single GPU; else frontier jobs are sharded over the communicator's ranks */
     void*    stream;              /* cudaStream_t to run on; NULL = an internal non-blocking stream */
+    uint32_t jit;                 /* closed-form programs: 0 = process default (hpsdf_set_jit / env HPSDF_JIT), 1 = compile the
+                                     fit kernels for this program at run time (NVRTC, once per program and degree, ~0.3 s each,
+                                     cached in memory), 2 = interpreted kernels. Mesh / octree programs are always interpreted. */
+    uint32_t _reserved;
 } hpsdf_build_opts;
 
 HPSDF_API void hpsdf_build_opts_default(hpsdf_build_opts* opts);
+/* Process-wide default for hpsdf_build_opts.jit == 0 and for hpsdf_fit_batch / hpsdf_bench_frontier (off at start). */
+HPSDF_API void hpsdf_set_jit(int on);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Device SDF programs: what replaces the std::function<f64(Vector3d, u32)> argument of         */
@@ -298,6 +306,12 @@ typedef struct hpsdf_frontier_bench
 HPSDF_API hpsdf_status hpsdf_bench_frontier(const hpsdf_config* cfg, const hpsdf_sdf_program* prog,
                                             uint32_t grid_depth, uint32_t degree, uint32_t repeats,
                                             int device, void* stream, hpsdf_frontier_bench* out);
+
+/* Generates the straight-line CUDA of `prog` (closed-form primitives only) and compiles the degree-`degree` fit kernel for
+ * sm_100a with NVRTC, without touching a device: the build check of the run-time specialiser (hpsdf_build_opts.jit).
+ * source_out (may be NULL) receives the generated translation unit, cubin_bytes (may be NULL) the size of the cubin. */
+HPSDF_API hpsdf_status hpsdf_jit_compile_check(const hpsdf_sdf_program* prog, uint32_t degree, char* source_out, size_t source_cap,
+                                               size_t* cubin_bytes);
 
 /* FP64 FMA peak of the device measured with a register-resident DFMA chain (TFLOP/s); the roofline
  * denominator for fitting, which MEASURED_PEAKS.json does not hold. */

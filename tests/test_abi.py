@@ -93,3 +93,19 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+\.*oracle", text, re.M), f
                 assert "hp_oracle" not in text and "hpref" not in text and "libhporacle" not in text, f
                 assert not re.search(r'#include\s+"[^"]*oracle', text), f
+
+
+@pytest.mark.parametrize("degree", [1, 2, 7, 11])
+def test_jit_specialisation_builds_for_sm100a_without_a_gpu(hp, degree):
+    """csrc/jit.cpp: generated straight-line SDF + fit_kernel_body.cuh compile with NVRTC (headers embedded in the library)."""
+    from cases import CSG_C2
+    src, nbytes = hp.jit_compile_check(hp.SdfProgram(CSG_C2), degree)
+    assert "sdfEval" in src and "0x1." in src          # parameters as exact hex-float literals
+    assert nbytes > 10000
+
+
+def test_jit_rejects_mesh_and_octree_programs(hp):
+    prog = hp.SdfProgram([("sphere", [0, 0, 0, 0.3])])
+    prog._instr[0].op = hp.PRIM["octree"]             # no handle: resolveProgram refuses before the generator is reached
+    with pytest.raises(Exception):
+        hp.jit_compile_check(prog, 2)

@@ -7,7 +7,11 @@ hp = importlib.import_module("hp-adaptive-signed-distance-field-octree_b200")
 from common import product_cfg
 what = sys.argv[1] if len(sys.argv) > 1 else "fit"
 cfg, prog = product_cfg(hp, "c2_csg")
-if what == "fit":
+if what == "fitjit":
+    hp.set_jit(True)
+    for p in (2, 3):
+        print(p, hp.bench_frontier(cfg, prog, 5, p, repeats=1))
+elif what == "fit":
     for p in (2, 3):
         print(p, hp.bench_frontier(cfg, prog, 5, p, repeats=1))
 elif what == "query":
