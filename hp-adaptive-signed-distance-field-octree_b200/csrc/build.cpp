@@ -298,7 +298,7 @@ namespace hpsdf
                     if (world_ > 1) hpsdf_shard_range(n, rank_, world_, &b, &e);
                     if (e > b)
                     {
-                        const hpsdf_status ls = launchFit(o_.jit, d, dTasks_.p + groupBegin[d] + b, (int)(e - b), pool_.p, dRecs_.p, prog_, t_.map, t_.ctx->fitTab, stream_);
+                        const hpsdf_status ls = launchFit(o_.jit, d, dTasks_.p + groupBegin[d] + b, (int)(e - b), pool_.p, dRecs_.p, prog_, t_.map, *t_.ctx, stream_);
                         if (ls != HPSDF_OK) return ls;
                         t_.stats.kernel_launches++;
                     }

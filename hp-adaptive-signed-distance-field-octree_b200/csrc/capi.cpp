@@ -300,7 +300,8 @@ extern "C"
         if (e == cudaSuccess) e = cudaEventCreate(&e1);
         if (e == cudaSuccess) e = cudaEventRecord(e0, nullptr);
         hpsdf_status ls = HPSDF_OK;
-        if (e == cudaSuccess) ls = launchFit(0, (int)degree, dT, (int)n, dPool, dR, dp, map, ctx->fitTab, nullptr);
+        std::unique_lock<std::mutex> wsLock(*(std::mutex*)ctx->wsMutex);      // the sample scratch of mesh / octree programs is per device
+        if (e == cudaSuccess) ls = launchFit(0, (int)degree, dT, (int)n, dPool, dR, dp, map, *ctx, nullptr);
         if (e == cudaSuccess) e = cudaEventRecord(e1, nullptr);
         if (e == cudaSuccess) e = cudaMemcpy(coeffs_out, dPool, n * nc * 8, cudaMemcpyDeviceToHost);
         std::vector<FitRecord> recs(n);
@@ -369,11 +370,12 @@ extern "C"
         if (e == cudaSuccess) e = cudaEventCreate(&e0);
         if (e == cudaSuccess) e = cudaEventCreate(&e1);
         hpsdf_status ls = HPSDF_OK;
+        std::unique_lock<std::mutex> wsLock(*(std::mutex*)ctx->wsMutex);
         for (uint32_t r = 0; r <= repeats && e == cudaSuccess && ls == HPSDF_OK; ++r)
         {
             if (r == 1) e = cudaEventRecord(e0, stream);          // launch 0 is the warm-up
-            if (e == cudaSuccess && ls == HPSDF_OK) ls = launchFit(0, (int)degree, dT, (int)nH, dPool, dR, dp, map, ctx->fitTab, stream);
-            if (e == cudaSuccess && ls == HPSDF_OK) ls = launchFit(0, (int)degree + 1, dT + nH, (int)nP, dPool, dR, dp, map, ctx->fitTab, stream);
+            if (e == cudaSuccess && ls == HPSDF_OK) ls = launchFit(0, (int)degree, dT, (int)nH, dPool, dR, dp, map, *ctx, stream);
+            if (e == cudaSuccess && ls == HPSDF_OK) ls = launchFit(0, (int)degree + 1, dT + nH, (int)nP, dPool, dR, dp, map, *ctx, stream);
         }
         if (e == cudaSuccess) e = cudaEventRecord(e1, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);

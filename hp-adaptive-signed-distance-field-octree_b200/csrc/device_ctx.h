@@ -58,6 +58,7 @@ namespace hpsdf
         DeviceBuf<FitTask>   tasks;
         DeviceBuf<FitRecord> recs;
         DeviceBuf<uint32_t>  segs;
+        DeviceBuf<double>    samples;     // F at the Gauss-Legendre points of a chunk of fits (mesh / octree programs only)
         PinnedBuf<FitTask>   hTasks;
         PinnedBuf<FitRecord> hRecs;
         PinnedBuf<uint32_t>  hSegs;
@@ -98,11 +99,12 @@ namespace hpsdf
 
     // kernels.cu
     void        uploadConstants();
+    constexpr size_t kSampleScratchDoubles = (size_t)1 << 26;      // 512 MB of samples per chunk at most
     cudaError_t launchFitKernel(int degree, const FitTask* dTasks, int n, double* pool, FitRecord* recs,
-                                const SdfProgramDev& prog, const RootMap& map, const FitTablesDev& tab, cudaStream_t stream);
+                                const SdfProgramDev& prog, const RootMap& map, DeviceCtx& ctx, cudaStream_t stream);
     // jit.cpp: the fit launch the scheduler calls (interpreted kernels, or NVRTC-specialised ones; see hpsdf_build_opts.jit)
     hpsdf_status launchFit(uint32_t jitMode, int degree, const FitTask* dTasks, int n, double* pool, FitRecord* recs,
-                           const SdfProgramDev& prog, const RootMap& map, const FitTablesDev& tab, cudaStream_t stream);
+                           const SdfProgramDev& prog, const RootMap& map, DeviceCtx& ctx, cudaStream_t stream);
     bool        jitCompileCheck(const SdfProgramDev& prog, int degree, std::string* source, size_t* cubinBytes, std::string& why);
     void        setJitDefault(bool on);
     bool        jitDefault();

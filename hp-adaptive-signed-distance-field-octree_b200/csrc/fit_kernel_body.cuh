@@ -37,14 +37,14 @@ namespace hpsdf
     template <int D, bool EXT>
     __global__ void __launch_bounds__(fitThreads(D))
     fitKernel(const FitTask* __restrict__ tasks, double* __restrict__ pool, FitRecord* __restrict__ recs,
-              const SdfProgramDev prog, const RootMap map, const FitTablesDev tab)
+              const SdfProgramDev prog, const RootMap map, const FitTablesDev tab, const double* __restrict__ samples)
     {
         constexpr int N  = fitRule(D);
         constexpr int N2 = N * N;
         constexpr int P2 = pairCount(D);
         extern __shared__ double smem[];
         __shared__ SdfProgramSmem sProg;
-        stageProgram(sProg, prog);
+        if constexpr (!EXT) stageProgram(sProg, prog);
         double* sQ  = smem;                    // Q[c][k]
         double* sR  = sQ + (D + 1) * N;        // roots
         double* sZ  = sR + N;                  // user-space z of sample k
@@ -61,25 +61,40 @@ namespace hpsdf
         {
             const double r = tab.roots[D][k];
             sR[k] = r;
-            sZ[k] = (r * half + (double)t.cz) * map.sizes[2] + map.centre[2];       // Octree.cpp:1039 then :327
+            sZ[k] = samplePos(r, half, (double)t.cz, map.sizes[2], map.centre[2]);
         }
         __syncthreads();
 
         // ---- stage 1: sample F and contract z ---------------------------------------------------------------------
         for (int col = tid; col < N2; col += blockDim.x)
         {
-            const int i = col % N, j = col / N;
-            const double X = (sR[i] * half + (double)t.cx) * map.sizes[0] + map.centre[0];
-            const double Y = (sR[j] * half + (double)t.cy) * map.sizes[1] + map.centre[1];
             double acc[D + 1];
             #pragma unroll
             for (int c = 0; c <= D; ++c) acc[c] = 0.0;
-            #pragma unroll 1
-            for (int k = 0; k < N; ++k)
+            if constexpr (EXT)
             {
-                const double f = sdfEval<EXT>(sProg, X, Y, sZ[k]);
-                #pragma unroll
-                for (int c = 0; c <= D; ++c) acc[c] = fma(f, sQ[c * N + k], acc[c]);
+                // mesh / octree programs: F was sampled by sampleKernel into samples[fit][k][j][i] (coalesced over col)
+                const double* __restrict__ fs = samples + (size_t)blockIdx.x * (N * N2) + col;
+                #pragma unroll 4
+                for (int k = 0; k < N; ++k)
+                {
+                    const double f = fs[(size_t)k * N2];
+                    #pragma unroll
+                    for (int c = 0; c <= D; ++c) acc[c] = fma(f, sQ[c * N + k], acc[c]);
+                }
+            }
+            else
+            {
+                const int i = col % N, j = col / N;
+                const double X = samplePos(sR[i], half, (double)t.cx, map.sizes[0], map.centre[0]);
+                const double Y = samplePos(sR[j], half, (double)t.cy, map.sizes[1], map.centre[1]);
+                #pragma unroll 1
+                for (int k = 0; k < N; ++k)
+                {
+                    const double f = sdfEval<false>(sProg, X, Y, sZ[k]);
+                    #pragma unroll
+                    for (int c = 0; c <= D; ++c) acc[c] = fma(f, sQ[c * N + k], acc[c]);
+                }
             }
             #pragma unroll
             for (int c = 0; c <= D; ++c) sT1[c * N2 + col] = acc[c];

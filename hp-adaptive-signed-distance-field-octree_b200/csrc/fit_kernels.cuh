@@ -1,5 +1,6 @@
 // fit_kernels.cuh — host launchers of fitKernel<D, EXT> (the kernel itself: fit_kernel_body.cuh).
 #pragma once
+#include <algorithm>
 #include <cuda_runtime.h>
 #include "hp_common.h"
 #include "device_ctx.h"
@@ -7,9 +8,38 @@
 
 namespace hpsdf
 {
+    // ---- mesh / octree programs: F is sampled by a separate kernel -------------------------------------------------------
+    // A BVH closest-triangle query (mesh_eval.cuh) or a tree Query is latency-bound pointer chasing that wants every warp
+    // slot of the SM; inside the fit kernel (one CTA per fit, a thread per (i, j) column walking k, 168 registers with the
+    // evaluators inlined) it ran at 12 warps per SM and 2.6e7 mesh samples/s. So for these programs the round is two
+    // launches per chunk: sampleKernel, one thread per Gauss-Legendre sample at full occupancy, writes F to a scratch
+    // buffer laid out [fit][k][j][i]; fitKernel<D, true> reads it back coalesced (16 bytes of HBM traffic per sample —
+    // nothing next to a traversal). Closed-form programs keep sampling in registers inside the fit kernel.
+    __global__ void __launch_bounds__(256) sampleKernel(const FitTask* __restrict__ tasks, unsigned long long nSamples, int D,
+                                                        const SdfProgramDev prog, const RootMap map, const FitTablesDev tab,
+                                                        double* __restrict__ samples)
+    {
+        __shared__ SdfProgramSmem sProg;
+        stageProgram(sProg, prog);
+        __syncthreads();
+        const unsigned n = (unsigned)fitRule(D), n2 = n * n, n3 = n2 * n;
+        const double* __restrict__ roots = tab.roots[D];
+        for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < nSamples; g += (unsigned long long)gridDim.x * blockDim.x)
+        {
+            const unsigned fit = (unsigned)(g / n3), s = (unsigned)(g - (unsigned long long)fit * n3);
+            const unsigned k = s / n2, col = s - k * n2, j = col / n, i = col - j * n;
+            const float4 cell = *reinterpret_cast<const float4*>(&tasks[fit]);          // cx, cy, cz, half
+            const double half = (double)cell.w;
+            const double X = samplePos(roots[i], half, (double)cell.x, map.sizes[0], map.centre[0]);
+            const double Y = samplePos(roots[j], half, (double)cell.y, map.sizes[1], map.centre[1]);
+            const double Z = samplePos(roots[k], half, (double)cell.z, map.sizes[2], map.centre[2]);
+            samples[g] = sdfEval<true>(sProg, X, Y, Z);
+        }
+    }
+
     template <int D, bool EXT>
     static cudaError_t launchOne(const FitTask* dTasks, int n, double* pool, FitRecord* recs, const SdfProgramDev& prog,
-                                 const RootMap& map, const FitTablesDev& tab, cudaStream_t stream)
+                                 const RootMap& map, const FitTablesDev& tab, double* samples, size_t sampleCap, int smCount, cudaStream_t stream)
     {
         constexpr size_t smem = fitSmemDoubles(D) * sizeof(double);
         static bool attrSet[16] = { false };
@@ -21,8 +51,26 @@ namespace hpsdf
             if (e != cudaSuccess) return e;
             attrSet[dev & 15] = true;
         }
-        fitKernel<D, EXT><<<n, fitThreads(D), smem, stream>>>(dTasks, pool, recs, prog, map, tab);
-        return cudaGetLastError();
+        if constexpr (!EXT)
+        {
+            fitKernel<D, false><<<n, fitThreads(D), smem, stream>>>(dTasks, pool, recs, prog, map, tab, nullptr);
+            return cudaGetLastError();
+        }
+        else
+        {
+            constexpr size_t n3 = (size_t)fitRule(D) * fitRule(D) * fitRule(D);
+            const size_t chunk = sampleCap / n3;
+            if (!samples || !chunk) return cudaErrorInvalidValue;
+            for (size_t b = 0; b < (size_t)n; b += chunk)
+            {
+                const size_t m = std::min(chunk, (size_t)n - b);
+                const unsigned long long total = (unsigned long long)m * n3;
+                const unsigned long long want = (total + 255) / 256, cap = (unsigned long long)(smCount > 0 ? smCount : 148) * 64;
+                sampleKernel<<<(unsigned)std::min(want, cap), 256, 0, stream>>>(dTasks + b, total, D, prog, map, tab, samples);
+                fitKernel<D, true><<<(unsigned)m, fitThreads(D), smem, stream>>>(dTasks + b, pool, recs, prog, map, tab, samples);
+            }
+            return cudaGetLastError();
+        }
     }
 
     static bool programHasExt(const SdfProgramDev& prog)
@@ -33,33 +81,36 @@ namespace hpsdf
     }
 
     template <bool EXT>
-    static cudaError_t launchFitKernelT(int degree, const FitTask* dTasks, int n, double* pool, FitRecord* recs,
-                                const SdfProgramDev& prog, const RootMap& map, const FitTablesDev& tab, cudaStream_t stream)
+    static cudaError_t launchFitKernelT(int degree, const FitTask* dTasks, int n, double* pool, FitRecord* recs, const SdfProgramDev& prog,
+                                        const RootMap& map, const FitTablesDev& tab, double* samples, size_t sampleCap, int smCount, cudaStream_t stream)
     {
         if (n <= 0) return cudaSuccess;
         switch (degree)
         {
-            case 1:  return launchOne<1, EXT>(dTasks, n, pool, recs, prog, map, tab, stream);
-            case 2:  return launchOne<2, EXT>(dTasks, n, pool, recs, prog, map, tab, stream);
-            case 3:  return launchOne<3, EXT>(dTasks, n, pool, recs, prog, map, tab, stream);
-            case 4:  return launchOne<4, EXT>(dTasks, n, pool, recs, prog, map, tab, stream);
-            case 5:  return launchOne<5, EXT>(dTasks, n, pool, recs, prog, map, tab, stream);
-            case 6:  return launchOne<6, EXT>(dTasks, n, pool, recs, prog, map, tab, stream);
-            case 7:  return launchOne<7, EXT>(dTasks, n, pool, recs, prog, map, tab, stream);
-            case 8:  return launchOne<8, EXT>(dTasks, n, pool, recs, prog, map, tab, stream);
-            case 9:  return launchOne<9, EXT>(dTasks, n, pool, recs, prog, map, tab, stream);
-            case 10: return launchOne<10, EXT>(dTasks, n, pool, recs, prog, map, tab, stream);
-            case 11: return launchOne<11, EXT>(dTasks, n, pool, recs, prog, map, tab, stream);
+#define HPSDF_FIT_CASE(d) case d: return launchOne<d, EXT>(dTasks, n, pool, recs, prog, map, tab, samples, sampleCap, smCount, stream);
+            HPSDF_FIT_CASE(1) HPSDF_FIT_CASE(2) HPSDF_FIT_CASE(3) HPSDF_FIT_CASE(4) HPSDF_FIT_CASE(5) HPSDF_FIT_CASE(6)
+            HPSDF_FIT_CASE(7) HPSDF_FIT_CASE(8) HPSDF_FIT_CASE(9) HPSDF_FIT_CASE(10) HPSDF_FIT_CASE(11)
+#undef HPSDF_FIT_CASE
             default: return cudaErrorInvalidValue;
         }
     }
 
-    // Launch the fits of one degree. dTasks: n tasks, all with task.degree == degree.
+    // Launch the fits of one degree. dTasks: n tasks, all with task.degree == degree. Programs with mesh / octree
+    // primitives need the device context's sample scratch (ctx.ws.samples, reserved here).
     cudaError_t launchFitKernel(int degree, const FitTask* dTasks, int n, double* pool, FitRecord* recs,
-                                const SdfProgramDev& prog, const RootMap& map, const FitTablesDev& tab, cudaStream_t stream)
+                                const SdfProgramDev& prog, const RootMap& map, DeviceCtx& ctx, cudaStream_t stream)
     {
-        return programHasExt(prog) ? launchFitKernelT<true>(degree, dTasks, n, pool, recs, prog, map, tab, stream)
-                                   : launchFitKernelT<false>(degree, dTasks, n, pool, recs, prog, map, tab, stream);
+        if (!programHasExt(prog)) return launchFitKernelT<false>(degree, dTasks, n, pool, recs, prog, map, ctx.fitTab, nullptr, 0, ctx.smCount, stream);
+        const size_t n3 = (size_t)fitRule(degree) * fitRule(degree) * fitRule(degree);
+        const size_t want = std::min<size_t>((size_t)std::max(n, 1) * n3, std::max<size_t>(kSampleScratchDoubles, n3));
+        if (ctx.ws.samples.cap < want)
+        {
+            // grow-only scratch; queued work that reads the old buffer must finish before it is freed
+            cudaError_t e = cudaStreamSynchronize(stream);
+            if (e == cudaSuccess) e = ctx.ws.samples.reserve(want);
+            if (e != cudaSuccess) return e;
+        }
+        return launchFitKernelT<true>(degree, dTasks, n, pool, recs, prog, map, ctx.fitTab, ctx.ws.samples.p, ctx.ws.samples.cap, ctx.smCount, stream);
     }
 
     // ---- program evaluation at arbitrary points (hpsdf_sdf_eval) and the FP64 peak probe ---------------------------

@@ -42,6 +42,9 @@ namespace hpsdf
     }
     // number of (b, c) pairs with b + c <= d
     HPSDF_HD constexpr int pairCount(int d) { return (d + 1) * (d + 2) / 2; }
+    // User-space coordinate of a Gauss-Legendre node: node -> cell (Octree.cpp:1039) -> root box (Octree.cpp:327). One
+    // definition, so the fit kernels and the sample kernel contract it identically.
+    HPSDF_HD inline double samplePos(double root, double half, double c, double size, double centre) { return (root * half + c) * size + centre; }
     // Gauss-Legendre points per axis of a degree-d fit (Octree.cpp:1016-1017: rule 4d+1)
     HPSDF_HD constexpr int fitRule(int d) { return 4 * d + 1; }
     // fit kernel geometry (fit_kernel_body.cuh): threads per CTA and dynamic shared memory per degree
