@@ -24,8 +24,12 @@ namespace hpsdf
         __syncthreads();
         const unsigned n = (unsigned)fitRule(D), n2 = n * n, n3 = n2 * n;
         const double* __restrict__ roots = tab.roots[D];
-        for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < nSamples; g += (unsigned long long)gridDim.x * blockDim.x)
+        // warp-uniform trip count (lanes past the end redo the last sample), so the traversals of a warp stay in step
+        for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x; base < nSamples; base += (unsigned long long)gridDim.x * blockDim.x)
         {
+            const unsigned long long gi = base + threadIdx.x;
+            const bool valid = gi < nSamples;
+            const unsigned long long g = valid ? gi : nSamples - 1;
             const unsigned fit = (unsigned)(g / n3), s = (unsigned)(g - (unsigned long long)fit * n3);
             const unsigned k = s / n2, col = s - k * n2, j = col / n, i = col - j * n;
             const float4 cell = *reinterpret_cast<const float4*>(&tasks[fit]);          // cx, cy, cz, half
@@ -33,7 +37,8 @@ namespace hpsdf
             const double X = samplePos(roots[i], half, (double)cell.x, map.sizes[0], map.centre[0]);
             const double Y = samplePos(roots[j], half, (double)cell.y, map.sizes[1], map.centre[1]);
             const double Z = samplePos(roots[k], half, (double)cell.z, map.sizes[2], map.centre[2]);
-            samples[g] = sdfEval<true>(sProg, X, Y, Z);
+            const double f = sdfEval<1>(sProg, X, Y, Z);
+            if (valid) samples[g] = f;
         }
     }
 
@@ -120,7 +125,7 @@ namespace hpsdf
         stageProgram(sProg, prog);
         __syncthreads();
         const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-        if (i < n) out[i] = sdfEval<true>(sProg, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        if (i < n) out[i] = sdfEval<1>(sProg, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
     }
 
     cudaError_t launchSdfEval(const SdfProgramDev& prog, const double* dXyz, size_t n, double* dOut, cudaStream_t stream)

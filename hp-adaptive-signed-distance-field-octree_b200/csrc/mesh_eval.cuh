@@ -10,7 +10,8 @@
 // intrinsics (__fadd_rn / __fmul_rn / __fdiv_rn / __fsqrt_rn are never contracted into FMAs), in the association order of
 // the CPU checker (3-term sums as a0 + (a1 + a2)). The pseudonormals are precomputed on the host with the reference's
 // formulas (mesh.cpp); the BVH itself is free to differ (any BVH yields the same closest triangle): here a host-built
-// median-split binary tree with up to 4 triangles per leaf, traversed with a small per-thread stack, nearer child first.
+// median-split binary tree with up to 4 triangles per leaf, every node bounded by an axis-aligned AND an oriented box,
+// traversed with a small per-thread stack, nearer child first.
 // Ties in squared distance go to the lower triangle index (the brute-force order of Mesh.cpp:134-159).
 #pragma once
 #include "hp_common.h"
@@ -82,66 +83,117 @@ namespace hpsdf
         return dx * dx + dy * dy + dz * dz;
     }
 
-    __device__ __noinline__ float meshSignedDistanceF(const DeviceMeshView* __restrict__ mesh, float px, float py, float pz)
+    // Closest-triangle state of one query point: winner = (smallest f32 d2, lowest triangle index).
+    struct MeshHit
     {
-        const F3 p = f3(px, py, pz);
+        float    best = 3.402823466e+38f;                               // FLT_MAX, BVH.cpp:279
+        uint32_t tri = 0xFFFFFFFFu;
+        int      simplex = 2, id = 0;
+        F3       pt;
+    };
+
+    __device__ __forceinline__ void testLeaf(const float4* __restrict__ tv, uint32_t first, uint32_t cnt, const F3& p, MeshHit& h)
+    {
+        for (uint32_t k = 0; k < cnt; ++k)
+        {
+            const float4 A = __ldg(tv + 3 * (first + k)), B = __ldg(tv + 3 * (first + k) + 1), C = __ldg(tv + 3 * (first + k) + 2);
+            const uint32_t tri = __float_as_uint(A.w);
+            int s, id;
+            const F3 cp = closestSimplex(p, f3(A.x, A.y, A.z), f3(B.x, B.y, B.z), f3(C.x, C.y, C.z), s, id);
+            const F3 d = sub3(p, cp);
+            const float d2 = dot3(d, d);                               // (pt - closestPt).squaredNorm(), BVH.cpp:320
+            if (d2 < h.best || (d2 == h.best && tri < h.tri)) { h.best = d2; h.tri = tri; h.simplex = s; h.id = id; h.pt = cp; }
+        }
+    }
+
+    // sign from the pseudonormal of the hit simplex (Mesh.cpp:162-242, precomputed): face | edge AB, BC, CA | vertex A, B, C
+    __device__ __forceinline__ float finishHit(const DeviceMeshView* __restrict__ mesh, const F3& p, const MeshHit& h)
+    {
+        if (h.tri == 0xFFFFFFFFu) return 3.402823466e+38f;
+        const float* pn = mesh->pseudo + 21 * (size_t)h.tri + (h.simplex == 2 ? 0 : h.simplex == 1 ? 3 + 3 * h.id : 12 + 3 * h.id);
+        const F3 d = sub3(p, h.pt);
+        const float sgn = dot3(f3(__ldg(pn), __ldg(pn + 1), __ldg(pn + 2)), d) > 0.0f ? 1.0f : -1.0f;      // Mesh.cpp:61
+        return __fmul_rn(sgn, __fsqrt_rn(dot3(d, d)));                                                      // Mesh.cpp:62
+    }
+
+    // Lower bound of the squared distance from p to anything inside node `i`: the larger of the axis-aligned bound and
+    // the bound of the node's oriented box (mesh.cpp: frame of the mean normal, extents inflated against float32 rounding).
+    // The oriented box is only fetched when the axis-aligned one does not already prune.
+    __device__ __forceinline__ float nodeDist2(const BvhNode& n, const float4* __restrict__ obb, uint32_t i, const F3& p, float lim)
+    {
+        const float d = boxDist2(n, p);
+        if (d > lim) return d;
+        const float4 o0 = __ldg(obb + 4 * (size_t)i), o1 = __ldg(obb + 4 * (size_t)i + 1), o2 = __ldg(obb + 4 * (size_t)i + 2), o3 = __ldg(obb + 4 * (size_t)i + 3);
+        const float qu = fmaxf(fabsf(p.x * o1.x + p.y * o1.y + p.z * o1.z - o0.x) - o0.w, 0.0f);
+        const float qv = fmaxf(fabsf(p.x * o2.x + p.y * o2.y + p.z * o2.z - o0.y) - o1.w, 0.0f);
+        const float qn = fmaxf(fabsf(p.x * o3.x + p.y * o3.y + p.z * o3.z - o0.z) - o2.w, 0.0f);
+        return fmaxf(d, qu * qu + qv * qv + qn * qn);
+    }
+
+    // Per-thread traversal, nearer child first, "while-while": the lanes of a warp first all walk inner nodes until each
+    // holds a leaf (or is done), then all test their leaf's triangles together — a lane in the 600-instruction triangle
+    // test no longer stalls 31 lanes that only want a 30-instruction node step. Pruning is conservative (bounds are
+    // evaluated with FMAs: a few ulps of slack). `h` may carry a candidate found earlier.
+    __device__ __forceinline__ void traverseThread(const DeviceMeshView* __restrict__ mesh, const F3& p, MeshHit& h)
+    {
         const BvhNode* __restrict__ nodes = mesh->nodes;
+        const float4* __restrict__ obb = (const float4*)mesh->obb;
         const float4* __restrict__ tv = (const float4*)mesh->triVerts;
-        float best = 3.402823466e+38f;                                 // FLT_MAX, BVH.cpp:279
-        uint32_t bestTri = 0xFFFFFFFFu;
-        int bestSimplex = 2, bestId = 0;
-        F3 bestPt = p;
         uint32_t stack[48];
+        float    stackD[48];
         int sp = 0;
         uint32_t cur = 0;
-        for (;;)
+        bool alive = true;
+        while (alive)
         {
-            const BvhNode n = nodes[cur];
-            if (n.b & 0x80000000u)
+            // phase 1: descend until `cur` is a leaf that can still hold something closer
+            uint32_t leafFirst = 0, leafCnt = 0;
+            for (;;)
             {
-                const uint32_t cnt = n.b & 0x7FFFFFFFu;
-                for (uint32_t k = 0; k < cnt; ++k)
-                {
-                    const float4 A = __ldg(tv + 3 * (n.a + k)), B = __ldg(tv + 3 * (n.a + k) + 1), C = __ldg(tv + 3 * (n.a + k) + 2);
-                    const uint32_t tri = __float_as_uint(A.w);
-                    int s, id;
-                    const F3 cp = closestSimplex(p, f3(A.x, A.y, A.z), f3(B.x, B.y, B.z), f3(C.x, C.y, C.z), s, id);
-                    const F3 d = sub3(p, cp);
-                    const float d2 = dot3(d, d);                       // (pt - closestPt).squaredNorm(), BVH.cpp:320
-                    if (d2 < best || (d2 == best && tri < bestTri)) { best = d2; bestTri = tri; bestSimplex = s; bestId = id; bestPt = cp; }
-                }
-            }
-            else
-            {
-                const float dl = boxDist2(nodes[n.a], p), dr = boxDist2(nodes[n.b], p);
-                // conservative pruning: the bound is evaluated with FMAs, leave a few ulps of slack
-                const float lim = best * 1.000001f;
+                const BvhNode n = nodes[cur];
+                if (n.b & 0x80000000u) { leafFirst = n.a; leafCnt = n.b & 0x7FFFFFFFu; break; }
+                const float lim = h.best * 1.000001f;
+                const float dl = nodeDist2(nodes[n.a], obb, n.a, p, lim), dr = nodeDist2(nodes[n.b], obb, n.b, p, lim);
                 const bool goL = dl <= lim, goR = dr <= lim;
                 if (goL && goR)
                 {
                     const bool leftFirst = dl <= dr;
-                    if (sp < 48) stack[sp++] = leftFirst ? n.b : n.a;
+                    if (sp < 48) { stack[sp] = leftFirst ? n.b : n.a; stackD[sp] = leftFirst ? dr : dl; ++sp; }
                     cur = leftFirst ? n.a : n.b;
                     continue;
                 }
                 if (goL) { cur = n.a; continue; }
                 if (goR) { cur = n.b; continue; }
+                bool found = false;
+                while (sp > 0)
+                {
+                    --sp;
+                    if (stackD[sp] <= h.best * 1.000001f) { cur = stack[sp]; found = true; break; }
+                }
+                if (!found) { alive = false; break; }
             }
-            // pop the next subtree that can still hold something closer
-            bool found = false;
-            while (sp > 0)
+            // phase 2: the leaf's triangles
+            if (alive)
             {
-                cur = stack[--sp];
-                if (boxDist2(nodes[cur], p) <= best * 1.000001f) { found = true; break; }
+                testLeaf(tv, leafFirst, leafCnt, p, h);
+                bool found = false;
+                while (sp > 0)
+                {
+                    --sp;
+                    if (stackD[sp] <= h.best * 1.000001f) { cur = stack[sp]; found = true; break; }
+                }
+                alive = found;
             }
-            if (!found) break;
         }
-        if (bestTri == 0xFFFFFFFFu) return 3.402823466e+38f;
-        // pseudonormal of the hit simplex (Mesh.cpp:162-242, precomputed): face | edge AB, BC, CA | vertex A, B, C
-        const float* pn = mesh->pseudo + 21 * (size_t)bestTri + (bestSimplex == 2 ? 0 : bestSimplex == 1 ? 3 + 3 * bestId : 12 + 3 * bestId);
-        const F3 d = sub3(p, bestPt);
-        const float sgn = dot3(f3(__ldg(pn), __ldg(pn + 1), __ldg(pn + 2)), d) > 0.0f ? 1.0f : -1.0f;      // Mesh.cpp:61
-        return __fmul_rn(sgn, __fsqrt_rn(dot3(d, d)));                                                      // Mesh.cpp:62
+    }
+
+    __device__ __noinline__ float meshSignedDistanceF(const DeviceMeshView* __restrict__ mesh, float px, float py, float pz)
+    {
+        const F3 p = f3(px, py, pz);
+        MeshHit h;
+        h.pt = p;
+        traverseThread(mesh, p, h);
+        return finishHit(mesh, p, h);
     }
 
     // The double-precision SDF the fit samples: the point is cast to float32, the result widened (the user-side glue the

@@ -41,6 +41,24 @@ def test_mesh_distance_matches_oracle_brute_force_and_bvh(hp, oracle, torus):
     assert len(m.SignedDistanceAtPt(np.zeros((0, 3)))) == 0
 
 
+def test_fine_mesh_far_and_near_points_match_the_oracle(hp, oracle):
+    """139 k triangles of 3 mm against distances up to 0.4: the regime where the oriented-box pruning of mesh_eval.cuh does
+    most of its work (hundreds of axis-aligned leaf boxes overlap the search sphere). Still bit-identical."""
+    v, t = bumpy_torus(400, 174)
+    m = hp.Mesh(v, t)
+    om = oracle.OracleMesh(v, t)
+    lo, hi = mesh_root(v)
+    rng = np.random.default_rng(11)
+    far = rng.uniform(lo, hi, (60000, 3)).astype(np.float32)
+    axis = np.stack([rng.normal(0, 1e-3, 4000), rng.normal(0, 1e-3, 4000), rng.uniform(-0.3, 0.3, 4000)], 1).astype(np.float32)   # torus axis: many equidistant triangles
+    cent = v[t[rng.integers(0, len(t), 30000)]].mean(1)
+    near = (cent + rng.normal(0, 1, (30000, 3)) * rng.choice([1e-5, 1e-4, 1e-3, 1e-2], (30000, 1))).astype(np.float32)
+    allp = np.concatenate([far, axis, near, v[:3000]])
+    d = m.SignedDistanceAtPt(allp)
+    ref = om.sdf(allp, True, 16)
+    assert np.array_equal(d, ref), "mismatches: %d of %d, max |diff| %g" % ((d != ref).sum(), len(d), np.abs(d - ref).max())
+
+
 def test_open_mesh_is_rejected(hp):
     v, t = bumpy_torus(12, 8)
     with pytest.raises(hp.HpsdfError) as e:
