@@ -59,6 +59,7 @@ namespace hpsdf
         DeviceBuf<FitRecord> recs;
         DeviceBuf<uint32_t>  segs;
         DeviceBuf<double>    samples;     // F at the Gauss-Legendre points of a chunk of fits (mesh / octree programs only)
+        DeviceBuf<unsigned long long> sampleCounter;   // work counter of meshSampleKernel
         PinnedBuf<FitTask>   hTasks;
         PinnedBuf<FitRecord> hRecs;
         PinnedBuf<uint32_t>  hSegs;

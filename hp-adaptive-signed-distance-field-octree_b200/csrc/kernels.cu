@@ -13,6 +13,7 @@ namespace hpsdf
 #include "mesh_eval.cuh"
 #include "query_eval.cuh"
 #include "sdf_eval.cuh"
+#include "mesh_sample_kernel.cuh"
 #include "fit_kernels.cuh"
 #include "query_kernels.cuh"
 #include "continuity_kernels.cuh"

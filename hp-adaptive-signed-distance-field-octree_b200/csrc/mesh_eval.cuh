@@ -130,6 +130,22 @@ namespace hpsdf
         return fmaxf(d, qu * qu + qv * qv + qn * qn);
     }
 
+    // the same two bounds on data already in registers (mesh_sample_kernel.cuh requests everything of a step at once)
+    __device__ __forceinline__ float aabbDist2(const float4& lo, const float4& hi, const F3& p)
+    {
+        const float dx = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.0f);
+        const float dy = fmaxf(fmaxf(lo.y - p.y, p.y - hi.y), 0.0f);
+        const float dz = fmaxf(fmaxf(lo.z - p.z, p.z - hi.z), 0.0f);
+        return dx * dx + dy * dy + dz * dz;
+    }
+    __device__ __forceinline__ float obbDist2(const float4& o0, const float4& o1, const float4& o2, const float4& o3, const F3& p)
+    {
+        const float qu = fmaxf(fabsf(p.x * o1.x + p.y * o1.y + p.z * o1.z - o0.x) - o0.w, 0.0f);
+        const float qv = fmaxf(fabsf(p.x * o2.x + p.y * o2.y + p.z * o2.z - o0.y) - o1.w, 0.0f);
+        const float qn = fmaxf(fabsf(p.x * o3.x + p.y * o3.y + p.z * o3.z - o0.z) - o2.w, 0.0f);
+        return qu * qu + qv * qv + qn * qn;
+    }
+
     // Per-thread traversal, nearer child first, "while-while": the lanes of a warp first all walk inner nodes until each
     // holds a leaf (or is done), then all test their leaf's triangles together — a lane in the 600-instruction triangle
     // test no longer stalls 31 lanes that only want a 30-instruction node step. Pruning is conservative (bounds are

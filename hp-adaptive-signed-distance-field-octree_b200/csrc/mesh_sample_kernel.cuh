@@ -1,0 +1,176 @@
+// mesh_sample_kernel.cuh — F at the Gauss-Legendre points of a chunk of fits when the SDF program is a single triangle
+// mesh: the kernel that dominates every mesh build (configs 3-5 of BASELINE.json).
+//
+// What ncu said about calling the per-thread traversal (mesh_eval.cuh) from sampleKernel, one sample per thread:
+// 5.9 of 32 lanes active per issued instruction. A closest-triangle query alternates between ~80-instruction node steps
+// and ~170-instruction exact triangle tests (ClosestSimplexToPt mirrored operation by operation), the lanes of a warp need
+// different numbers of node steps to reach their next leaf (the node loop ran 788 iterations per warp for 111 per lane),
+// and a lane whose query is finished idles until the slowest one of its warp is.
+//
+// Here the warp is a scheduler over 32 independent query state machines:
+//   * every loop iteration is EITHER a node step OR a triangle test for all lanes that have one pending — the choice is
+//     warp-uniform (ballots), so the two instruction streams are never serialised against each other;
+//   * reaching a leaf does not test it: the leaf goes into a 4-entry per-lane queue and the lane keeps walking; triangle
+//     iterations run when at least `triThreshold` (12) lanes have a triangle waiting (or nobody has a node left), re-checking the leaf's
+//     bound against the lane's current best first;
+//   * a lane that finishes its query writes the sample and takes the next one (warps grab 32-128 samples at a time from a
+//     global counter), so lanes do not wait for their neighbours and far / near cells balance across the grid.
+// Results are those of meshSignedDistanceF: same exact test, same (smallest f32 d2, lowest triangle index) winner, same
+// conservative pruning — the order in which candidates are met does not matter to that rule.
+#pragma once
+#include "hp_common.h"
+#include "mesh_eval.cuh"
+
+namespace hpsdf
+{
+    constexpr int      kMeshQueue = 4;
+    constexpr int      kMeshStack = 40;
+    constexpr uint32_t kNoNode    = 0xFFFFFFFFu;
+
+    __global__ void __launch_bounds__(256, 4)
+    meshSampleKernel(const FitTask* __restrict__ tasks, unsigned long long nSamples, int D, const DeviceMeshView* __restrict__ mesh,
+                     const RootMap map, const FitTablesDev tab, double* __restrict__ samples, unsigned long long* __restrict__ counter,
+                     const unsigned grab, const int triThreshold)
+    {
+        const float4* __restrict__ nodes4 = (const float4*)mesh->nodes;        // 2 float4 per node: {mn, a}, {mx, b}
+        const float4* __restrict__ obb = (const float4*)mesh->obb;
+        const float4* __restrict__ tv = (const float4*)mesh->triVerts;
+        const double* __restrict__ roots = tab.roots[D];
+        const unsigned n = (unsigned)fitRule(D), n2 = n * n, n3 = n2 * n;
+        const unsigned lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
+        const uint32_t rootA = __float_as_uint(__ldg(&nodes4[0].w)), rootB = __float_as_uint(__ldg(&nodes4[1].w));
+
+        // per-lane query state
+        long long sid = -1;                       // sample index, -1 = idle
+        F3 p = f3(0.0f, 0.0f, 0.0f);
+        MeshHit h;
+        uint32_t stackN[kMeshStack]; float stackD[kMeshStack];
+        int sp = 0;
+        uint32_t cur = kNoNode, curA = 0, curB = 0; float curD = 0.0f;       // node to process, its child / leaf words, its bound
+        uint32_t qLeaf[kMeshQueue]; float qD[kMeshQueue];        // circular: head qh, count qn; entry = first slot | count << 29
+        int qh = 0, qn = 0, tcur = 0;
+        // warp-uniform work cursor
+        unsigned long long cursor = 0, grabEnd = 0;
+        bool exhausted = false;
+
+        auto pop = [&]()
+        {
+            cur = kNoNode;
+            while (sp > 0)
+            {
+                --sp;
+                if (stackD[sp] <= h.best * 1.000001f) { cur = stackN[sp]; curD = stackD[sp]; break; }
+            }
+            if (cur != kNoNode)
+            {
+                curA = __float_as_uint(__ldg(&nodes4[2 * (size_t)cur].w));
+                curB = __float_as_uint(__ldg(&nodes4[2 * (size_t)cur + 1].w));
+            }
+        };
+
+        for (;;)
+        {
+            // ---- retire finished queries, hand out new samples -----------------------------------------------------
+            if (sid >= 0 && cur == kNoNode && qn == 0)
+            {
+                samples[sid] = (double)finishHit(mesh, p, h);
+                sid = -1;
+            }
+            unsigned idle = __ballot_sync(0xFFFFFFFFu, sid < 0);
+            while (idle && !exhausted)
+            {
+                if (cursor == grabEnd)
+                {
+                    unsigned long long g = 0;
+                    if (lane == 0) g = atomicAdd(counter, (unsigned long long)grab);
+                    g = __shfl_sync(0xFFFFFFFFu, g, 0);
+                    if (g >= nSamples) { exhausted = true; break; }
+                    cursor = g;
+                    grabEnd = g + grab < nSamples ? g + grab : nSamples;
+                }
+                const unsigned avail = (unsigned)(grabEnd - cursor), want = (unsigned)__popc(idle);
+                const unsigned rank = (unsigned)__popc(idle & ltMask);
+                if (sid < 0 && rank < avail)
+                {
+                    sid = (long long)(cursor + rank);
+                    const unsigned long long g = (unsigned long long)sid;
+                    const unsigned fit = (unsigned)(g / n3), s = (unsigned)(g - (unsigned long long)fit * n3);
+                    const unsigned k = s / n2, col = s - k * n2, j = col / n, i = col - j * n;
+                    const float4 cell = *reinterpret_cast<const float4*>(&tasks[fit]);          // cx, cy, cz, half
+                    const double half = (double)cell.w;
+                    // the same expressions as the closed-form fit kernels (samplePos), then the float32 cast of the mesh SDF glue
+                    p = f3((float)samplePos(roots[i], half, (double)cell.x, map.sizes[0], map.centre[0]),
+                           (float)samplePos(roots[j], half, (double)cell.y, map.sizes[1], map.centre[1]),
+                           (float)samplePos(roots[k], half, (double)cell.z, map.sizes[2], map.centre[2]));
+                    h = MeshHit();
+                    h.pt = p;
+                    sp = 0; cur = 0; curD = 0.0f; qh = 0; qn = 0; tcur = 0;
+                    curA = rootA; curB = rootB;
+                }
+                cursor += want < avail ? want : avail;
+                idle = __ballot_sync(0xFFFFFFFFu, sid < 0);
+            }
+            if (idle == 0xFFFFFFFFu) break;                                   // nothing in flight and nothing left to take
+
+            // ---- one step for everybody who has one ----------------------------------------------------------------
+            const bool wantNode = sid >= 0 && cur != kNoNode && qn < kMeshQueue;
+            const unsigned nodeMask = __ballot_sync(0xFFFFFFFFu, wantNode);
+            const unsigned triMask = __ballot_sync(0xFFFFFFFFu, qn > 0);
+            if (nodeMask != 0u && __popc(triMask) < triThreshold)
+            {
+                if (wantNode)
+                {
+                    const uint32_t a = curA, b = curB;
+                    if (b & 0x80000000u)
+                    {
+                        const int slot = (qh + qn) & (kMeshQueue - 1);
+                        qLeaf[slot] = a | (b << 29);                             // first triangle slot (< 2^29) | count (1..4)
+                        qD[slot] = curD;
+                        ++qn;
+                        pop();
+                    }
+                    else
+                    {
+                        // one round trip per step: both children's axis-aligned AND oriented boxes are requested together
+                        // (the walk is latency-bound: ncu showed 10 cycles of long-scoreboard stall per issued instruction)
+                        const float4 l0 = __ldg(nodes4 + 2 * (size_t)a), l1 = __ldg(nodes4 + 2 * (size_t)a + 1);
+                        const float4 r0 = __ldg(nodes4 + 2 * (size_t)b), r1 = __ldg(nodes4 + 2 * (size_t)b + 1);
+                        const float4 lo0 = __ldg(obb + 4 * (size_t)a), lo1 = __ldg(obb + 4 * (size_t)a + 1), lo2 = __ldg(obb + 4 * (size_t)a + 2), lo3 = __ldg(obb + 4 * (size_t)a + 3);
+                        const float4 ro0 = __ldg(obb + 4 * (size_t)b), ro1 = __ldg(obb + 4 * (size_t)b + 1), ro2 = __ldg(obb + 4 * (size_t)b + 2), ro3 = __ldg(obb + 4 * (size_t)b + 3);
+                        const float lim = h.best * 1.000001f;
+                        const float dl = fmaxf(aabbDist2(l0, l1, p), obbDist2(lo0, lo1, lo2, lo3, p));
+                        const float dr = fmaxf(aabbDist2(r0, r1, p), obbDist2(ro0, ro1, ro2, ro3, p));
+                        const bool goL = dl <= lim, goR = dr <= lim;
+                        if (goL && goR)
+                        {
+                            const bool leftFirst = dl <= dr;
+                            if (sp < kMeshStack) { stackN[sp] = leftFirst ? b : a; stackD[sp] = leftFirst ? dr : dl; ++sp; }
+                            cur = leftFirst ? a : b; curD = leftFirst ? dl : dr;
+                            curA = __float_as_uint(leftFirst ? l0.w : r0.w); curB = __float_as_uint(leftFirst ? l1.w : r1.w);
+                        }
+                        else if (goL) { cur = a; curD = dl; curA = __float_as_uint(l0.w); curB = __float_as_uint(l1.w); }
+                        else if (goR) { cur = b; curD = dr; curA = __float_as_uint(r0.w); curB = __float_as_uint(r1.w); }
+                        else pop();
+                    }
+                }
+            }
+            else if (qn > 0)
+            {
+                const uint32_t e = qLeaf[qh];
+                const uint32_t first = e & 0x1FFFFFFFu, cnt = e >> 29;
+                if (tcur == 0 && qD[qh] > h.best * 1.000001f) { qh = (qh + 1) & (kMeshQueue - 1); --qn; }      // pruned while it waited
+                else
+                {
+                    const float4 A = __ldg(tv + 3 * (size_t)(first + tcur)), B = __ldg(tv + 3 * (size_t)(first + tcur) + 1), C = __ldg(tv + 3 * (size_t)(first + tcur) + 2);
+                    const uint32_t tri = __float_as_uint(A.w);
+                    int s, id;
+                    const F3 cp = closestSimplex(p, f3(A.x, A.y, A.z), f3(B.x, B.y, B.z), f3(C.x, C.y, C.z), s, id);
+                    const F3 d = sub3(p, cp);
+                    const float d2 = dot3(d, d);                               // (pt - closestPt).squaredNorm(), BVH.cpp:320
+                    if (d2 < h.best || (d2 == h.best && tri < h.tri)) { h.best = d2; h.tri = tri; h.simplex = s; h.id = id; h.pt = cp; }
+                    if (++tcur == (int)cnt) { tcur = 0; qh = (qh + 1) & (kMeshQueue - 1); --qn; }
+                }
+            }
+        }
+    }
+}
