@@ -395,6 +395,8 @@ def main():
         "roofline": {"kernel": "fitKernel<D> specialised to the program (all fit launches of the timed builds)", "bound": "fp64",
                      "achieved": fit_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fit_tflops / fp64_peak,
                      "traffic": None,
+                     "traffic_note": "the fit kernels read a 32-byte task and write N_d coefficients per fit; ncu on the frontier launch "
+                                     "(262 144 fits @2): 8.4 MB DRAM read, writes stay in L2 (profiles/r1_fit_kernel_jit.md)",
                      "note": "achieved = SURVEY.md 8d algorithmic FLOPs (sum-factorised contraction + c_F = %.0f per SDF sample, sqrt/div "
                              "counted as 1) / device time of the fit launches; peak = DFMA rate measured in this run "
                              "(hpsdf_measure_fp64_peak; MEASURED_PEAKS.json holds no FP64 figure); a C2 build has only ~%d fits per "
@@ -406,7 +408,10 @@ def main():
                   "e2e": {"value": qe_value, "unit": "points/s", "h2d_bytes_per_step": n_qe * 24, "d2h_bytes_per_step": n_qe * 8},
                   "roofline": {"kernel": "queryKernel", "bound": "hbm", "achieved": n_q * 32 / (q_ms * 1e-3) / 1e9,
                                "peak": hbm_peak, "unit": "GB/s", "frac": n_q * 32 / (q_ms * 1e-3) / 1e9 / hbm_peak,
-                               "traffic": None, "peak_source": peak_src}},
+                               "traffic": 525.06e6 if n_q == (1 << 24) else None,
+                               "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch on 2^24 points, profiles/r1_query_kernel.md "
+                                                 "(algorithmic bytes of the same launch: 536.9e6)",
+                               "peak_source": peak_src}},
     }
     if mesh_line is not None:
         line["mesh_build"] = mesh_line
