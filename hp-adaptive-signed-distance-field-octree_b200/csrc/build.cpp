@@ -22,6 +22,8 @@
 #include <mutex>
 #include <queue>
 #include <vector>
+#include <cstdio>
+#include <cstdlib>
 #include "octree.h"
 #include "comm.h"
 
@@ -32,7 +34,8 @@ namespace hpsdf
         struct Job
         {
             bool     coarse = false, doH = false, doP = false;
-            uint32_t hSlot[8] = { 0 }, pSlot = 0;
+            uint32_t hSlot0 = 0, pSlot = 0;                  // pool slots: child c at hSlot0 + c * N_degree, the p-fit
+            uint32_t hPos = 0, pPos = 0;                     // record indices of child 0 / the p-fit in their round
             double   hErr[8] = { 0 }, pErr = 0.0, hImp = 0.0, pImp = 0.0;
         };
 
@@ -88,7 +91,6 @@ namespace hpsdf
             double                   applyLevel_ = std::numeric_limits<double>::infinity();   // entries >= this are certain to be popped
             size_t                   levelLogStart_ = 0;     // first apply-log entry of the current level
             double                   pendingMax_ = 0.0;      // largest error among pending_ (uncached) leaves
-            std::vector<uint32_t>    owner_;                 // per task: job index << 4 | child slot (8 = the p-fit)
             std::vector<uint64_t>    evaluated_;
             std::vector<uint64_t>    coarseReady_;           // coarse cells whose degree-2 fit is cached
             std::vector<uint64_t>    ready_;                 // freshly evaluated leaves not yet in the heap
@@ -98,13 +100,20 @@ namespace hpsdf
             std::vector<double>      errOf_;        // per node: its current (weighted) error
             std::vector<uint8_t>     inQueue_;      // per node: 1 while the leaf is in the priority queue
             std::vector<Job>         jobs_;
-            std::vector<uint64_t>    pending_;      // leaves created / changed by the last replay
+            // leaves of the conceptual queue whose job has not been evaluated yet, bucketed by error exponent like the
+            // histogram, so that a round only touches the entries it selects (a flat list was rescanned every round:
+            // 20 k entries x 18 rounds = a fifth of a C2 build)
+            std::vector<std::vector<uint64_t>> pendB_ = std::vector<std::vector<uint64_t>>(kBuckets);
+            size_t                   pendCount_ = 0;
+            std::vector<uint64_t>    coarseCells_;  // the 16^3 cells in visiting order (UniformlyRefine)
+            int                      pendTop_ = 0;  // no non-empty bucket above this one
 
             BuildWorkspace&          ws_ = t_.ctx->ws;
             DeviceBuf<double>&       pool_ = ws_.pool;  size_t poolUsed_ = 0;
             DeviceBuf<FitTask>&      dTasks_ = ws_.tasks;
             DeviceBuf<FitRecord>&    dRecs_ = ws_.recs;
-            PinnedBuf<FitTask>&      hTasks_ = ws_.hTasks;
+            DeviceBuf<JobDesc>&      dJobs_ = ws_.jobs;
+            PinnedBuf<JobDesc>&      hJobs_ = ws_.hJobs;
             PinnedBuf<FitRecord>&    hRecs_ = ws_.hRecs;
 
             double      total_ = 0.0;               // totalCoeffError, reference bookkeeping (Octree.cpp:212, 257, 272, 276)
@@ -135,7 +144,9 @@ namespace hpsdf
                 inQueue_[idx] = 1;
                 const int b = bucketOf(err);
                 bucketSum_[b] += err; bucketCount_[b]++;
-                pending_.push_back(idx);
+                pendB_[b].push_back(idx);
+                ++pendCount_;
+                pendTop_ = std::max(pendTop_, b);
                 pendingMax_ = std::max(pendingMax_, err);
             }
             void hPop()
@@ -149,7 +160,7 @@ namespace hpsdf
             double conceptualTop() const
             {
                 const double h = queue_.empty() ? 0.0 : queue_.top().second;
-                return pending_.empty() ? h : std::max(h, pendingMax_);
+                return pendCount_ == 0 ? h : std::max(h, pendingMax_);
             }
             double checkValue() const
             {
@@ -184,7 +195,7 @@ namespace hpsdf
             else
             {
                 nodes_[idx].degree = 0;
-                pending_.push_back(idx);        // enters the queue with err = 100 in run(), in this (visiting) order
+                coarseCells_.push_back(idx);    // enters the queue with err = 100 in run(), in this (visiting) order
             }
         }
 
@@ -207,12 +218,14 @@ namespace hpsdf
             const size_t firstJob = jobs_.size();
             evaluated_.clear();
             size_t cnt[kMaxDegree + 2] = { 0 };
-            size_t keepN = 0;
-            pendingMax_ = 0.0;
-            for (size_t k = 0; k < pending_.size(); ++k)
+            // Everything at or above the level is needed work. If that is only a handful of jobs the round would cost a full
+            // upload / launch / synchronise / replay cycle for them (10 of the 18 rounds of a C2 build selected fewer than 20
+            // jobs), so the round is topped up to `min_round_jobs` with the next-largest pending errors: the greedy loop is
+            // about to reach them anyway and their results stay cached until it does.
+            const size_t minJobs = o_.min_round_jobs ? o_.min_round_jobs : 512u;
+            const size_t pendBefore = pendCount_;
+            auto select = [&](uint64_t idx)
             {
-                const uint64_t idx = pending_[k];
-                if (errOf_[idx] < level) { pending_[keepN++] = idx; pendingMax_ = std::max(pendingMax_, errOf_[idx]); continue; }
                 const HostNode& n = nodes_[idx];
                 jobs_.emplace_back();
                 Job& j = jobs_.back();
@@ -227,8 +240,30 @@ namespace hpsdf
                 }
                 jobOf_[idx] = (int32_t)(jobs_.size() - 1);
                 evaluated_.push_back(idx);
+            };
+            const int levelBucket = bucketOf(level);
+            pendingMax_ = 0.0;
+            for (int b = pendTop_; b >= 0 && pendCount_ > 0; --b)
+            {
+                std::vector<uint64_t>& B = pendB_[b];
+                if (B.empty()) { if (b == pendTop_ && pendTop_ > 0) --pendTop_; continue; }
+                if (b < levelBucket && evaluated_.size() >= minJobs) break;
+                size_t keep = 0;
+                for (size_t k = 0; k < B.size(); ++k)
+                {
+                    const uint64_t idx = B[k];
+                    if (errOf_[idx] >= level || evaluated_.size() < minJobs) select(idx);
+                    else B[keep++] = idx;
+                }
+                pendCount_ -= B.size() - keep;
+                B.resize(keep);
+                if (keep) break;                 // the bucket was only partly taken: nothing below it is selected
             }
-            pending_.resize(keepN);
+            while (pendTop_ > 0 && pendB_[pendTop_].empty()) --pendTop_;
+            if (pendCount_) for (uint64_t idx : pendB_[pendTop_]) pendingMax_ = std::max(pendingMax_, errOf_[idx]);
+            static const bool dbgRounds = getenv("HPSDF_DEBUG_ROUNDS") != nullptr;
+            if (dbgRounds) fprintf(stderr, "round %llu: pending %zu -> %zu, jobs %zu, heap %zu, level %.3e, passA %.3f ms\n", (unsigned long long)t_.stats.rounds,
+                                   pendBefore, pendCount_, evaluated_.size(), queue_.entries().size(), level, nowMs() - tTask0);
 
             // Tasks in degree order; task index == record index; slots allocated in task order (contiguous per degree,
             // so a rank's shard of a degree group is one contiguous pool range).
@@ -246,40 +281,46 @@ namespace hpsdf
                 HPSDF_CUDA(pool_.reserve(poolNeed + 1024, stream_, poolUsed_));
                 HPSDF_CUDA(dTasks_.reserve(nTasks));
                 HPSDF_CUDA(dRecs_.reserve(nTasks));
-                HPSDF_CUDA(hTasks_.reserve(nTasks));
                 HPSDF_CUDA(hRecs_.reserve(nTasks));
+                HPSDF_CUDA(dJobs_.reserve(evaluated_.size()));
+                HPSDF_CUDA(hJobs_.reserve(evaluated_.size()));
             }
-            owner_.resize(nTasks);
-            // pass B: write the 32-byte task descriptors straight into pinned memory. Cells are dyadic, so centre and half size
-            // of a child follow exactly (in f32) from the parent's: c +- h/2, h/2 — the values CornerAABB + center() give.
-            FitTask* T = hTasks_.p;
-            auto emit = [&](int d, float cx, float cy, float cz, float half, uint8_t depth, uint8_t degreeIn, uint32_t src, uint32_t own) -> uint32_t
-            {
-                const size_t pos = cursor[d]++;
-                FitTask& t = T[pos];
-                t.cx = cx; t.cy = cy; t.cz = cz; t.half = half;
-                t.out = (uint32_t)(groupPool[d] + (pos - groupBegin[d]) * (size_t)coeffCount(d));
-                t.src = src; t.depth = depth; t.degree = (uint8_t)d; t.degreeIn = degreeIn; t.pad = 0; t.rec = (uint32_t)pos;
-                owner_[pos] = own;
-                return t.out;
-            };
+            // pass B: one 32-byte job record per job straight into pinned memory; expandJobsKernel derives the fit tasks on
+            // the device (the host used to write all 9 descriptors of a job: 75 k x 32 B per C2 build, a quarter of its time).
+            // Task index == record index; slots are allocated in task order (contiguous per degree, so a rank's shard of a
+            // degree group is one contiguous pool range).
+            RoundLayout lay;
+            for (int d = 0; d <= kMaxDegree + 1; ++d) { lay.groupBegin[d] = (uint32_t)groupBegin[d]; lay.groupPool[d] = (uint32_t)groupPool[d]; }
+            auto slotOf = [&](int d, size_t pos) { return (uint32_t)(groupPool[d] + (pos - groupBegin[d]) * (size_t)coeffCount(d)); };
+            JobDesc* J = hJobs_.p;
             for (size_t k = 0; k < evaluated_.size(); ++k)
             {
                 const uint64_t idx = evaluated_[k];
                 const HostNode& n = nodes_[idx];
-                const uint32_t jobIdx = (uint32_t)(firstJob + k);
-                Job& j = jobs_[jobIdx];
-                const float cx = (n.mn[0] + n.mx[0]) / 2.0f, cy = (n.mn[1] + n.mx[1]) / 2.0f, cz = (n.mn[2] + n.mx[2]) / 2.0f;   // AlignedBox::center() in f32
-                const float half = (n.mx[0] - n.mn[0]) * 0.5f;
-                if (j.coarse) { j.pSlot = emit(kCoarseDegree, cx, cy, cz, half, n.depth, 0, kNoSrc, jobIdx << 4 | 8u); continue; }   // Octree.cpp:840
-                if (j.doH)
+                Job& j = jobs_[firstJob + k];
+                JobDesc& o = J[k];
+                o.cx = (n.mn[0] + n.mx[0]) / 2.0f; o.cy = (n.mn[1] + n.mx[1]) / 2.0f; o.cz = (n.mn[2] + n.mx[2]) / 2.0f;   // AlignedBox::center() in f32
+                o.half = (n.mx[0] - n.mn[0]) * 0.5f;
+                o.depth = n.depth; o.degree = n.degree; o.pad = 0; o.src = n.slot; o.hPos = o.pPos = 0;
+                if (j.coarse)                                                                    // Octree.cpp:840
                 {
-                    const float q = half * 0.5f;
-                    for (uint32_t c = 0; c < 8; ++c)                                                                 // Octree.cpp:820
-                        j.hSlot[c] = emit(n.degree, cx + ((c & 1) ? q : -q), cy + ((c & 2) ? q : -q), cz + ((c & 4) ? q : -q), q,
-                                          (uint8_t)(n.depth + 1), 0, kNoSrc, jobIdx << 4 | c);
+                    o.flags = 4u;
+                    j.pPos = o.pPos = (uint32_t)cursor[kCoarseDegree]++;
+                    j.pSlot = slotOf(kCoarseDegree, j.pPos);
+                    continue;
                 }
-                if (j.doP) j.pSlot = emit(n.degree + 1, cx, cy, cz, half, n.depth, n.degree, n.slot, jobIdx << 4 | 8u);   // Octree.cpp:846-851
+                o.flags = (j.doH ? 1u : 0u) | (j.doP ? 2u : 0u);
+                if (j.doH)                                                                       // Octree.cpp:820
+                {
+                    j.hPos = o.hPos = (uint32_t)cursor[n.degree];
+                    cursor[n.degree] += 8;
+                    j.hSlot0 = slotOf(n.degree, j.hPos);
+                }
+                if (j.doP)                                                                       // Octree.cpp:846-851
+                {
+                    j.pPos = o.pPos = (uint32_t)cursor[n.degree + 1]++;
+                    j.pSlot = slotOf(n.degree + 1, j.pPos);
+                }
             }
             poolUsed_ = poolNeed;
             double roundFlops = 0.0; uint64_t roundEvals = 0;
@@ -288,7 +329,9 @@ namespace hpsdf
             // ---- 2. upload, launch one kernel per degree present (this rank's shard), gather across ranks ----------
             if (nTasks)
             {
-                HPSDF_CUDA(cudaMemcpyAsync(dTasks_.p, hTasks_.p, nTasks * sizeof(FitTask), cudaMemcpyHostToDevice, stream_));
+                HPSDF_CUDA(cudaMemcpyAsync(dJobs_.p, hJobs_.p, evaluated_.size() * sizeof(JobDesc), cudaMemcpyHostToDevice, stream_));
+                HPSDF_CUDA(launchExpandJobs(dJobs_.p, (uint32_t)evaluated_.size(), lay, dTasks_.p, stream_));
+                t_.stats.kernel_launches++;
                 HPSDF_CUDA(cudaEventRecord(ev0_, stream_));
                 for (int d = 1; d <= kMaxDegree; ++d)
                 {
@@ -343,13 +386,14 @@ namespace hpsdf
             // ---- 3. errors (host, same expressions and libm as the CPU checker); the evaluated leaves enter the heap ------
             const double tRec0 = nowMs();
             const bool weighted = cfg_.nearness_type != HPSDF_NEARNESS_NONE;
-            for (size_t ti = 0; ti < nTasks; ++ti)
+            const FitRecord* R = hRecs_.p;
+            for (size_t k = 0; k < evaluated_.size() && nTasks; ++k)
             {
-                Job& j = jobs_[owner_[ti] >> 4];
-                const uint32_t which = owner_[ti] & 15u;
-                const FitRecord& r = hRecs_.p[ti];
-                const double e = weighted ? r.rawErr * nearnessWeight(cfg_, r.c0, hTasks_.p[ti].depth) : r.rawErr;
-                if (which == 8u) j.pErr = e; else j.hErr[which] = e;
+                Job& j = jobs_[firstJob + k];
+                const uint32_t depth = nodes_[evaluated_[k]].depth;
+                auto err = [&](const FitRecord& r, uint32_t dep) { return weighted ? r.rawErr * nearnessWeight(cfg_, r.c0, dep) : r.rawErr; };
+                if (j.coarse || j.doP) j.pErr = err(R[j.pPos], depth);
+                if (j.doH) for (uint32_t c = 0; c < 8; ++c) j.hErr[c] = err(R[j.hPos + c], depth + 1);
             }
             for (size_t k = firstJob; k < jobs_.size(); ++k)
                 if (jobs_[k].coarse) { jobs_[k].hImp = 0.0; jobs_[k].pImp = jobs_[k].pErr; }             // Octree.cpp:806-810, 836-843
@@ -377,7 +421,7 @@ namespace hpsdf
             applyLevel_ = inf;
             double remaining = checkValue();
             evalLevel_ = conceptualTop();
-            if (!(remaining >= thr) || (queue_.empty() && pending_.empty())) { t_.stats.host_select_ms += nowMs() - tSel0; return; }
+            if (!(remaining >= thr) || (queue_.empty() && pendCount_ == 0)) { t_.stats.host_select_ms += nowMs() - tSel0; return; }
             int b = kBuckets - 1, crossing = -1;
             for (; b >= 0; --b)
             {
@@ -391,7 +435,7 @@ namespace hpsdf
             {
                 std::vector<double> errs;
                 for (const auto& e : queue_.entries()) if (bucketOf(e.second) == crossing) errs.push_back(e.second);
-                for (uint64_t idx : pending_) if (bucketOf(errOf_[idx]) == crossing) errs.push_back(errOf_[idx]);
+                for (uint64_t idx : pendB_[crossing]) errs.push_back(errOf_[idx]);
                 std::sort(errs.begin(), errs.end(), std::greater<double>());
                 size_t k = 0;
                 for (; k < errs.size() && remaining >= thr; ++k) remaining -= errs[k] * (1.0 + 1e-9);
@@ -467,7 +511,7 @@ namespace hpsdf
                     const uint64_t c = nodes_[idx].child + i;                                        // Octree.cpp:275-290
                     total_ += j.hErr[i];
                     exactSum_ += (long double)j.hErr[i];
-                    nodes_[c].slot = j.hSlot[i];
+                    nodes_[c].slot = j.hSlot0 + i * (uint32_t)coeffCount((int)p);
                     nodes_[c].degree = (uint8_t)p;
                     errOf_[c] = j.hErr[i];
                     qPush(c, j.hErr[i]);
@@ -546,7 +590,7 @@ namespace hpsdf
             ready_.clear();
             for (;;)
             {
-                if (queue_.empty() && pending_.empty()) { done = true; break; }                          // nodeQueue.empty(), Octree.cpp:216
+                if (queue_.empty() && pendCount_ == 0) { done = true; break; }                          // nodeQueue.empty(), Octree.cpp:216
                 if (!queue_.empty() && queue_.top().second >= applyLevel_)
                 {
                     const std::pair<uint64_t, double> top = queue_.top();
@@ -554,9 +598,9 @@ namespace hpsdf
                     applyJob(top.first, top.second);
                     continue;
                 }
-                if (pendingMax_ >= applyLevel_ && !pending_.empty()) break;     // entries above the level still wait for their results
+                if (pendingMax_ >= applyLevel_ && pendCount_ != 0) break;     // entries above the level still wait for their results
                 if (checkValue() < thr) { done = true; break; }                                          // Octree.cpp:216
-                if (!queue_.empty() && (pending_.empty() || queue_.top().second >= pendingMax_))
+                if (!queue_.empty() && (pendCount_ == 0 || queue_.top().second >= pendingMax_))
                 {
                     const std::pair<uint64_t, double> top = queue_.top();                                // Octree.cpp:231: the overall maximum
                     hPop();
@@ -584,7 +628,7 @@ namespace hpsdf
         // other members of the group. Log the whole group: kind 2 = refined before the cut, kind 3 = left unrefined.
         void Builder::logCutTies()
         {
-            if (t_.applyLog.empty() || (queue_.empty() && pending_.empty())) return;
+            if (t_.applyLog.empty() || (queue_.empty() && pendCount_ == 0)) return;
             // the sequential loop's last pop is the smallest-error entry applied since the last sequential state
             double eLast = t_.applyLog.back().initial_err;
             for (size_t k = std::min(levelLogStart_, t_.applyLog.size() - 1); k < t_.applyLog.size(); ++k) eLast = std::min(eLast, t_.applyLog[k].initial_err);
@@ -677,13 +721,9 @@ namespace hpsdf
             errOf_.assign(nodes_.size(), kInitialErr);
             jobOf_.assign(nodes_.size(), -1);
             inQueue_.assign(nodes_.size(), 0);
-            {
-                std::vector<uint64_t> coarse;
-                coarse.swap(pending_);
-                for (uint64_t idx : coarse) qPush(idx, kInitialErr);                                    // Octree.cpp:176-177
-            }
+            for (uint64_t idx : coarseCells_) qPush(idx, kInitialErr);                                  // Octree.cpp:176-177
             total_ = std::pow(8, 4) * kInitialErr;                                                      // Octree.cpp:212
-            unfitted_ = (long)pending_.size();
+            unfitted_ = (long)pendCount_;
             lastTotal_ = totalBeforeLast_ = total_;
             computeLevel();
 
@@ -697,7 +737,7 @@ namespace hpsdf
                 const bool done = replay();
                 replayMs += nowMs() - r0;
                 if (done) break;
-                if (pending_.empty()) { setLastError("internal: replay stalled with nothing to evaluate"); st = HPSDF_ERR_CUDA; break; }
+                if (pendCount_ == 0) { setLastError("internal: replay stalled with nothing to evaluate"); st = HPSDF_ERR_CUDA; break; }
                 if (++stallGuard > 100000) { setLastError("internal: build does not converge"); st = HPSDF_ERR_CUDA; break; }
             }
             const double tPack0 = nowMs();

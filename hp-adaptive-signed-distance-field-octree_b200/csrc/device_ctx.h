@@ -61,6 +61,8 @@ namespace hpsdf
         DeviceBuf<double>    samples;     // F at the Gauss-Legendre points of a chunk of fits (mesh / octree programs only)
         DeviceBuf<unsigned long long> sampleCounter;   // work counter of meshSampleKernel
         PinnedBuf<FitTask>   hTasks;
+        DeviceBuf<JobDesc>   jobs;
+        PinnedBuf<JobDesc>   hJobs;
         PinnedBuf<FitRecord> hRecs;
         PinnedBuf<uint32_t>  hSegs;
         DeviceBuf<char>      cont;        // continuity: faces, COO, CSR, CG vectors, CUB temp
@@ -109,6 +111,7 @@ namespace hpsdf
     bool        jitCompileCheck(const SdfProgramDev& prog, int degree, std::string* source, size_t* cubinBytes, std::string& why);
     void        setJitDefault(bool on);
     bool        jitDefault();
+    cudaError_t launchExpandJobs(const JobDesc* dJobs, uint32_t nJobs, const RoundLayout& layout, FitTask* dTasks, cudaStream_t stream);
     cudaError_t launchSdfEval(const SdfProgramDev& prog, const double* dXyz, size_t n, double* dOut, cudaStream_t stream);
     cudaError_t launchDfmaPeak(double* dOut, int blocks, cudaStream_t stream);
     cudaError_t launchQuery(const DeviceTreeView& view, const double* dXyz, size_t n, double* dOut, int smCount, cudaStream_t stream);

@@ -124,6 +124,24 @@ namespace hpsdf
     };
     constexpr uint32_t kNoSrc = 0xFFFFFFFFu;
 
+    // One refinement job of a round as the host writes it (32 bytes instead of 9 FitTasks): expandJobsKernel turns it into
+    // the 8 child fits @degree at task positions hPos..hPos+7 of that degree's group and the p-fit @degree+1 at pPos.
+    struct JobDesc
+    {
+        float    cx, cy, cz, half;   // the parent cell
+        uint32_t hPos, pPos;         // task (= record) index of child 0 / of the p-fit
+        uint32_t src;                // pool slot of the parent's coefficients (kept shells of the p-fit)
+        uint8_t  depth, degree;      // of the parent
+        uint8_t  flags;              // 1 = child fits wanted, 2 = p-fit wanted, 4 = coarse cell (one from-scratch fit @kCoarseDegree at pPos)
+        uint8_t  pad;
+    };
+    // where each degree's tasks and output slots start in this round
+    struct RoundLayout
+    {
+        uint32_t groupBegin[kMaxDegree + 2];
+        uint32_t groupPool[kMaxDegree + 2];
+    };
+
     // What the host replay needs from a fit: the raw top-shell energy (Octree.cpp:1062-1069) and coeffs[0]
     // (the cell mean of the approximant up to NL[0][depth]^3, for the nearness weight).
     struct FitRecord

@@ -123,7 +123,8 @@ typedef struct hpsdf_build_opts
     uint32_t jit;                 /* closed-form programs: 0 = process default (hpsdf_set_jit / env HPSDF_JIT), 1 = compile the
                                      fit kernels for this program at run time (NVRTC, once per program and degree, ~0.3 s each,
                                      cached in memory), 2 = interpreted kernels. Mesh / octree programs are always interpreted. */
-    uint32_t _reserved;
+    uint32_t min_round_jobs;      /* a batched round evaluates at least this many refinement jobs when that many leaves are waiting
+                                     (the next-largest errors beyond the guaranteed level); 0 = 512 */
 } hpsdf_build_opts;
 
 HPSDF_API void hpsdf_build_opts_default(hpsdf_build_opts* opts);
