@@ -121,6 +121,7 @@ namespace hpsdf
             long        unfitted_ = 0;
             int         rank_ = 0, world_ = 1;
             double      sdfFlops_ = 0.0;
+            bool        progHasExt_ = false;       // the program samples a mesh or another octree
             hpsdf_decision_log_entry lastApplied_{};      // last job applied before the termination cut
             double      lastTotal_ = 0.0, totalBeforeLast_ = 0.0;
 
@@ -222,7 +223,8 @@ namespace hpsdf
             // upload / launch / synchronise / replay cycle for them (10 of the 18 rounds of a C2 build selected fewer than 20
             // jobs), so the round is topped up to `min_round_jobs` with the next-largest pending errors: the greedy loop is
             // about to reach them anyway and their results stay cached until it does.
-            const size_t minJobs = o_.min_round_jobs ? o_.min_round_jobs : 512u;
+            // (not for mesh / octree programs by default: there a fit costs 10^3-10^4 BVH queries and speculation measured 25-35 % slower)
+            const size_t minJobs = o_.min_round_jobs ? o_.min_round_jobs : (progHasExt_ ? 1u : 512u);
             const size_t pendBefore = pendCount_;
             auto select = [&](uint64_t idx)
             {
@@ -705,7 +707,11 @@ namespace hpsdf
             ev0_ = ws_.ev0; ev1_ = ws_.ev1;
             if (o_.comm) { rank_ = commRank(o_.comm); world_ = commWorld(o_.comm); }
             sdfFlops_ = 6.0;
-            for (uint32_t i = 0; i < prog_.n; ++i) sdfFlops_ += sdfOpFlops(prog_.instr[i].op);
+            for (uint32_t i = 0; i < prog_.n; ++i)
+            {
+                sdfFlops_ += sdfOpFlops(prog_.instr[i].op);
+                progHasExt_ |= prog_.instr[i].op == HPSDF_PRIM_MESH || prog_.instr[i].op == HPSDF_PRIM_OCTREE;
+            }
             t_.stats.sdf_flops_per_eval = sdfFlops_;
 
             hpsdf_status st = HPSDF_OK;

@@ -124,7 +124,8 @@ typedef struct hpsdf_build_opts
                                      fit kernels for this program at run time (NVRTC, once per program and degree, ~0.3 s each,
                                      cached in memory), 2 = interpreted kernels. Mesh / octree programs are always interpreted. */
     uint32_t min_round_jobs;      /* a batched round evaluates at least this many refinement jobs when that many leaves are waiting
-                                     (the next-largest errors beyond the guaranteed level); 0 = 512 */
+                                     (the next-largest errors beyond the guaranteed level); 0 = 512 for closed-form programs,
+                                     1 for mesh / octree programs, whose fits are too expensive to speculate on */
 } hpsdf_build_opts;
 
 HPSDF_API void hpsdf_build_opts_default(hpsdf_build_opts* opts);

@@ -11,6 +11,7 @@ thr = float(sys.argv[3])
 cont = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 nq = int(float(sys.argv[5])) if len(sys.argv) > 5 else 0
 maxdeg = int(sys.argv[6]) if len(sys.argv) > 6 else 11
+minjobs = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 verts, tris = bumpy_torus(U, V)
 t0 = time.perf_counter()
 mesh = hp.Mesh(verts, tris)
@@ -24,7 +25,7 @@ keys = ["rounds", "fits_evaluated", "sdf_evals", "total_ms", "fit_kernel_ms", "d
 for i in range(2):
     t = hp.Octree()
     t0 = time.perf_counter()
-    t.Create(cfg, prog, hp.BuildOpts(max_degree=maxdeg))
+    t.Create(cfg, prog, hp.BuildOpts(max_degree=maxdeg, min_round_jobs=minjobs))
     wall = 1e3 * (time.perf_counter() - t0)
     s = t.stats()
     print("run", i, "wall %.1f ms" % wall, {k: (round(s[k], 3) if isinstance(s[k], float) else s[k]) for k in keys}, flush=True)
