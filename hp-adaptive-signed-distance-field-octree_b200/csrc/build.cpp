@@ -226,23 +226,7 @@ namespace hpsdf
             // (not for mesh / octree programs by default: there a fit costs 10^3-10^4 BVH queries and speculation measured 25-35 % slower)
             const size_t minJobs = o_.min_round_jobs ? o_.min_round_jobs : (progHasExt_ ? 1u : 512u);
             const size_t pendBefore = pendCount_;
-            auto select = [&](uint64_t idx)
-            {
-                const HostNode& n = nodes_[idx];
-                jobs_.emplace_back();
-                Job& j = jobs_.back();
-                j.coarse = std::abs(errOf_[idx] - kInitialErr) < std::numeric_limits<double>::epsilon() && n.degree == 0;   // Octree.cpp:806, 831
-                if (j.coarse) { j.doP = true; cnt[kCoarseDegree]++; }
-                else
-                {
-                    j.doH = n.depth < o_.max_depth;             // child fits at depth > TREE_MAX_DEPTH are never used (Octree.cpp:600-601)
-                    j.doP = n.degree < o_.max_degree;           // nor is the p-fit of a max-degree node
-                    if (j.doH) cnt[n.degree] += 8;
-                    if (j.doP) cnt[n.degree + 1]++;
-                }
-                jobOf_[idx] = (int32_t)(jobs_.size() - 1);
-                evaluated_.push_back(idx);
-            };
+            auto select = [&](uint64_t idx) { evaluated_.push_back(idx); };
             const int levelBucket = bucketOf(level);
             pendingMax_ = 0.0;
             for (int b = pendTop_; b >= 0 && pendCount_ > 0; --b)
@@ -263,6 +247,34 @@ namespace hpsdf
             }
             while (pendTop_ > 0 && pendB_[pendTop_].empty()) --pendTop_;
             if (pendCount_) for (uint64_t idx : pendB_[pendTop_]) pendingMax_ = std::max(pendingMax_, errOf_[idx]);
+            // Several GPUs evaluate contiguous shards of each degree group. Selection order is spatially coherent (far and near
+            // cells of a mesh cluster, and their fits differ 10x in cost), so the jobs of a round are dealt out by a fixed
+            // stride permutation first: every shard gets the same mix. (Only node numbering depends on the order.)
+            if (world_ > 1 && evaluated_.size() > 2)
+            {
+                const size_t n = evaluated_.size();
+                size_t stride = 7919;
+                for (const size_t cand : { (size_t)7919, (size_t)7907, (size_t)7901, (size_t)7883 }) if (n % cand != 0) { stride = cand; break; }
+                std::vector<uint64_t> perm(n);
+                for (size_t k = 0; k < n; ++k) perm[k] = evaluated_[(k * stride) % n];
+                evaluated_.swap(perm);
+            }
+            for (const uint64_t idx : evaluated_)
+            {
+                const HostNode& n = nodes_[idx];
+                jobs_.emplace_back();
+                Job& j = jobs_.back();
+                j.coarse = std::abs(errOf_[idx] - kInitialErr) < std::numeric_limits<double>::epsilon() && n.degree == 0;   // Octree.cpp:806, 831
+                if (j.coarse) { j.doP = true; cnt[kCoarseDegree]++; }
+                else
+                {
+                    j.doH = n.depth < o_.max_depth;             // child fits at depth > TREE_MAX_DEPTH are never used (Octree.cpp:600-601)
+                    j.doP = n.degree < o_.max_degree;           // nor is the p-fit of a max-degree node
+                    if (j.doH) cnt[n.degree] += 8;
+                    if (j.doP) cnt[n.degree + 1]++;
+                }
+                jobOf_[idx] = (int32_t)(jobs_.size() - 1);
+            }
             static const bool dbgRounds = getenv("HPSDF_DEBUG_ROUNDS") != nullptr;
             if (dbgRounds) fprintf(stderr, "round %llu: pending %zu -> %zu, jobs %zu, heap %zu, level %.3e, passA %.3f ms\n", (unsigned long long)t_.stats.rounds,
                                    pendBefore, pendCount_, evaluated_.size(), queue_.entries().size(), level, nowMs() - tTask0);
@@ -549,6 +561,8 @@ namespace hpsdf
             levelTried_ = false;
             if (!coarseReady_.empty())
             {
+                // visiting order of UniformlyRefine = ascending node index (pre-order allocation); a multi-GPU round deals its jobs out
+                std::sort(coarseReady_.begin(), coarseReady_.end());
                 // Coarse stage (Octree.cpp:112-191, 228-238): all 16^3 cells sit in the reference's queue with err = 100; each is
                 // popped, fitted and pushed back with its real error. The ORDER in which the equal keys pop is a property of
                 // the heap algorithm and of the re-pushed entries, and it matters: totalCoeffError starts at 8^4 * 100, so

@@ -75,7 +75,7 @@ namespace hpsdf
                 if (prog.n == 1 && prog.instr[0].op == HPSDF_PRIM_MESH)
                 {
                     // the whole program is one mesh: the warp-scheduled traversal kernel (mesh_sample_kernel.cuh)
-                    const unsigned grab = total >= ((unsigned long long)1 << 20) ? 128u : 32u;
+                    const unsigned grab = 32u;      // one query per lane per grab: a larger grab leaves a tail of sequential ~1 ms queries at the end of the launch
                     const unsigned long long want = (total + 8ull * grab - 1) / (8ull * grab);
                     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
                     if (e != cudaSuccess) return e;
