@@ -192,6 +192,27 @@ def test_build_option_switches_match_oracle(hp, oracle):
         assert max(rel_inf(ca[i], cb[mb[k]]) for k, i in ma.items() if k in mb and k not in div) <= COEFF_TOL
 
 
+@pytest.mark.parametrize("name", ["csg_small", "sphere_poly_1e8"])
+def test_scheduling_knobs_do_not_change_the_tree(hp, built, name):
+    """Round size (min_round_jobs), speculation and strict ordering only change WHEN a job is evaluated and node numbering:
+    canonical topology and coefficients are those of the default schedule (outside the logged tie group at the cut)."""
+    base = built(name)
+    a = hp.parse_block(base.ToMemoryBlockBytes())
+    pa, da, ga, ca = leaf_table(a, hp.COEFF_COUNT)
+    ma = {(path_code(p), int(d)): i for i, (p, d) in enumerate(zip(pa, da))}
+    for kw in (dict(min_round_jobs=1), dict(min_round_jobs=4096), dict(speculate=1), dict(strict_order=1, min_round_jobs=64), dict(jit=1, min_round_jobs=7)):
+        t = built(name, **kw)
+        b = hp.parse_block(t.ToMemoryBlockBytes())
+        assert a["n_nodes"] == b["n_nodes"] and a["n_coeffs"] == b["n_coeffs"], kw
+        pb, db, gb, cb = leaf_table(b, hp.COEFF_COUNT)
+        mb = {(path_code(p), int(d)): i for i, (p, d) in enumerate(zip(pb, db))}
+        div = divergent_cells({k: int(ga[i]) for k, i in ma.items()}, {k: int(gb[i]) for k, i in mb.items()})
+        allowed = logged_cut_group(t)[0] | logged_cut_group(base)[0]
+        assert all(cell_of(c, d) in allowed for c, d in div), kw
+        assert max(rel_inf(ca[i], cb[mb[k]]) for k, i in ma.items() if k in mb and k not in div) <= 1e-12, kw
+        assert t.stats()["jobs_applied_p"] == base.stats()["jobs_applied_p"] and t.stats()["jobs_applied_h"] == base.stats()["jobs_applied_h"], kw
+
+
 def test_memory_block_is_accepted_by_the_cpu_side_and_back(hp, oracle, built):
     """ToMemoryBlock is byte-compatible: the oracle's (and, where built, the reference's own) FromMemoryBlock + Query
     accepts GPU-built trees; FromMemoryBlock accepts CPU-built trees."""
