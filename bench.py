@@ -331,10 +331,11 @@ def main():
         t0 = time.perf_counter()
         t2 = hp.Octree()
         t2.Create(cfg, prog, opts)
-        blk = t2.ToMemoryBlockBytes()                      # device -> host copy of the whole tree
+        blk = t2.ToMemoryBlock()                           # device -> host copy of the whole tree (malloc-owned MemoryBlock)
         torch.cuda.synchronize()
         e2e_times.append(time.perf_counter() - t0)
-        blk_bytes = len(blk)
+        blk_bytes = blk.size
+        blk.free()
         t2.Clear()
     e2e_ms = 1e3 * float(np.mean(e2e_times[1:]))
     te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")

@@ -341,6 +341,11 @@ namespace hpsdf
             t_.stats.host_tasks_ms += nowMs() - tTask0;
 
             // ---- 2. upload, launch one kernel per degree present (this rank's shard), gather across ranks ----------
+            // Sharding a round costs one grouped broadcast per (degree group, rank) and its latency. It pays when fits are
+            // expensive (mesh / octree programs: 10^3-10^4 BVH queries each) or the round is large; a small round of closed-form
+            // fits (tens of microseconds of kernel time) is cheaper to evaluate redundantly on every rank — identical
+            // kernels on identical hardware give identical bits, so the replicas stay in lock-step without an exchange.
+            const bool shard = world_ > 1 && (progHasExt_ || nTasks >= (size_t)1 << 18);
             if (nTasks)
             {
                 HPSDF_CUDA(cudaMemcpyAsync(dJobs_.p, hJobs_.p, evaluated_.size() * sizeof(JobDesc), cudaMemcpyHostToDevice, stream_));
@@ -352,7 +357,7 @@ namespace hpsdf
                     const size_t n = cnt[d];
                     if (!n) continue;
                     size_t b = 0, e = n;
-                    if (world_ > 1) hpsdf_shard_range(n, rank_, world_, &b, &e);
+                    if (shard) hpsdf_shard_range(n, rank_, world_, &b, &e);
                     if (e > b)
                     {
                         const hpsdf_status ls = launchFit(o_.jit, d, dTasks_.p + groupBegin[d] + b, (int)(e - b), pool_.p, dRecs_.p, prog_, t_.map, *t_.ctx, stream_);
@@ -364,7 +369,7 @@ namespace hpsdf
                     roundEvals += (uint64_t)n * fitRule(d) * fitRule(d) * fitRule(d);
                 }
                 HPSDF_CUDA(cudaEventRecord(ev1_, stream_));
-                if (world_ > 1)
+                if (shard)
                 {
                     // every rank receives every other rank's shard: coefficients and records (replicated pool, identical replay)
                     std::vector<CommSegment> segs;

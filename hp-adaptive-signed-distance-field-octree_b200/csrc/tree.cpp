@@ -170,8 +170,7 @@ namespace hpsdf
         const size_t bytes = 8 + 8 * nC + 8 + 56 * nN + 80;
         uint8_t* p = (uint8_t*)malloc(bytes);                     // malloc-owned, the caller free()s it (Octree.cpp:445)
         if (!p) { setLastError("malloc failed"); return HPSDF_ERR_OOM; }
-        memset(p, 0, bytes);
-        const uint64_t nc = nC, nn = nN;
+        const uint64_t nc = nC, nn = nN;                           // (every byte is written below: no memset of the 8 nC payload)
         memcpy(p, &nc, 8);
         if (nC)
         {
@@ -185,7 +184,8 @@ namespace hpsdf
         {
             const HostNode& n = t.nodes[i];
             memcpy(q, &n.child, 8); memcpy(q + 8, n.mn, 12); memcpy(q + 20, n.mx, 12);
-            memcpy(q + 32, &n.cstart, 8); q[40] = n.degree; q[48] = n.depth;
+            const uint64_t deg = n.degree, dep = n.depth;            // u8 + 7 bytes of zero padding each (LP64 layout of SDF::Node)
+            memcpy(q + 32, &n.cstart, 8); memcpy(q + 40, &deg, 8); memcpy(q + 48, &dep, 8);
         }
         memcpy(q, &t.cfg, 80);
         *size = bytes; *ptr = p;
