@@ -386,6 +386,9 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "nodes_fitted_per_step": fits, "fits_evaluated_per_step": stats["fits_evaluated"],
                    "rounds_per_step": stats["rounds"], "n_nodes": stats["n_nodes"], "n_coeffs": stats["n_coeffs"],
+                   "multi_gpu": "one tree built by all ranks: mesh / octree programs and rounds of >= 2^18 fits are sharded (grouped NCCL broadcasts "
+                                "per round); small closed-form rounds are evaluated redundantly on every rank (an exchange costs more than the "
+                                "kernels), so this 4 ms host-bound build does not speed up with N — mesh_build and query are the paths that scale",
                    "jit": "fit kernels specialised to the SDF program at run time (NVRTC, compiled during warm-up)",
                    "l2": "build inputs are a 480-byte program; query inputs (%d MB) are larger than L2" % (n_q * 32 >> 20),
                    "timing": "CUDA events on the build stream around each Create (max over ranks)"},
