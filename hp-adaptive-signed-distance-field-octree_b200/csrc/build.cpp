@@ -352,7 +352,16 @@ namespace hpsdf
                 HPSDF_CUDA(launchExpandJobs(dJobs_.p, (uint32_t)evaluated_.size(), lay, dTasks_.p, stream_));
                 t_.stats.kernel_launches++;
                 HPSDF_CUDA(cudaEventRecord(ev0_, stream_));
-                for (int d = 1; d <= kMaxDegree; ++d)
+                // The launches of a round (one per degree present) are independent and individually too small to fill 148 SMs:
+                // closed-form programs fan them out over four auxiliary streams and join again (mesh / octree programs share
+                // one sample scratch buffer and stay on the build stream).
+                int groups = 0;
+                for (int d = 1; d <= kMaxDegree; ++d) groups += cnt[d] != 0;
+                const bool fan = !progHasExt_ && groups > 1;
+                if (fan) HPSDF_CUDA(cudaEventRecord(ws_.evFork, stream_));
+                int g = 0;
+                bool used[4] = { false, false, false, false };
+                for (int d = kMaxDegree; d >= 1; --d)                 // highest degree first: the longest kernels start earliest
                 {
                     const size_t n = cnt[d];
                     if (!n) continue;
@@ -360,7 +369,14 @@ namespace hpsdf
                     if (shard) hpsdf_shard_range(n, rank_, world_, &b, &e);
                     if (e > b)
                     {
-                        const hpsdf_status ls = launchFit(o_.jit, d, dTasks_.p + groupBegin[d] + b, (int)(e - b), pool_.p, dRecs_.p, prog_, t_.map, *t_.ctx, stream_);
+                        cudaStream_t s = stream_;
+                        if (fan)
+                        {
+                            s = ws_.aux[g & 3];
+                            if (!used[g & 3]) { HPSDF_CUDA(cudaStreamWaitEvent(s, ws_.evFork, 0)); used[g & 3] = true; }
+                            ++g;
+                        }
+                        const hpsdf_status ls = launchFit(o_.jit, d, dTasks_.p + groupBegin[d] + b, (int)(e - b), pool_.p, dRecs_.p, prog_, t_.map, *t_.ctx, s);
                         if (ls != HPSDF_OK) return ls;
                         t_.stats.kernel_launches++;
                     }
@@ -368,6 +384,13 @@ namespace hpsdf
                     roundFlops += (double)n * (fitFlops(d) + sdfFlops_ * fitRule(d) * fitRule(d) * fitRule(d));
                     roundEvals += (uint64_t)n * fitRule(d) * fitRule(d) * fitRule(d);
                 }
+                if (fan)
+                    for (int i = 0; i < 4; ++i)
+                        if (used[i])
+                        {
+                            HPSDF_CUDA(cudaEventRecord(ws_.evJoin[i], ws_.aux[i]));
+                            HPSDF_CUDA(cudaStreamWaitEvent(stream_, ws_.evJoin[i], 0));
+                        }
                 HPSDF_CUDA(cudaEventRecord(ev1_, stream_));
                 if (shard)
                 {

@@ -147,6 +147,12 @@ namespace hpsdf
         cudaStreamCreateWithFlags(&ctx->ws.stream, cudaStreamNonBlocking);
         cudaEventCreate(&ctx->ws.ev0);
         cudaEventCreate(&ctx->ws.ev1);
+        cudaEventCreateWithFlags(&ctx->ws.evFork, cudaEventDisableTiming);
+        for (int i = 0; i < 4; ++i)
+        {
+            cudaStreamCreateWithFlags(&ctx->ws.aux[i], cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&ctx->ws.evJoin[i], cudaEventDisableTiming);
+        }
         // a first pool of 32 M doubles (256 MB) and pinned staging for 128 K fits: a README-sized build never reallocates
         ctx->ws.pool.reserve((size_t)32 << 20);
         ctx->ws.tasks.reserve((size_t)1 << 17); ctx->ws.recs.reserve((size_t)1 << 17);
