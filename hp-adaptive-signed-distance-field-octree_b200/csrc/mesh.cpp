@@ -222,7 +222,7 @@ extern "C"
     {
         if (!out) { setLastError("out is null"); return HPSDF_ERR_INVALID_ARG; }
         *out = nullptr;
-        if (!vertices || !tri_indices || n_vertices == 0 || n_tris == 0 || n_tris >= 0x2AAAAAAAull)
+        if (!vertices || !tri_indices || n_vertices == 0 || n_tris == 0 || n_tris >= 0x20000000ull)      // leaf slots are packed into 29 bits (mesh_sample_kernel.cuh)
         { setLastError("mesh arrays are null, empty or too large"); return HPSDF_ERR_INVALID_ARG; }
         std::string err;
         DeviceCtx* ctx = getDeviceCtx(device, err);

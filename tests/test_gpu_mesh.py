@@ -94,3 +94,29 @@ def test_octree_of_a_mesh_matches_the_oracle(hp, oracle, torus):
     st = tree.stats()
     print("mesh octree: nodes", st["n_nodes"], "coeffs", st["n_coeffs"], "fits", st["fits_evaluated"], "sdf evals", st["sdf_evals"],
           "ms", st["total_ms"], "fit ms", st["fit_kernel_ms"], "worst", worst)
+
+
+@pytest.mark.parametrize("degree", [2, 4, 7])
+def test_mixed_mesh_and_closed_form_program_fits_match_the_oracle(hp, oracle, torus, degree):
+    """A mesh combined with closed-form primitives goes through the generic sample kernel (interpreter + per-thread BVH
+    traversal) instead of meshSampleKernel: min(mesh, sphere) minus a box, fitted on cells near all three surfaces."""
+    from oracle import hpref
+    v, t, m = torus
+    om = oracle.OracleMesh(v, t)
+    lo, hi = mesh_root(v)
+    items = [("sphere", [0.1, 0.05, 0.0, 0.3]), ("union", []), ("box", [0.3, 0.0, 0.0, 0.1, 0.2, 0.05]), ("subtract", [])]
+    prog = hp.SdfProgram([("mesh", [], m)] + items)
+    oprog = hpref.make_program([("mesh", [], om.h)] + items)
+    cfg = hp.Config(target_error_threshold=1e-6, continuity_enforce=0, root_min=lo, root_max=hi)
+    ocfg = hpref.make_config(threshold=1e-6, continuity=False, root_min=lo, root_max=hi, threads=1)
+    rng = np.random.default_rng(40 + degree)
+    depth = 4
+    half = 0.5 ** (depth + 1)
+    n = 5 if degree < 7 else 2
+    centres = (rng.integers(3, 13, (n, 3)) + 0.5) * 2 * half - 0.5
+    cells = np.concatenate([centres, np.full((n, 1), half)], 1).astype(np.float32)
+    coeffs, err, _ = hp.fit_batch(cfg, prog, cells, np.full(n, depth), degree)
+    for i in range(n):
+        c, e = oracle.oracle_fit(ocfg, oprog, centres[i] - half, centres[i] + half, degree, depth)
+        assert rel_inf(coeffs[i], c) <= 1e-10
+        assert abs(err[i] - e) <= 1e-9 * e + (1e-12 * np.abs(c).max()) ** 2
