@@ -38,6 +38,7 @@ WORKLOAD = "c2_csg"
 METRIC = "octree_build_nodes_fitted_per_s"
 QUERY_POINTS = 1 << 24            # 16.7 M points = 512 MB in + 128 MB out: larger than the 126 MB L2
 MESH_UV = (1000, 435)             # bumpy torus with 870 000 triangles: the stand-in of configs[2]'s dragon.obj (absent from the reference tree)
+MESH_C4_UV = (1000, 800)          # 1.6 M triangles: the stand-in of configs[3]'s Ramesses.obj
 
 
 def peaks():
@@ -98,40 +99,79 @@ def product_case(hp, name):
 
 
 def mesh_bench(hp, torch, local, stream, comm, barrier, world, rank, with_cpu):
-    """configs[2] at scale (mesh SDF through the device BVH, threshold 1e-6, continuity strength 8): Create ms, mesh SDF
-    samples/s inside it, and — rank 0, N=1 — the reference's Mesh::SignedDistanceAtPt on a bounded sample of the same
-    points distribution on all host cores."""
+    """The mesh configs at scale, on procedural stand-ins of the missing dragon.obj / Ramesses.obj:
+    C3 = 870 k triangles, threshold 1e-6, continuity strength 8; C4 = 1.6 M triangles, threshold 1e-8, max degree 6, frontier
+    sharded over the ranks; C5 = batched Query of 1e9 uniform points on the C3 octree (replicated tree, points sharded).
+    Rank 0 at N=1 also times the reference's Mesh::SignedDistanceAtPt on a bounded sample on all host cores."""
     from meshgen import bumpy_torus, mesh_root
-    verts, tris = bumpy_torus(*MESH_UV)
-    t0 = time.perf_counter()
-    mesh = hp.Mesh(verts, tris, device=local)
-    create_s = time.perf_counter() - t0
-    mn, mx = mesh_root(verts)
-    cfg = hp.Config(target_error_threshold=1e-6, nearness_type=0, nearness_strength=0.0, continuity_enforce=1, continuity_strength=8.0,
-                    thread_count=os.cpu_count() or 1, root_min=mn, root_max=mx)
-    prog = hp.SdfProgram([("mesh", [], mesh)])
-    opts = hp.BuildOpts(device=local, stream=stream)
-    if comm is not None:
-        opts.comm = comm._h
-    tree = hp.Octree()
-    tree.Create(cfg, prog, opts)                       # warm-up (sample scratch allocation)
-    barrier()
-    reps, t0 = 3, time.perf_counter()
-    for _ in range(reps):
-        tree.Create(cfg, prog, opts)
-    barrier()
-    ms = 1e3 * (time.perf_counter() - t0) / reps
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.cpu()[0])
-    st = tree.stats()
-    out = {"workload": "bumpy-torus mesh, %d triangles, threshold 1e-6, continuity 8 (configs[2] stand-in)" % len(tris),
-           "create_ms": ms, "fits_per_s": useful_fits(st) / (ms * 1e-3), "fits_evaluated": st["fits_evaluated"],
-           "mesh_sdf_evals": st["sdf_evals"], "mesh_sdf_evals_per_s": st["sdf_evals"] / (st["fit_kernel_ms"] * 1e-3) * 1.0,
-           "fit_and_sample_kernel_ms": st["fit_kernel_ms"], "continuity_ms": st["continuity_ms"], "n_nodes": st["n_nodes"],
-           "mesh_upload_and_bvh_s": create_s, "scaling": "strong"}
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.cpu()[0])
+
+    def build(uv, thr, cont, max_degree, reps):
+        verts, tris = bumpy_torus(*uv)
+        t0 = time.perf_counter()
+        mesh = hp.Mesh(verts, tris, device=local)
+        create_s = time.perf_counter() - t0
+        mn, mx = mesh_root(verts)
+        cfg = hp.Config(target_error_threshold=thr, nearness_type=0, nearness_strength=0.0, continuity_enforce=cont,
+                        continuity_strength=8.0, thread_count=os.cpu_count() or 1, root_min=mn, root_max=mx)
+        prog = hp.SdfProgram([("mesh", [], mesh)])
+        opts = hp.BuildOpts(device=local, stream=stream, max_degree=max_degree)
+        if comm is not None:
+            opts.comm = comm._h
+        tree = hp.Octree()
+        tree.Create(cfg, prog, opts)                       # warm-up (sample scratch allocation)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            tree.Create(cfg, prog, opts)
+        barrier()
+        ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / reps)
+        st = tree.stats()
+        out = {"triangles": int(len(tris)), "threshold": thr, "continuity": bool(cont), "max_degree": max_degree,
+               "create_ms": ms, "fits_per_s": useful_fits(st) / (ms * 1e-3), "fits_evaluated": st["fits_evaluated"],
+               "mesh_sdf_evals": st["sdf_evals"], "mesh_sdf_evals_per_s_per_gpu_kernel_time": st["sdf_evals"] / world / (st["fit_kernel_ms"] * 1e-3),
+               "mesh_sdf_evals_per_s": st["sdf_evals"] / (ms * 1e-3),
+               "fit_and_sample_kernel_ms": st["fit_kernel_ms"], "continuity_ms": st["continuity_ms"], "rounds": st["rounds"],
+               "n_nodes": st["n_nodes"], "n_coeffs": st["n_coeffs"], "mesh_upload_and_bvh_s": create_s, "scaling": "strong"}
+        return out, tree, mesh, verts, tris, (mn, mx)
+
+    c3, tree3, mesh3, verts3, tris3, (mn, mx) = build(MESH_UV, 1e-6, 1, 11, 3)
+    res = {"c3_dragon_standin": c3}
+
+    # ---- C5: 1e9 points on the C3 tree, generated on the device (Philox) in chunks of 2^26, sharded over the ranks ------
+    total, chunk = 1_000_000_000, 1 << 26
+    mine = total // world + (1 if rank < total % world else 0)
+    gen = torch.Generator(device="cuda").manual_seed(0x5DF0C7EE + rank)
+    lo = torch.tensor(mn, device="cuda", dtype=torch.float64)
+    ext = torch.tensor([mx[i] - mn[i] for i in range(3)], device="cuda", dtype=torch.float64)
+    out = torch.empty(chunk, device="cuda", dtype=torch.float64)
+    q_ms, done, checksum = 0.0, 0, 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    while done < mine:
+        m = min(chunk, mine - done)
+        pts = (torch.rand((m, 3), generator=gen, device="cuda", dtype=torch.float64) * ext + lo).contiguous()    # untimed
+        e0.record()
+        tree3.QueryDevice(pts.data_ptr(), m, out.data_ptr(), stream)
+        e1.record()
+        torch.cuda.synchronize()
+        q_ms += e0.elapsed_time(e1)
+        checksum += float(out[:m].sum())
+        done += m
+        del pts
+    q_ms = max_over_ranks(q_ms)
+    res["c5_query_1e9"] = {"points": total, "ms": q_ms, "points_per_s": total / (q_ms * 1e-3), "scaling": "strong",
+                           "tree": "C3 octree replicated on every rank, points sharded contiguously, generated on the device",
+                           "hbm_GBps": total / world * 32 / (q_ms * 1e-3) / 1e9, "checksum_rank0": checksum}
+    cpu = None
     if with_cpu and rank == 0:
         try:
             from oracle import hpref, hporacle
@@ -139,30 +179,33 @@ def mesh_bench(hp, torch, local, stream, comm, barrier, world, rank, with_cpu):
             pts = np.random.default_rng(5).uniform(mn, mx, (20000, 3)).astype(np.float32)
             if hpref.available(fast=True):
                 t0 = time.perf_counter()
-                rm = hpref.RefMesh.create(verts, tris, True, fast=True)
+                rm = hpref.RefMesh.create(verts3, tris3, True, fast=True)
                 ref_create = time.perf_counter() - t0
-                t0 = time.perf_counter()
-                d = rm.sdf(pts, True, threads)
                 kind = "reference"
             else:
                 t0 = time.perf_counter()
-                rm = hporacle.OracleMesh(verts, tris)
+                rm = hporacle.OracleMesh(verts3, tris3)
                 ref_create = time.perf_counter() - t0
-                t0 = time.perf_counter()
-                d = rm.sdf(pts, True, threads)
                 kind = "port"
+            t0 = time.perf_counter()
+            d = rm.sdf(pts, True, threads)
             dt = time.perf_counter() - t0
             # identity is checked against the strict (-ffp-contract=off) restatement, which tests/ pin to the reference built the
             # same way; the -O3 -march=x86-64-v3 reference build timed above contracts FMAs and is 1 ulp off ITSELF in ~9 % of points
-            ours = mesh.SignedDistanceAtPt(pts)
-            strict = hporacle.OracleMesh(verts, tris).sdf(pts, True, threads)
-            out["cpu_baseline"] = {"mesh_sdf_evals_per_s": len(pts) / dt, "cores": threads, "kind": kind,
-                                   "sample": "Mesh::SignedDistanceAtPt (BVH) at 20 000 uniform points of the root box",
-                                   "mesh_setup_s": ref_create, "gpu_bit_identical_to_strict_checker": bool(np.array_equal(ours, strict)),
-                                   "fma_build_points_differing_from_strict": int((d != strict).sum())}
+            ours = mesh3.SignedDistanceAtPt(pts)
+            strict = hporacle.OracleMesh(verts3, tris3).sdf(pts, True, threads)
+            cpu = {"mesh_sdf_evals_per_s": len(pts) / dt, "cores": threads, "kind": kind,
+                   "sample": "Mesh::SignedDistanceAtPt (BVH) at 20 000 uniform points of the C3 root box",
+                   "mesh_setup_s": ref_create, "gpu_bit_identical_to_strict_checker": bool(np.array_equal(ours, strict)),
+                   "fma_build_points_differing_from_strict": int((d != strict).sum())}
         except Exception as e:      # the checker is optional here: report, do not fail the bench line
-            out["cpu_baseline"] = {"unavailable": repr(e)}
-    return out
+            cpu = {"unavailable": repr(e)}
+    if cpu is not None:
+        res["cpu_baseline"] = cpu
+    del tree3, mesh3
+    c4, tree4, mesh4, _, _, _ = build(MESH_C4_UV, 1e-8, 0, 6, 1)
+    res["c4_ramesses_standin"] = c4
+    return res
 
 
 def useful_fits(stats):
@@ -239,7 +282,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-mesh", action="store_true", help="skip the mesh-SDF build sub-benchmark (configs[2] stand-in)")
+    ap.add_argument("--no-mesh", action="store_true", help="skip the mesh sub-benchmarks (configs[2..4] stand-ins)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":
