@@ -12,8 +12,11 @@
 // Device side: mesh_eval.cuh.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
-#include <map>
+#include <thread>
+#include <unordered_map>
 #include <numeric>
 #include <vector>
 #include "octree.h"
@@ -93,6 +96,21 @@ namespace hpsdf
 
         struct BuildNode { float mn[3], mx[3]; uint32_t a, b, begin, end; };
 
+        // static partition of [0, n) over the host cores (mesh set-up is per-triangle / per-node independent work)
+        template <typename F>
+        void parallelFor(size_t n, F&& body)
+        {
+            const size_t nt = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+            if (nt <= 1 || n < 4096) { body((size_t)0, n); return; }
+            std::vector<std::thread> th;
+            for (size_t t = 0; t < nt; ++t)
+            {
+                const size_t b = n * t / nt, e = n * (t + 1) / nt;
+                th.emplace_back([&body, b, e] { body(b, e); });
+            }
+            for (std::thread& x : th) x.join();
+        }
+
         void triBounds(const std::vector<V3>& v, const std::vector<uint32_t>& tri, uint32_t t, float mn[3], float mx[3])
         {
             for (int k = 0; k < 3; ++k)
@@ -155,7 +173,8 @@ namespace hpsdf
             for (int d = 0; d < 3; ++d) maxAbs = std::max(maxAbs, std::max(std::fabs((double)nodes[0].mn[d]), std::fabs((double)nodes[0].mx[d])));
             // float32 projection error on the device is ~1e-7 |p|; query points live in a root box of about the mesh's size
             const double inflate = 1e-5 * std::max(std::sqrt(diag2), maxAbs);
-            for (size_t i = 0; i < nodes.size(); ++i)
+            parallelFor(nodes.size(), [&](size_t i0, size_t i1) {
+            for (size_t i = i0; i < i1; ++i)
             {
                 float* o = &obb[16 * i];
                 o[3] = o[7] = o[11] = 3.402823466e+38f;
@@ -209,6 +228,7 @@ namespace hpsdf
                 o[8] = fw[0]; o[9] = fw[1]; o[10] = fw[2];
                 o[12] = fn[0]; o[13] = fn[1]; o[14] = fn[2];
             }
+            });
         }
     }
 }
@@ -228,6 +248,9 @@ extern "C"
         DeviceCtx* ctx = getDeviceCtx(device, err);
         if (!ctx) { setLastError(err); return HPSDF_ERR_NO_DEVICE; }
 
+        const bool dbg = getenv("HPSDF_DEBUG_MESH") != nullptr;
+        double tS = nowMs();
+        auto stage = [&](const char* what) { if (dbg) { const double t = nowMs(); fprintf(stderr, "mesh_create: %-14s %.1f ms\n", what, t - tS); tS = t; } };
         std::vector<V3> v(n_vertices);
         memcpy(v.data(), vertices, n_vertices * 12);
         std::vector<uint32_t> tri(tri_indices, tri_indices + 3 * n_tris);
@@ -236,33 +259,40 @@ extern "C"
         // CreateHalfEdges (Mesh.cpp:87-131): twin of the directed edge (a, b) is the edge (b, a); first occurrence wins
         Builder b{ v, tri, std::vector<uint32_t>(3 * n_tris, 0xFFFFFFFFu) };
         {
-            std::map<std::pair<uint32_t, uint32_t>, uint32_t> edgeMap;
+            // same find / insert sequence as the reference's std::map (Mesh.cpp:96-118), on a hash map of packed (from, to) keys
+            std::unordered_map<uint64_t, uint32_t> edgeMap;
+            edgeMap.reserve(3 * n_tris);
             for (uint32_t i = 0; i < 3 * n_tris; ++i)
             {
-                const std::pair<uint32_t, uint32_t> edge(tri[i], (i % 3 == 2) ? tri[i - 2] : tri[i + 1]);
-                const auto f = edgeMap.find({ edge.second, edge.first });
+                const uint64_t from = tri[i], to = (i % 3 == 2) ? tri[i - 2] : tri[i + 1];
+                const auto f = edgeMap.find(to << 32 | from);
                 if (f != edgeMap.end()) { b.he[f->second] = i; b.he[i] = f->second; }
-                else edgeMap.insert({ edge, i });
+                else edgeMap.insert({ from << 32 | to, i });
             }
             for (uint32_t h : b.he)
                 if (h == 0xFFFFFFFFu) { setLastError("mesh has an edge without a twin: not a closed manifold (Mesh.cpp:121-128)"); return HPSDF_ERR_MESH; }
         }
 
+        stage("half-edges");
         // pseudonormals: 21 floats per triangle
         std::vector<float> pseudo(21 * n_tris);
-        for (uint32_t t = 0; t < n_tris; ++t)
+        parallelFor(n_tris, [&](size_t t0, size_t t1)
         {
-            float* p = pseudo.data() + 21 * (size_t)t;
-            const V3 f = b.faceNormal(t);
-            p[0] = f.x; p[1] = f.y; p[2] = f.z;
-            for (uint32_t s = 0; s < 3; ++s)
+            for (uint32_t t = (uint32_t)t0; t < (uint32_t)t1; ++t)
             {
-                const V3 e = b.edgeNormal(t, s), w = b.vertexNormal(t, s);
-                p[3 + 3 * s] = e.x; p[4 + 3 * s] = e.y; p[5 + 3 * s] = e.z;
-                p[12 + 3 * s] = w.x; p[13 + 3 * s] = w.y; p[14 + 3 * s] = w.z;
+                float* p = pseudo.data() + 21 * (size_t)t;
+                const V3 f = b.faceNormal(t);
+                p[0] = f.x; p[1] = f.y; p[2] = f.z;
+                for (uint32_t s = 0; s < 3; ++s)
+                {
+                    const V3 e = b.edgeNormal(t, s), w = b.vertexNormal(t, s);
+                    p[3 + 3 * s] = e.x; p[4 + 3 * s] = e.y; p[5 + 3 * s] = e.z;
+                    p[12 + 3 * s] = w.x; p[13 + 3 * s] = w.y; p[14 + 3 * s] = w.z;
+                }
             }
-        }
+        });
 
+        stage("pseudonormals");
         // BVH
         std::vector<float> cen(3 * n_tris), tmn(3 * n_tris), tmx(3 * n_tris);
         for (uint32_t t = 0; t < n_tris; ++t)
@@ -281,8 +311,10 @@ extern "C"
             memcpy(nodes[i].mn, bn[i].mn, 12); memcpy(nodes[i].mx, bn[i].mx, 12);
             nodes[i].a = bn[i].a; nodes[i].b = bn[i].b;
         }
+        stage("bvh");
         std::vector<float> obb;
         computeObbs(bn, order, v, tri, obb);
+        stage("oriented boxes");
         std::vector<float> tv(12 * n_tris);
         for (uint32_t slot = 0; slot < n_tris; ++slot)
         {
@@ -316,6 +348,7 @@ extern "C"
         if (e == cudaSuccess) e = cudaMemcpy(p + bNodes + bTv + bPs, obb.data(), obb.size() * 4, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(m->dView, &m->view, sizeof(DeviceMeshView), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { cudaFree(m->blob); delete m; return failCuda(e, "mesh upload"); }
+        stage("upload");
         *out = m;
         return HPSDF_OK;
     }
