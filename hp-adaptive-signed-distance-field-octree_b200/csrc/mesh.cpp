@@ -139,7 +139,8 @@ namespace hpsdf
             }
             memcpy(nodes[idx].mn, mn, 12); memcpy(nodes[idx].mx, mx, 12);
             nodes[idx].begin = begin; nodes[idx].end = end;
-            if (end - begin <= 4)
+            static const uint32_t leafMax = getenv("HPSDF_LEAF") ? (uint32_t)atoi(getenv("HPSDF_LEAF")) : 4u;      // <= 7 (3-bit count)
+            if (end - begin <= leafMax)
             {
                 nodes[idx].a = begin; nodes[idx].b = 0x80000000u | (end - begin);
                 return idx;
@@ -230,6 +231,53 @@ namespace hpsdf
             }
             });
         }
+
+        // 4-wide collapse for meshSampleKernel: a wide node holds the grandchildren of a binary node (or its children where
+        // they are leaves), so a query needs half as many dependent memory round trips. 68 floats per node: the 4 child
+        // references (kWideNone | leaf: 0x80000000 | count << 28 | first slot | index of a wide node), then per child one
+        // oriented box; nodes without one (large or with incoherent normals) get their axis-aligned box in the same form.
+        constexpr uint32_t kWideNone = 0xFFFFFFFFu;
+        uint32_t collapseWide(const std::vector<BuildNode>& bn, const std::vector<float>& obb, std::vector<float>& wide, uint32_t b, double inflate)
+        {
+            const uint32_t idx = (uint32_t)(wide.size() / 68);
+            wide.resize(wide.size() + 68, 0.0f);
+            uint32_t kids[4], nk = 0;
+            const uint32_t two[2] = { bn[b].a, bn[b].b };
+            for (int s = 0; s < 2; ++s)
+            {
+                const BuildNode& c = bn[two[s]];
+                if (c.b & 0x80000000u) kids[nk++] = two[s];
+                else { kids[nk++] = c.a; kids[nk++] = c.b; }
+            }
+            for (uint32_t k = 0; k < 4; ++k)
+            {
+                uint32_t ref = kWideNone;
+                float box[16] = { 0 };
+                box[3] = box[7] = box[11] = -3.0e38f;                 // absent child: |q| - he overflows to +inf
+                if (k < nk)
+                {
+                    const BuildNode& c = bn[kids[k]];
+                    const float* o = &obb[16 * (size_t)kids[k]];
+                    if (o[3] < 1e38f) memcpy(box, o, 64);
+                    else
+                    {
+                        for (int d = 0; d < 3; ++d)
+                        {
+                            const double lo = c.mn[d], hi = c.mx[d];
+                            box[d] = (float)(0.5 * (lo + hi));
+                            const double ce = (double)box[d];
+                            box[3 + 4 * d] = std::nextafter((float)(std::max(hi - ce, ce - lo) + inflate), 3.402823466e+38f);
+                        }
+                        box[4] = 1.0f; box[9] = 1.0f; box[14] = 1.0f;       // u = x, v = y, n = z
+                    }
+                    if (c.b & 0x80000000u) ref = 0x80000000u | ((c.b & 7u) << 28) | c.a;
+                    else ref = collapseWide(bn, obb, wide, kids[k], inflate);
+                }
+                memcpy(&wide[68 * (size_t)idx + k], &ref, 4);
+                memcpy(&wide[68 * (size_t)idx + 4 + 16 * k], box, 64);
+            }
+            return idx;
+        }
     }
 }
 
@@ -242,7 +290,7 @@ extern "C"
     {
         if (!out) { setLastError("out is null"); return HPSDF_ERR_INVALID_ARG; }
         *out = nullptr;
-        if (!vertices || !tri_indices || n_vertices == 0 || n_tris == 0 || n_tris >= 0x20000000ull)      // leaf slots are packed into 29 bits (mesh_sample_kernel.cuh)
+        if (!vertices || !tri_indices || n_vertices == 0 || n_tris == 0 || n_tris >= 0x10000000ull)      // leaf slots are packed into 28 bits (mesh_sample_kernel.cuh)
         { setLastError("mesh arrays are null, empty or too large"); return HPSDF_ERR_INVALID_ARG; }
         std::string err;
         DeviceCtx* ctx = getDeviceCtx(device, err);
@@ -314,6 +362,25 @@ extern "C"
         stage("bvh");
         std::vector<float> obb;
         computeObbs(bn, order, v, tri, obb);
+        std::vector<float> wide;
+        wide.reserve(68 * (bn.size() / 2 + 2));
+        {
+            double diag2 = 0.0, maxAbs = 0.0;
+            for (int d = 0; d < 3; ++d)
+            {
+                diag2 += ((double)bn[0].mx[d] - bn[0].mn[d]) * ((double)bn[0].mx[d] - bn[0].mn[d]);
+                maxAbs = std::max(maxAbs, std::max(std::fabs((double)bn[0].mn[d]), std::fabs((double)bn[0].mx[d])));
+            }
+            const double inflate = 1e-5 * std::max(std::sqrt(diag2), maxAbs);
+            if (bn[0].b & 0x80000000u)
+            {
+                // the whole mesh is one leaf: a root with that single child
+                wide.assign(68, 0.0f);
+                const uint32_t none = kWideNone, ref = 0x80000000u | ((bn[0].b & 7u) << 28) | bn[0].a;
+                for (int k = 0; k < 4; ++k) { memcpy(&wide[k], k ? &none : &ref, 4); wide[4 + 16 * k + 3] = wide[4 + 16 * k + 7] = wide[4 + 16 * k + 11] = k ? -3.0e38f : 3.0e38f; }
+            }
+            else collapseWide(bn, obb, wide, 0, inflate);
+        }
         stage("oriented boxes");
         std::vector<float> tv(12 * n_tris);
         for (uint32_t slot = 0; slot < n_tris; ++slot)
@@ -332,8 +399,8 @@ extern "C"
         m->device = ctx->device; m->nTris = (uint32_t)n_tris; m->nVerts = (uint32_t)n_vertices;
         memcpy(m->mn, bn[0].mn, 12); memcpy(m->mx, bn[0].mx, 12);          // CalculateMeshAABB (Mesh.cpp:66-84)
         auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
-        const size_t bNodes = align(nodes.size() * sizeof(BvhNode)), bTv = align(tv.size() * 4), bPs = align(pseudo.size() * 4), bObb = align(obb.size() * 4);
-        cudaError_t e = cudaMalloc(&m->blob, bNodes + bTv + bPs + bObb + 256);
+        const size_t bNodes = align(nodes.size() * sizeof(BvhNode)), bTv = align(tv.size() * 4), bPs = align(pseudo.size() * 4), bObb = align(obb.size() * 4), bWide = align(wide.size() * 4);
+        cudaError_t e = cudaMalloc(&m->blob, bNodes + bTv + bPs + bObb + bWide + 256);
         if (e != cudaSuccess) { delete m; return failCuda(e, "mesh allocation"); }
         char* p = (char*)m->blob;
         m->view.nodes = (const BvhNode*)p;
@@ -341,11 +408,13 @@ extern "C"
         m->view.pseudo = (const float*)(p + bNodes + bTv);
         m->view.nTris = (uint32_t)n_tris; m->view.nNodes = (uint32_t)nodes.size();
         m->view.obb = (const void*)(p + bNodes + bTv + bPs);
-        m->dView = (DeviceMeshView*)(p + bNodes + bTv + bPs + bObb);
+        m->view.wide = (const void*)(p + bNodes + bTv + bPs + bObb);
+        m->dView = (DeviceMeshView*)(p + bNodes + bTv + bPs + bObb + bWide);
         e = cudaMemcpy(p, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(p + bNodes, tv.data(), tv.size() * 4, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(p + bNodes + bTv, pseudo.data(), pseudo.size() * 4, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(p + bNodes + bTv + bPs, obb.data(), obb.size() * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(p + bNodes + bTv + bPs + bObb, wide.data(), wide.size() * 4, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(m->dView, &m->view, sizeof(DeviceMeshView), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { cudaFree(m->blob); delete m; return failCuda(e, "mesh upload"); }
         stage("upload");

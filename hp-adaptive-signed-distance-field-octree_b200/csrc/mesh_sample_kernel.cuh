@@ -14,7 +14,9 @@
 //     iterations run when at least `triThreshold` (12) lanes have a triangle waiting (or nobody has a node left), re-checking the leaf's
 //     bound against the lane's current best first;
 //   * a lane that finishes its query writes the sample and takes the next one (warps grab 32-128 samples at a time from a
-//     global counter), so lanes do not wait for their neighbours and far / near cells balance across the grid.
+//     global counter), so lanes do not wait for their neighbours and far / near cells balance across the grid;
+//   * the tree is walked in its 4-wide collapse (mesh.cpp: collapseWide), one 272-byte record and one memory round trip per
+//     step: the walk is latency-bound, and leaf sizes 1 / 2 / 4 / 7 measured 98 / 90 / 83 / 80 ms — node steps are the cost.
 // Results are those of meshSignedDistanceF: same exact test, same (smallest f32 d2, lowest triangle index) winner, same
 // conservative pruning — the order in which candidates are met does not matter to that rule.
 #pragma once
@@ -32,13 +34,11 @@ namespace hpsdf
                      const RootMap map, const FitTablesDev tab, double* __restrict__ samples, unsigned long long* __restrict__ counter,
                      const unsigned grab, const int triThreshold)
     {
-        const float4* __restrict__ nodes4 = (const float4*)mesh->nodes;        // 2 float4 per node: {mn, a}, {mx, b}
-        const float4* __restrict__ obb = (const float4*)mesh->obb;
+        const float4* __restrict__ wide = (const float4*)mesh->wide;           // 17 float4 per 4-wide node: {child refs}, 4 x oriented box
         const float4* __restrict__ tv = (const float4*)mesh->triVerts;
         const double* __restrict__ roots = tab.roots[D];
         const unsigned n = (unsigned)fitRule(D), n2 = n * n, n3 = n2 * n;
         const unsigned lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
-        const uint32_t rootA = __float_as_uint(__ldg(&nodes4[0].w)), rootB = __float_as_uint(__ldg(&nodes4[1].w));
 
         // per-lane query state
         long long sid = -1;                       // sample index, -1 = idle
@@ -46,8 +46,8 @@ namespace hpsdf
         MeshHit h;
         uint32_t stackN[kMeshStack]; float stackD[kMeshStack];
         int sp = 0;
-        uint32_t cur = kNoNode, curA = 0, curB = 0; float curD = 0.0f;       // node to process, its child / leaf words, its bound
-        uint32_t qLeaf[kMeshQueue]; float qD[kMeshQueue];        // circular: head qh, count qn; entry = first slot | count << 29
+        uint32_t cur = kNoNode; float curD = 0.0f;       // wide node (or leaf reference, bit 31) to process and its bound
+        uint32_t qLeaf[kMeshQueue]; float qD[kMeshQueue];        // circular: head qh, count qn; entry = leaf reference
         int qh = 0, qn = 0, tcur = 0;
         // warp-uniform work cursor
         unsigned long long cursor = 0, grabEnd = 0;
@@ -60,11 +60,6 @@ namespace hpsdf
             {
                 --sp;
                 if (stackD[sp] <= h.best * 1.000001f) { cur = stackN[sp]; curD = stackD[sp]; break; }
-            }
-            if (cur != kNoNode)
-            {
-                curA = __float_as_uint(__ldg(&nodes4[2 * (size_t)cur].w));
-                curB = __float_as_uint(__ldg(&nodes4[2 * (size_t)cur + 1].w));
             }
         };
 
@@ -105,7 +100,6 @@ namespace hpsdf
                     h = MeshHit();
                     h.pt = p;
                     sp = 0; cur = 0; curD = 0.0f; qh = 0; qn = 0; tcur = 0;
-                    curA = rootA; curB = rootB;
                 }
                 cursor += want < avail ? want : avail;
                 idle = __ballot_sync(0xFFFFFFFFu, sid < 0);
@@ -120,36 +114,41 @@ namespace hpsdf
             {
                 if (wantNode)
                 {
-                    const uint32_t a = curA, b = curB;
-                    if (b & 0x80000000u)
+                    if (cur & 0x80000000u)
                     {
                         const int slot = (qh + qn) & (kMeshQueue - 1);
-                        qLeaf[slot] = a | (b << 29);                             // first triangle slot (< 2^29) | count (1..4)
+                        qLeaf[slot] = cur;                                       // 0x80000000 | count << 28 | first triangle slot
                         qD[slot] = curD;
                         ++qn;
                         pop();
                     }
                     else
                     {
-                        // one round trip per step: both children's axis-aligned AND oriented boxes are requested together
+                        // one round trip per step: the four child references and their oriented boxes sit in one 272-byte record
                         // (the walk is latency-bound: ncu showed 10 cycles of long-scoreboard stall per issued instruction)
-                        const float4 l0 = __ldg(nodes4 + 2 * (size_t)a), l1 = __ldg(nodes4 + 2 * (size_t)a + 1);
-                        const float4 r0 = __ldg(nodes4 + 2 * (size_t)b), r1 = __ldg(nodes4 + 2 * (size_t)b + 1);
-                        const float4 lo0 = __ldg(obb + 4 * (size_t)a), lo1 = __ldg(obb + 4 * (size_t)a + 1), lo2 = __ldg(obb + 4 * (size_t)a + 2), lo3 = __ldg(obb + 4 * (size_t)a + 3);
-                        const float4 ro0 = __ldg(obb + 4 * (size_t)b), ro1 = __ldg(obb + 4 * (size_t)b + 1), ro2 = __ldg(obb + 4 * (size_t)b + 2), ro3 = __ldg(obb + 4 * (size_t)b + 3);
+                        const float4* __restrict__ w = wide + 17 * (size_t)cur;
+                        const float4 hdr = __ldg(w);
+                        const uint32_t ref[4] = { __float_as_uint(hdr.x), __float_as_uint(hdr.y), __float_as_uint(hdr.z), __float_as_uint(hdr.w) };
                         const float lim = h.best * 1.000001f;
-                        const float dl = fmaxf(aabbDist2(l0, l1, p), obbDist2(lo0, lo1, lo2, lo3, p));
-                        const float dr = fmaxf(aabbDist2(r0, r1, p), obbDist2(ro0, ro1, ro2, ro3, p));
-                        const bool goL = dl <= lim, goR = dr <= lim;
-                        if (goL && goR)
+                        float cd[4];
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k)
                         {
-                            const bool leftFirst = dl <= dr;
-                            if (sp < kMeshStack) { stackN[sp] = leftFirst ? b : a; stackD[sp] = leftFirst ? dr : dl; ++sp; }
-                            cur = leftFirst ? a : b; curD = leftFirst ? dl : dr;
-                            curA = __float_as_uint(leftFirst ? l0.w : r0.w); curB = __float_as_uint(leftFirst ? l1.w : r1.w);
+                            const float4 o0 = __ldg(w + 1 + 4 * k), o1 = __ldg(w + 2 + 4 * k), o2 = __ldg(w + 3 + 4 * k), o3 = __ldg(w + 4 + 4 * k);
+                            const float d = obbDist2(o0, o1, o2, o3, p);
+                            cd[k] = (ref[k] != kNoNode && d <= lim) ? d : 3.402823466e+38f;          // FLT_MAX = "do not visit" (lim < FLT_MAX once a triangle was seen; before that every real child passes)
                         }
-                        else if (goL) { cur = a; curD = dl; curA = __float_as_uint(l0.w); curB = __float_as_uint(l1.w); }
-                        else if (goR) { cur = b; curD = dr; curA = __float_as_uint(r0.w); curB = __float_as_uint(r1.w); }
+                        // visit order: nearest first; the others go on the stack farthest first so that the nearest of them is popped next
+                        uint32_t r0 = ref[0], r1 = ref[1], r2 = ref[2], r3 = ref[3];
+                        float d0 = cd[0], d1 = cd[1], d2 = cd[2], d3 = cd[3];
+                        #define HPSDF_CSWAP(da, ra, db, rb) if (db < da) { const float td = da; da = db; db = td; const uint32_t tr = ra; ra = rb; rb = tr; }
+                        HPSDF_CSWAP(d0, r0, d1, r1) HPSDF_CSWAP(d2, r2, d3, r3) HPSDF_CSWAP(d0, r0, d2, r2) HPSDF_CSWAP(d1, r1, d3, r3) HPSDF_CSWAP(d1, r1, d2, r2)
+                        #undef HPSDF_CSWAP
+                        const bool v0 = d0 < 3.0e38f;
+                        if (d3 < 3.0e38f && sp < kMeshStack) { stackN[sp] = r3; stackD[sp] = d3; ++sp; }
+                        if (d2 < 3.0e38f && sp < kMeshStack) { stackN[sp] = r2; stackD[sp] = d2; ++sp; }
+                        if (d1 < 3.0e38f && sp < kMeshStack) { stackN[sp] = r1; stackD[sp] = d1; ++sp; }
+                        if (v0) { cur = r0; curD = d0; }
                         else pop();
                     }
                 }
@@ -157,7 +156,7 @@ namespace hpsdf
             else if (qn > 0)
             {
                 const uint32_t e = qLeaf[qh];
-                const uint32_t first = e & 0x1FFFFFFFu, cnt = e >> 29;
+                const uint32_t first = e & 0x0FFFFFFFu, cnt = (e >> 28) & 7u;
                 if (tcur == 0 && qD[qh] > h.best * 1.000001f) { qh = (qh + 1) & (kMeshQueue - 1); --qn; }      // pruned while it waited
                 else
                 {
