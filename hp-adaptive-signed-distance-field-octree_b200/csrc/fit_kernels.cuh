@@ -80,7 +80,8 @@ namespace hpsdf
                     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
                     if (e != cudaSuccess) return e;
                     // 4 CTAs of 256 per SM (64 registers) and "test triangles once 12 lanes have one waiting" measured best on
-                    // B200 (870 k-triangle mesh: 2 CTAs/24 lanes 113 ms, 3/24 101 ms, 4/24 95 ms, 4/12 88 ms, 4/4 95 ms)
+                    // B200 (870 k-triangle mesh, binary tree: 2 CTAs/24 lanes 113 ms, 3/24 101 ms, 4/24 95 ms, 4/12 88 ms, 4/4 95 ms;
+                    // 4-wide tree: 8 or 12 lanes 62.8 ms, 16 63.9, 20 66.3, 24 70.5)
                     meshSampleKernel<<<(unsigned)std::min(want, sms * 4), 256, 0, stream>>>(dTasks + b, total, D, (const DeviceMeshView*)prog.instr[0].handle,
                                                                                           map, tab, samples, counter, grab, 12);
                 }

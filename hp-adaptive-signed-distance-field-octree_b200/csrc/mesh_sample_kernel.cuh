@@ -32,7 +32,7 @@ namespace hpsdf
     __global__ void __launch_bounds__(256, 4)
     meshSampleKernel(const FitTask* __restrict__ tasks, unsigned long long nSamples, int D, const DeviceMeshView* __restrict__ mesh,
                      const RootMap map, const FitTablesDev tab, double* __restrict__ samples, unsigned long long* __restrict__ counter,
-                     const unsigned grab, const int triThreshold)
+                     const unsigned grab, const int triThreshold)   // (triThreshold: see launchOne)
     {
         const float4* __restrict__ wide = (const float4*)mesh->wide;           // 17 float4 per 4-wide node: {child refs}, 4 x oriented box
         const float4* __restrict__ tv = (const float4*)mesh->triVerts;
@@ -53,14 +53,13 @@ namespace hpsdf
         unsigned long long cursor = 0, grabEnd = 0;
         bool exhausted = false;
 
+        // One entry per call: a stale entry (its bound no longer beats the lane's best) is recognised by the next node step,
+        // which then pops again — a divergent "skip the stale ones" loop here ran with 2-4 active lanes and drew 29 % of the
+        // kernel's stall samples on its dependent local-memory loads.
         auto pop = [&]()
         {
-            cur = kNoNode;
-            while (sp > 0)
-            {
-                --sp;
-                if (stackD[sp] <= h.best * 1.000001f) { cur = stackN[sp]; curD = stackD[sp]; break; }
-            }
+            if (sp > 0) { --sp; cur = stackN[sp]; curD = stackD[sp]; }
+            else cur = kNoNode;
         };
 
         for (;;)
@@ -114,7 +113,8 @@ namespace hpsdf
             {
                 if (wantNode)
                 {
-                    if (cur & 0x80000000u)
+                    if (curD > h.best * 1.000001f) pop();                        // went stale on the stack
+                    else if (cur & 0x80000000u)
                     {
                         const int slot = (qh + qn) & (kMeshQueue - 1);
                         qLeaf[slot] = cur;                                       // 0x80000000 | count << 28 | first triangle slot
