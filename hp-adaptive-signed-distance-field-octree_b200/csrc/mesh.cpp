@@ -235,7 +235,8 @@ namespace hpsdf
         // 4-wide collapse for meshSampleKernel: a wide node holds the grandchildren of a binary node (or its children where
         // they are leaves), so a query needs half as many dependent memory round trips. 68 floats per node: the 4 child
         // references (kWideNone | leaf: 0x80000000 | count << 28 | first slot | index of a wide node), then per child one
-        // oriented box; nodes without one (large or with incoherent normals) get their axis-aligned box in the same form.
+        // oriented box (a 256-byte record with the references folded into the boxes' padding measured 5-12 % SLOWER: the
+        // power-of-two stride maps the nodes onto half of the L1 sets); nodes without one (large or with incoherent normals) get their axis-aligned box in the same form.
         constexpr uint32_t kWideNone = 0xFFFFFFFFu;
         uint32_t collapseWide(const std::vector<BuildNode>& bn, const std::vector<float>& obb, std::vector<float>& wide, uint32_t b, double inflate)
         {
