@@ -48,7 +48,7 @@ namespace hpsdf
         int sp = 0;
         uint32_t cur = kNoNode; float curD = 0.0f;       // wide node (or leaf reference, bit 31) to process and its bound
         uint32_t qLeaf[kMeshQueue]; float qD[kMeshQueue];        // circular: head qh, count qn; entry = leaf reference
-        int qh = 0, qn = 0, tcur = 0;
+        int qh = 0, qn = 0;
         // warp-uniform work cursor
         unsigned long long cursor = 0, grabEnd = 0;
         bool exhausted = false;
@@ -98,7 +98,7 @@ namespace hpsdf
                            (float)samplePos(roots[k], half, (double)cell.z, map.sizes[2], map.centre[2]));
                     h = MeshHit();
                     h.pt = p;
-                    sp = 0; cur = 0; curD = 0.0f; qh = 0; qn = 0; tcur = 0;
+                    sp = 0; cur = 0; curD = 0.0f; qh = 0; qn = 0;
                 }
                 cursor += want < avail ? want : avail;
                 idle = __ballot_sync(0xFFFFFFFFu, sid < 0);
@@ -157,18 +157,23 @@ namespace hpsdf
             {
                 const uint32_t e = qLeaf[qh];
                 const uint32_t first = e & 0x0FFFFFFFu, cnt = (e >> 28) & 7u;
-                if (tcur == 0 && qD[qh] > h.best * 1.000001f) { qh = (qh + 1) & (kMeshQueue - 1); --qn; }      // pruned while it waited
-                else
+                if (qD[qh] <= h.best * 1.000001f)                              // else: pruned while it waited
                 {
-                    const float4 A = __ldg(tv + 3 * (size_t)(first + tcur)), B = __ldg(tv + 3 * (size_t)(first + tcur) + 1), C = __ldg(tv + 3 * (size_t)(first + tcur) + 2);
-                    const uint32_t tri = __float_as_uint(A.w);
-                    int s, id;
-                    const F3 cp = closestSimplex(p, f3(A.x, A.y, A.z), f3(B.x, B.y, B.z), f3(C.x, C.y, C.z), s, id);
-                    const F3 d = sub3(p, cp);
-                    const float d2 = dot3(d, d);                               // (pt - closestPt).squaredNorm(), BVH.cpp:320
-                    if (d2 < h.best || (d2 == h.best && tri < h.tri)) { h.best = d2; h.tri = tri; h.simplex = s; h.id = id; h.pt = cp; }
-                    if (++tcur == (int)cnt) { tcur = 0; qh = (qh + 1) & (kMeshQueue - 1); --qn; }
+                    // the whole leaf in one iteration (3-4 triangles): the scheduler's ballots are paid once per leaf
+                    #pragma unroll 1
+                    for (uint32_t t = 0; t < cnt; ++t)
+                    {
+                        const float4 A = __ldg(tv + 3 * (size_t)(first + t)), B = __ldg(tv + 3 * (size_t)(first + t) + 1), C = __ldg(tv + 3 * (size_t)(first + t) + 2);
+                        const uint32_t tri = __float_as_uint(A.w);
+                        int s, id;
+                        const F3 cp = closestSimplex(p, f3(A.x, A.y, A.z), f3(B.x, B.y, B.z), f3(C.x, C.y, C.z), s, id);
+                        const F3 d = sub3(p, cp);
+                        const float d2 = dot3(d, d);                           // (pt - closestPt).squaredNorm(), BVH.cpp:320
+                        if (d2 < h.best || (d2 == h.best && tri < h.tri)) { h.best = d2; h.tri = tri; h.simplex = s; h.id = id; h.pt = cp; }
+                    }
                 }
+                qh = (qh + 1) & (kMeshQueue - 1);
+                --qn;
             }
         }
     }
