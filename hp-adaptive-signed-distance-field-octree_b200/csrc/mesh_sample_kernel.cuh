@@ -26,7 +26,7 @@
 namespace hpsdf
 {
     constexpr int      kMeshQueue = 4;
-    constexpr int      kMeshStack = 40;
+    constexpr int      kMeshStack = 48;         // >= 3 pushes x 14 levels: the 4-wide tree of the largest accepted mesh (2^28 triangles, median split)
     constexpr uint32_t kNoNode    = 0xFFFFFFFFu;
 
     __global__ void __launch_bounds__(256, 4)
