@@ -759,7 +759,12 @@ namespace hpsdf
             hpsdf_status st = HPSDF_OK;
             // CreateRoot (Octree.cpp:792-801) + UniformlyRefine
             nodes_.clear();
-            nodes_.reserve(8192);
+            // growth of these vectors during the replay is pure overhead: start from the size of the last build on this device
+            const size_t guess = std::max<size_t>(ws_.lastNodeCount + ws_.lastNodeCount / 4, 8192);
+            nodes_.reserve(guess);
+            errOf_.reserve(guess); jobOf_.reserve(guess); inQueue_.reserve(guess);
+            jobs_.reserve(guess / 2);
+            t_.applyLog.reserve(guess / 2);
             HostNode root;
             root.depth = 0;
             for (int i = 0; i < 3; ++i) { root.mn[i] = -0.5f; root.mx[i] = 0.5f; }
@@ -819,7 +824,7 @@ namespace hpsdf
             {
                 uint64_t leaves = 0;
                 for (const HostNode& n : nodes_) leaves += n.child == kNoChild;
-                t_.stats.n_nodes = nodes_.size(); t_.stats.n_leaves = leaves; t_.stats.n_coeffs = t_.nCoeffs;
+                t_.stats.n_nodes = nodes_.size(); ws_.lastNodeCount = nodes_.size(); t_.stats.n_leaves = leaves; t_.stats.n_coeffs = t_.nCoeffs;
             }
             cudaStreamSynchronize(stream_);
             t_.stats.total_ms = nowMs() - t0;
