@@ -392,7 +392,7 @@ def main():
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.cpu()[0])
-    h2d = 80 + 80 * len(CASES[WORKLOAD]["prog"]) + 32 * stats["fits_evaluated"]      # config + program + fit task descriptors
+    h2d = 80 + 80 * len(CASES[WORKLOAD]["prog"]) + 32 * stats["jobs_evaluated"]      # config + program + one 32-byte record per refinement job
     d2h = blk_bytes + 16 * stats["fits_evaluated"]                                    # MemoryBlock + {error, c0} records
     # query e2e: pinned host points in, host values out
     n_qe = 1 << 22
