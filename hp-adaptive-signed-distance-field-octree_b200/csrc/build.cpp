@@ -135,8 +135,11 @@ namespace hpsdf
             void         computeLevel();
             static int   bucketOf(double e)
             {
-                int ex = -1100;
-                if (e > 0.0) std::frexp(e, &ex);
+                // binary exponent as frexp would give it for normal numbers, read from the bits (called ~10 times per job)
+                if (!(e > 0.0)) return 0;
+                uint64_t bits;
+                memcpy(&bits, &e, 8);
+                const int ex = (int)((bits >> 52) & 0x7FFu) - 1022;
                 return std::min(std::max(ex + 1100, 0), kBuckets - 1);
             }
             // a new / changed leaf enters the conceptual queue: histogram + pending list (it reaches the heap once evaluated)
