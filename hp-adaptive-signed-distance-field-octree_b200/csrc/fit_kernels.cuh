@@ -1,6 +1,7 @@
 // fit_kernels.cuh — host launchers of fitKernel<D, EXT> (the kernel itself: fit_kernel_body.cuh).
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "hp_common.h"
 #include "device_ctx.h"
@@ -126,7 +127,11 @@ namespace hpsdf
     {
         if (!programHasExt(prog)) return launchFitKernelT<false>(degree, dTasks, n, pool, recs, prog, map, ctx.fitTab, nullptr, 0, nullptr, ctx.smCount, stream);
         const size_t n3 = (size_t)fitRule(degree) * fitRule(degree) * fitRule(degree);
-        const size_t want = std::min<size_t>((size_t)std::max(n, 1) * n3, std::max<size_t>(kSampleScratchDoubles, n3));
+        // chunk size limit; HPSDF_SAMPLE_CAP (doubles, read per call) lets the tests force the multi-chunk path on small inputs
+        size_t limit = kSampleScratchDoubles;
+        if (const char* env = getenv("HPSDF_SAMPLE_CAP")) limit = (size_t)strtoull(env, nullptr, 10);
+        limit = std::max(limit, n3);
+        const size_t want = std::min<size_t>((size_t)std::max(n, 1) * n3, limit);
         if (ctx.ws.samples.cap < want)
         {
             // grow-only scratch; queued work that reads the old buffer must finish before it is freed
@@ -139,7 +144,7 @@ namespace hpsdf
             const cudaError_t e = ctx.ws.sampleCounter.reserve(2);
             if (e != cudaSuccess) return e;
         }
-        return launchFitKernelT<true>(degree, dTasks, n, pool, recs, prog, map, ctx.fitTab, ctx.ws.samples.p, ctx.ws.samples.cap,
+        return launchFitKernelT<true>(degree, dTasks, n, pool, recs, prog, map, ctx.fitTab, ctx.ws.samples.p, std::min(ctx.ws.samples.cap, limit),
                                       ctx.ws.sampleCounter.p, ctx.smCount, stream);
     }
 

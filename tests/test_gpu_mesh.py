@@ -120,3 +120,26 @@ def test_mixed_mesh_and_closed_form_program_fits_match_the_oracle(hp, oracle, to
         c, e = oracle.oracle_fit(ocfg, oprog, centres[i] - half, centres[i] + half, degree, depth)
         assert rel_inf(coeffs[i], c) <= 1e-10
         assert abs(err[i] - e) <= 1e-9 * e + (1e-12 * np.abs(c).max()) ** 2
+
+
+def test_sample_scratch_chunking_gives_the_same_fits(hp, torus, monkeypatch):
+    """Mesh programs sample F into a scratch buffer in chunks of at most 2^26 doubles; force chunks of 3 fits (and of a single
+    fit) on a small batch: coefficients and errors must be bitwise those of the one-chunk run, for both sample kernels."""
+    v, t, m = torus
+    lo, hi = mesh_root(v)
+    cfg = hp.Config(target_error_threshold=1e-6, continuity_enforce=0, root_min=lo, root_max=hi)
+    rng = np.random.default_rng(9)
+    depth, half, n = 4, 0.5 ** 5, 20
+    centres = (rng.integers(2, 14, (n, 3)) + 0.5) * 2 * half - 0.5
+    cells = np.concatenate([centres, np.full((n, 1), half)], 1).astype(np.float32)
+    for items in ([("mesh", [], m)], [("mesh", [], m), ("sphere", [0.1, 0.0, 0.0, 0.25]), ("intersect", [])]):
+        prog = hp.SdfProgram(items)
+        for degree in (2, 3):
+            monkeypatch.delenv("HPSDF_SAMPLE_CAP", raising=False)
+            c0, e0, _ = hp.fit_batch(cfg, prog, cells, np.full(n, depth), degree)
+            n3 = (4 * degree + 1) ** 3
+            for cap in (3 * n3 + 5, 1):
+                monkeypatch.setenv("HPSDF_SAMPLE_CAP", str(cap))
+                c1, e1, _ = hp.fit_batch(cfg, prog, cells, np.full(n, depth), degree)
+                assert np.array_equal(c0, c1) and np.array_equal(e0, e1), (len(items), degree, cap)
+    monkeypatch.delenv("HPSDF_SAMPLE_CAP", raising=False)
