@@ -37,44 +37,48 @@ namespace hpsdf
     template <int D, bool EXT>
     __global__ void __launch_bounds__(fitThreads(D))
     fitKernel(const FitTask* __restrict__ tasks, double* __restrict__ pool, FitRecord* __restrict__ recs,
-              const SdfProgramDev prog, const RootMap map, const FitTablesDev tab, const double* __restrict__ samples)
+              const SdfProgramDev prog, const RootMap map, const FitTablesDev tab, const double* __restrict__ samples, const int nFits)
     {
         constexpr int N  = fitRule(D);
         constexpr int N2 = N * N;
         constexpr int P2 = pairCount(D);
+        constexpr int G  = fitGroup(D);                     // fits per CTA; fit g of the group is task blockIdx.x * G + g
+        constexpr int PF = (int)fitSmemPerFit(D);
         extern __shared__ double smem[];
         __shared__ SdfProgramSmem sProg;
         if constexpr (!EXT) stageProgram(sProg, prog);
-        double* sQ  = smem;                    // Q[c][k]
-        double* sR  = sQ + (D + 1) * N;        // roots
-        double* sZ  = sR + N;                  // user-space z of sample k
-        double* sT1 = sZ + N;                  // T1[c][j][i]
-        double* sT2 = sT1 + (D + 1) * N2;      // T2[q][i]
-        double* sC  = sT1;                     // final coefficients (T1 is dead after stage 2)
+        double* sQ   = smem;                   // Q[c][k]
+        double* sR   = sQ + (D + 1) * N;       // roots
+        double* sFit = sR + N;                 // per fit: z of sample k (n) | T1[c][j][i] | T2[q][i]; coefficients alias T1
+        auto sZ  = [&](int g) { return sFit + g * PF; };
+        auto sT1 = [&](int g) { return sFit + g * PF + N; };
+        auto sT2 = [&](int g) { return sFit + g * PF + N + (D + 1) * N2; };
 
-        const FitTask t = tasks[blockIdx.x];
         const int tid = threadIdx.x;
-        const double half = (double)t.half;    // aabbScale = sizes * 0.5 (Octree.cpp:1020); cells are cubes
+        const int first = blockIdx.x * G;
+        const int nHere = nFits - first < G ? nFits - first : G;
 
         for (int e = tid; e < (D + 1) * N; e += blockDim.x) sQ[e] = tab.q[D][e];
-        for (int k = tid; k < N; k += blockDim.x)
+        for (int k = tid; k < N; k += blockDim.x) sR[k] = tab.roots[D][k];
+        for (int e = tid; e < nHere * N; e += blockDim.x)
         {
-            const double r = tab.roots[D][k];
-            sR[k] = r;
-            sZ[k] = samplePos(r, half, (double)t.cz, map.sizes[2], map.centre[2]);
+            const int g = e / N, k = e - g * N;
+            const FitTask& t = tasks[first + g];
+            sZ(g)[k] = samplePos(tab.roots[D][k], (double)t.half, (double)t.cz, map.sizes[2], map.centre[2]);
         }
         __syncthreads();
 
         // ---- stage 1: sample F and contract z ---------------------------------------------------------------------
-        for (int col = tid; col < N2; col += blockDim.x)
+        for (int item = tid; item < nHere * N2; item += blockDim.x)
         {
+            const int g = item / N2, col = item - g * N2;
             double acc[D + 1];
             #pragma unroll
             for (int c = 0; c <= D; ++c) acc[c] = 0.0;
             if constexpr (EXT)
             {
                 // mesh / octree programs: F was sampled by sampleKernel into samples[fit][k][j][i] (coalesced over col)
-                const double* __restrict__ fs = samples + (size_t)blockIdx.x * (N * N2) + col;
+                const double* __restrict__ fs = samples + (size_t)(first + g) * (N * N2) + col;
                 #pragma unroll 4
                 for (int k = 0; k < N; ++k)
                 {
@@ -85,52 +89,60 @@ namespace hpsdf
             }
             else
             {
+                const FitTask& t = tasks[first + g];
+                const double half = (double)t.half;    // aabbScale = sizes * 0.5 (Octree.cpp:1020); cells are cubes
                 const int i = col % N, j = col / N;
                 const double X = samplePos(sR[i], half, (double)t.cx, map.sizes[0], map.centre[0]);
                 const double Y = samplePos(sR[j], half, (double)t.cy, map.sizes[1], map.centre[1]);
+                const double* __restrict__ z = sZ(g);
                 #pragma unroll 1
                 for (int k = 0; k < N; ++k)
                 {
-                    const double f = sdfEval<false>(sProg, X, Y, sZ[k]);
+                    const double f = sdfEval<false>(sProg, X, Y, z[k]);
                     #pragma unroll
                     for (int c = 0; c <= D; ++c) acc[c] = fma(f, sQ[c * N + k], acc[c]);
                 }
             }
+            double* t1 = sT1(g);
             #pragma unroll
-            for (int c = 0; c <= D; ++c) sT1[c * N2 + col] = acc[c];
+            for (int c = 0; c <= D; ++c) t1[c * N2 + col] = acc[c];
         }
         __syncthreads();
 
         // ---- stage 2: contract y --------------------------------------------------------------------------------
-        for (int o = tid; o < P2 * N; o += blockDim.x)
+        for (int item = tid; item < nHere * (P2 * N); item += blockDim.x)
         {
+            const int g = item / (P2 * N), o = item - g * (P2 * N);
             const int i = o % N, q = o / N;
             // q -> (b, c): pairs enumerated b = 0..D, c = 0..D-b
             int b = 0, rem = q;
             while (rem >= D + 1 - b) { rem -= D + 1 - b; ++b; }
             const int c = rem;
-            const double* t1 = sT1 + c * N2 + i;
+            const double* t1 = sT1(g) + c * N2 + i;
             const double* qb = sQ + b * N;
             double s = 0.0;
             #pragma unroll 4
             for (int j = 0; j < N; ++j) s = fma(t1[j * N], qb[j], s);
-            sT2[q * N + i] = s;
+            sT2(g)[q * N + i] = s;
         }
         __syncthreads();
 
         // ---- stage 3: contract x for the wanted indices, scale, write ----------------------------------------------
-        const int start = t.degreeIn > 0 ? coeffCount(t.degreeIn) : 0;       // Octree.cpp:1012-1013
-        const int end   = coeffCount(D);
-        const double V  = half * half * half;                                // aabbScale.prod() (Octree.cpp:1022)
-        for (int idx = tid; idx < end; idx += blockDim.x)
+        constexpr int end = coeffCount(D);
+        for (int item = tid; item < nHere * end; item += blockDim.x)
         {
+            const int g = item / end, idx = item - g * end;
+            const FitTask& t = tasks[first + g];
+            const int start = t.degreeIn > 0 ? coeffCount(t.degreeIn) : 0;   // Octree.cpp:1012-1013
             double v;
             if (idx >= start)
             {
+                const double half = (double)t.half;
+                const double V = half * half * half;                         // aabbScale.prod() (Octree.cpp:1022)
                 const uint32_t abc = tab.bidx[idx];
                 const int a = abc & 0xFF, b = (abc >> 8) & 0xFF, c = (abc >> 16) & 0xFF;
                 const int q = b * (D + 1) - (b * (b - 1)) / 2 + c;
-                const double* t2 = sT2 + q * N;
+                const double* t2 = sT2(g) + q * N;
                 const double* qa = sQ + a * N;
                 double s = 0.0;
                 #pragma unroll 4
@@ -139,22 +151,25 @@ namespace hpsdf
             }
             else v = pool[t.src + idx];                                      // kept lower shells (Octree.cpp:847)
             pool[t.out + idx] = v;
-            sC[idx] = v;
+            sT1(g)[idx] = v;                                                 // T1 is dead after stage 2
         }
         __syncthreads();
 
-        // ---- top-shell energy (Octree.cpp:1062-1069): sum of c^2 over idx < end with a+b+c == D --------------------
-        if (tid < 32)
+        // ---- top-shell energy (Octree.cpp:1062-1069): sum of c^2 over idx < end with a+b+c == D; one warp per fit -------
+        for (int g = tid >> 5; g < nHere; g += blockDim.x >> 5)
         {
+            const FitTask& t = tasks[first + g];
+            const int start = t.degreeIn > 0 ? coeffCount(t.degreeIn) : 0;
+            const double* sC = sT1(g);
             double e = 0.0;
-            for (int idx = start + tid; idx < end; idx += 32)
+            for (int idx = start + (tid & 31); idx < end; idx += 32)
             {
                 const uint32_t abc = tab.bidx[idx];
                 if ((int)((abc & 0xFF) + ((abc >> 8) & 0xFF) + ((abc >> 16) & 0xFF)) == D) e = fma(sC[idx], sC[idx], e);
             }
             #pragma unroll
             for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
-            if (tid == 0) { FitRecord r; r.rawErr = e; r.c0 = sC[0]; recs[t.rec] = r; }
+            if ((tid & 31) == 0) { FitRecord r; r.rawErr = e; r.c0 = sC[0]; recs[t.rec] = r; }
         }
     }
 }

@@ -60,7 +60,7 @@ namespace hpsdf
         }
         if constexpr (!EXT)
         {
-            fitKernel<D, false><<<n, fitThreads(D), smem, stream>>>(dTasks, pool, recs, prog, map, tab, nullptr);
+            fitKernel<D, false><<<(n + fitGroup(D) - 1) / fitGroup(D), fitThreads(D), smem, stream>>>(dTasks, pool, recs, prog, map, tab, nullptr, n);
             return cudaGetLastError();
         }
         else
@@ -91,7 +91,7 @@ namespace hpsdf
                     const unsigned long long want = (total + 255) / 256;
                     sampleKernel<<<(unsigned)std::min(want, sms * 64), 256, 0, stream>>>(dTasks + b, total, D, prog, map, tab, samples);
                 }
-                fitKernel<D, true><<<(unsigned)m, fitThreads(D), smem, stream>>>(dTasks + b, pool, recs, prog, map, tab, samples);
+                fitKernel<D, true><<<(unsigned)((m + fitGroup(D) - 1) / fitGroup(D)), fitThreads(D), smem, stream>>>(dTasks + b, pool, recs, prog, map, tab, samples, (int)m);
             }
             return cudaGetLastError();
         }

@@ -47,18 +47,25 @@ namespace hpsdf
     HPSDF_HD inline double samplePos(double root, double half, double c, double size, double centre) { return (root * half + c) * size + centre; }
     // Gauss-Legendre points per axis of a degree-d fit (Octree.cpp:1016-1017: rule 4d+1)
     HPSDF_HD constexpr int fitRule(int d) { return 4 * d + 1; }
-    // fit kernel geometry (fit_kernel_body.cuh): threads per CTA and dynamic shared memory per degree
-    HPSDF_HD constexpr int fitPasses(int d)  { return (fitRule(d) * fitRule(d) + 639) / 640; }
+    // fit kernel geometry (fit_kernel_body.cuh): fits per CTA, threads per CTA and dynamic shared memory per degree.
+    // A fit has n^2 columns of samples, one thread each: 25 / 81 / 169 for d = 1..3 would leave 22 / 16 / 12 % of the lanes
+    // of a CTA idle, so those degrees pack several fits into one CTA (125 of 128, 243 of 256, 507 of 512 lanes busy).
+    HPSDF_HD constexpr int fitGroup(int d)   { return d == 1 ? 5 : (d == 2 || d == 3) ? 3 : 1; }
+    HPSDF_HD constexpr int fitPasses(int d)  { return (fitGroup(d) * fitRule(d) * fitRule(d) + 639) / 640; }
     HPSDF_HD constexpr int fitThreads(int d)
     {
-        return (((fitRule(d) * fitRule(d) + fitPasses(d) - 1) / fitPasses(d)) + 31) / 32 * 32;
+        return (((fitGroup(d) * fitRule(d) * fitRule(d) + fitPasses(d) - 1) / fitPasses(d)) + 31) / 32 * 32;
     }
-    // shared memory (doubles): Q (d+1)*n | roots n | user-space z n | T1 (d+1)*n*n | T2 pairCount*n ; coefficients alias T1
+    // shared memory (doubles): Q (d+1)*n | roots n | then per fit of the group: user-space z n | T1 (d+1)*n*n | T2 pairCount*n ;
+    // coefficients alias T1
+    HPSDF_HD constexpr size_t fitSmemPerFit(int d)
+    {
+        return (size_t)fitRule(d) + (size_t)(d + 1) * fitRule(d) * fitRule(d) + (size_t)pairCount(d) * fitRule(d);
+    }
     HPSDF_HD constexpr size_t fitSmemDoubles(int d)
     {
-        return (size_t)(d + 1) * fitRule(d) + 2 * fitRule(d) + (size_t)(d + 1) * fitRule(d) * fitRule(d) + (size_t)pairCount(d) * fitRule(d);
+        return (size_t)(d + 1) * fitRule(d) + fitRule(d) + (size_t)fitGroup(d) * fitSmemPerFit(d);
     }
-
 #ifndef __CUDACC_RTC__
     // Sum-factorised FLOPs of one full fit at degree d, SDF evaluation excluded:
     // 2(d+1)n^3 + 2 T2(d) n^2 + 2 N_d n + 4 n^3.
