@@ -1,4 +1,4 @@
-// fit_kernels.cuh — batched FitPolynomial (Source/HP/Octree.cpp:1007-1093) for every fit of a build round.
+// fit_kernel_body.cuh — batched FitPolynomial (Source/HP/Octree.cpp:1007-1093) for every fit of a build round.
 //
 // Reference loop: for each of the n^3 Gauss-Legendre samples (n = 4d+1 per axis) and each coefficient index,
 // coeffs[idx] += prod_axis(LpX(a_axis, xi_axis) * NL[a_axis][depth]) * (V * w_i w_j w_k * F(x))        (:1028-1056)
@@ -9,8 +9,10 @@
 //   stage 2 (shared memory): T2[(b,c)][i] = sum_j T1[c][j][i] * Q[b][j]      for b + c <= d
 //   stage 3: C[a][b][c] = V * NL[a] NL[b] NL[c] * sum_i T2[(b,c)][i] * Q[a][i]   for the wanted indices [start, end)
 //
-// followed by the top-shell energy (:1062-1069). One CTA per fit; the SDF program is evaluated in place (sdf_eval.cuh),
-// so samples never touch HBM: per fit the kernel reads a 32-byte task and writes N_d coefficients + a 16-byte record.
+// followed by the top-shell energy (:1062-1069). One CTA per fit (degrees 1-3: 5 / 3 / 3 fits per CTA, hp_common.h:
+// fitGroup); closed-form SDF programs are evaluated in place (sdf_eval.cuh, or generated code under NVRTC), so samples
+// never touch HBM: per fit the kernel reads a 32-byte task and writes N_d coefficients + a 16-byte record. Mesh / octree
+// programs (EXT) read F from the scratch buffer a sample kernel filled (fit_kernels.cuh, mesh_sample_kernel.cuh).
 // The nearness weight (:1071-1090) and the h-vs-p decision (:558-659) are host-side in the greedy replay (build.cpp),
 // where they use the same libm as the CPU checker.
 //
