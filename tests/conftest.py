@@ -14,9 +14,14 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def hp():
-    """The product package (ctypes over lib/libhpsdf.so)."""
+    """The product package (ctypes over lib/libhpsdf.so); built on demand (nvcc cross-compiles without a GPU)."""
     import importlib
-    return importlib.import_module("hp-adaptive-signed-distance-field-octree_b200")
+    import subprocess
+    mod = importlib.import_module("hp-adaptive-signed-distance-field-octree_b200")
+    if not os.path.exists(mod.LIB_PATH) and "HPSDF_LIB" not in os.environ:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "hp-adaptive-signed-distance-field-octree_b200"), "-j8"],
+                              stdout=subprocess.DEVNULL)
+    return mod
 
 
 @pytest.fixture(scope="session")
