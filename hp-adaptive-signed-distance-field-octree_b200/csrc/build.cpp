@@ -121,6 +121,7 @@ namespace hpsdf
             long        unfitted_ = 0;
             int         rank_ = 0, world_ = 1;
             double      sdfFlops_ = 0.0;
+            double      launchMs_ = 0.0;           // host time spent in upload / launch calls (diagnostics)
             bool        progHasExt_ = false;       // the program samples a mesh or another octree
             hpsdf_decision_log_entry lastApplied_{};      // last job applied before the termination cut
             double      lastTotal_ = 0.0, totalBeforeLast_ = 0.0;
@@ -349,6 +350,7 @@ namespace hpsdf
             // fits (tens of microseconds of kernel time) is cheaper to evaluate redundantly on every rank — identical
             // kernels on identical hardware give identical bits, so the replicas stay in lock-step without an exchange.
             const bool shard = world_ > 1 && (progHasExt_ || nTasks >= (size_t)1 << 18);
+            const double tLaunch0 = nowMs();
             if (nTasks)
             {
                 HPSDF_CUDA(cudaMemcpyAsync(dJobs_.p, hJobs_.p, evaluated_.size() * sizeof(JobDesc), cudaMemcpyHostToDevice, stream_));
@@ -417,6 +419,7 @@ namespace hpsdf
                 }
                 HPSDF_CUDA(cudaMemcpyAsync(hRecs_.p, dRecs_.p, nTasks * sizeof(FitRecord), cudaMemcpyDeviceToHost, stream_));
                 const double tWait0 = nowMs();
+                launchMs_ += tWait0 - tLaunch0;
                 HPSDF_CUDA(cudaStreamSynchronize(stream_));
                 t_.stats.device_wait_ms += nowMs() - tWait0;
                 float ms = 0.0f;
@@ -760,6 +763,7 @@ namespace hpsdf
             t_.stats.sdf_flops_per_eval = sdfFlops_;
 
             hpsdf_status st = HPSDF_OK;
+            const double tSetup0 = nowMs();
             // CreateRoot (Octree.cpp:792-801) + UniformlyRefine
             nodes_.clear();
             // growth of these vectors during the replay is pure overhead: start from the size of the last build on this device
@@ -782,6 +786,7 @@ namespace hpsdf
             unfitted_ = (long)pendCount_;
             lastTotal_ = totalBeforeLast_ = total_;
             computeLevel();
+            if (getenv("HPSDF_DEBUG_ROUNDS")) fprintf(stderr, "setup %.3f ms\n", nowMs() - tSetup0);
 
             double replayMs = 0.0;
             size_t stallGuard = 0;
@@ -796,6 +801,7 @@ namespace hpsdf
                 if (pendCount_ == 0) { setLastError("internal: replay stalled with nothing to evaluate"); st = HPSDF_ERR_CUDA; break; }
                 if (++stallGuard > 100000) { setLastError("internal: build does not converge"); st = HPSDF_ERR_CUDA; break; }
             }
+            if (getenv("HPSDF_DEBUG_ROUNDS")) fprintf(stderr, "launch calls %.3f ms\n", launchMs_);
             const double tPack0 = nowMs();
             if (st == HPSDF_OK) st = pack();
             t_.stats.pack_ms = nowMs() - tPack0;
