@@ -16,7 +16,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
-#include <unordered_map>
 #include <numeric>
 #include <vector>
 #include "octree.h"
@@ -121,11 +120,13 @@ namespace hpsdf
             }
         }
 
-        uint32_t buildBvh(std::vector<BuildNode>& nodes, std::vector<uint32_t>& order, const std::vector<float>& cen,
-                          const std::vector<float>& tmn, const std::vector<float>& tmx, uint32_t begin, uint32_t end)
+        // nodes of the median-split tree over m triangles (leaf <= 4): known up front, so subtrees can be built in parallel
+        // into their final index ranges (node, then its left subtree, then its right subtree — the order a serial build gives)
+        uint32_t bvhNodeCount(uint32_t m) { return m <= 4 ? 1u : 1u + bvhNodeCount(m / 2) + bvhNodeCount(m - m / 2); }
+
+        void buildBvh(BuildNode* nodes, uint32_t idx, uint32_t* order, const float* cen, const float* tmn, const float* tmx,
+                      uint32_t begin, uint32_t end, int depth)
         {
-            const uint32_t idx = (uint32_t)nodes.size();
-            nodes.push_back({});
             float mn[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, mx[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
             float cmn[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, cmx[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
             for (uint32_t i = begin; i < end; ++i)
@@ -142,18 +143,28 @@ namespace hpsdf
             if (end - begin <= 4)            // at most 7 fit the 3-bit count of the wide tree; 1 / 2 / 4 / 7 measured 98 / 90 / 83 / 80 ms on the binary walk, 4 best on the 4-wide one
             {
                 nodes[idx].a = begin; nodes[idx].b = 0x80000000u | (end - begin);
-                return idx;
+                return;
             }
             int axis = 0;
             if (cmx[1] - cmn[1] > cmx[axis] - cmn[axis]) axis = 1;
             if (cmx[2] - cmn[2] > cmx[axis] - cmn[axis]) axis = 2;
             const uint32_t mid = (begin + end) / 2;
-            std::nth_element(order.begin() + begin, order.begin() + mid, order.begin() + end,
+            std::nth_element(order + begin, order + mid, order + end,
                              [&](uint32_t x, uint32_t y) { return cen[3 * x + axis] < cen[3 * y + axis] || (cen[3 * x + axis] == cen[3 * y + axis] && x < y); });
-            const uint32_t l = buildBvh(nodes, order, cen, tmn, tmx, begin, mid);
-            const uint32_t r = buildBvh(nodes, order, cen, tmn, tmx, mid, end);
+            const uint32_t l = idx + 1, r = idx + 1 + bvhNodeCount(mid - begin);
             nodes[idx].a = l; nodes[idx].b = r;
-            return idx;
+            if (depth < 4 && end - begin > 65536)
+            {
+                // the two halves touch disjoint ranges of `order` and of `nodes`: the left one gets its own thread (16 at depth 4)
+                std::thread left([=] { buildBvh(nodes, l, order, cen, tmn, tmx, begin, mid, depth + 1); });
+                buildBvh(nodes, r, order, cen, tmn, tmx, mid, end, depth + 1);
+                left.join();
+            }
+            else
+            {
+                buildBvh(nodes, l, order, cen, tmn, tmx, begin, mid, depth + 1);
+                buildBvh(nodes, r, order, cen, tmn, tmx, mid, end, depth + 1);
+            }
         }
 
         // Oriented boxes. The axis-aligned box of a slanted patch of surface overhangs it by about its own size L, so a
@@ -307,15 +318,29 @@ extern "C"
         // CreateHalfEdges (Mesh.cpp:87-131): twin of the directed edge (a, b) is the edge (b, a); first occurrence wins
         Builder b{ v, tri, std::vector<uint32_t>(3 * n_tris, 0xFFFFFFFFu) };
         {
-            // same find / insert sequence as the reference's std::map (Mesh.cpp:96-118), on a hash map of packed (from, to) keys
-            std::unordered_map<uint64_t, uint32_t> edgeMap;
-            edgeMap.reserve(3 * n_tris);
+            // same find / insert sequence as the reference's std::map (Mesh.cpp:96-118): "is the reverse edge known? pair them :
+            // remember this edge unless an equal one is already known", on a flat linear-probing table of packed (from, to) keys
+            size_t cap = 1;
+            while (cap < 6 * n_tris) cap <<= 1;                              // load factor <= 0.5
+            const uint64_t kEmpty = ~0ull;                                   // (0xFFFFFFFF, 0xFFFFFFFF) is not an edge: indices are < n_vertices
+            std::vector<uint64_t> keys(cap, kEmpty);
+            std::vector<uint32_t> vals(cap);
+            auto slotOf = [&](uint64_t key) -> size_t
+            {
+                size_t h = (size_t)((key * 0x9E3779B97F4A7C15ull) >> 20) & (cap - 1);
+                while (keys[h] != kEmpty && keys[h] != key) h = (h + 1) & (cap - 1);
+                return h;
+            };
             for (uint32_t i = 0; i < 3 * n_tris; ++i)
             {
                 const uint64_t from = tri[i], to = (i % 3 == 2) ? tri[i - 2] : tri[i + 1];
-                const auto f = edgeMap.find(to << 32 | from);
-                if (f != edgeMap.end()) { b.he[f->second] = i; b.he[i] = f->second; }
-                else edgeMap.insert({ from << 32 | to, i });
+                const size_t f = slotOf(to << 32 | from);
+                if (keys[f] != kEmpty) { b.he[vals[f]] = i; b.he[i] = vals[f]; }
+                else
+                {
+                    const size_t g = slotOf(from << 32 | to);
+                    if (keys[g] == kEmpty) { keys[g] = from << 32 | to; vals[g] = i; }
+                }
             }
             for (uint32_t h : b.he)
                 if (h == 0xFFFFFFFFu) { setLastError("mesh has an edge without a twin: not a closed manifold (Mesh.cpp:121-128)"); return HPSDF_ERR_MESH; }
@@ -350,9 +375,8 @@ extern "C"
         }
         std::vector<uint32_t> order(n_tris);
         std::iota(order.begin(), order.end(), 0u);
-        std::vector<BuildNode> bn;
-        bn.reserve(n_tris);
-        buildBvh(bn, order, cen, tmn, tmx, 0, (uint32_t)n_tris);
+        std::vector<BuildNode> bn(bvhNodeCount((uint32_t)n_tris));
+        buildBvh(bn.data(), 0, order.data(), cen.data(), tmn.data(), tmx.data(), 0, (uint32_t)n_tris, 0);
         std::vector<BvhNode> nodes(bn.size());
         for (size_t i = 0; i < bn.size(); ++i)
         {
