@@ -208,6 +208,21 @@ def mesh_bench(hp, torch, local, stream, comm, barrier, world, rank, with_cpu):
     return res
 
 
+def query_flops_per_point(hp, tree):
+    """Algorithmic FP64 flops of one Query on `tree`, averaged over uniform points of the root box: per leaf of degree p the
+    three Legendre recurrences (about 3 flops per degree and axis: 9p) and the N_p-term sum sum c * Lx * Ly * Lz (4 N_p),
+    weighted by the leaf's share of the volume."""
+    nodes = hp.parse_block(tree.ToMemoryBlockBytes())["nodes"]
+    leaf = nodes["child"] == np.iinfo(np.uint64).max
+    if not leaf.any():
+        leaf = nodes["deg"] != 13
+    ext = (nodes["mx"][leaf] - nodes["mn"][leaf]).astype(np.float64)
+    vol = ext.prod(1)
+    deg = nodes["deg"][leaf].astype(np.int64)
+    ncoef = np.asarray(hp.COEFF_COUNT)[deg]
+    return float(((9 * deg + 4 * ncoef) * vol).sum() / vol.sum())
+
+
 def useful_fits(stats):
     """FitPolynomial-equivalents on the strict-greedy path: 4096 coarse fits + the 9 fits of every applied job."""
     return 4096 + 9 * (stats["jobs_applied_p"] - 4096 + stats["jobs_applied_h"])
@@ -373,6 +388,7 @@ def main():
     ms_per_step = max(dev_ms, wall_ms) / args.steps if world > 1 else dev_ms / args.steps
     value = fits / (ms_per_step * 1e-3)                    # one tree built cooperatively by all ranks: strong scaling
     q_value = world * n_q / (q_ms * 1e-3)                  # every rank queries its own batch on the replicated tree: weak
+    q_flops = query_flops_per_point(hp, tree)
 
     # ---- e2e through the public API with host buffers -------------------------------------------------------------
     barrier()
@@ -465,7 +481,12 @@ def main():
                                "traffic": 525.06e6 if n_q == (1 << 24) else None,
                                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch on 2^24 points, profiles/r1_query_kernel.md "
                                                  "(algorithmic bytes of the same launch: 536.9e6)",
-                               "peak_source": peak_src}},
+                               "peak_source": peak_src,
+                               "fp64": {"algorithmic_flops_per_point": q_flops, "achieved": q_flops * n_q / (q_ms * 1e-3) / 1e12,
+                                        "peak": fp64_peak, "unit": "TFLOP/s", "frac": q_flops * n_q / (q_ms * 1e-3) / 1e12 / fp64_peak,
+                                        "note": "the kernel is neither HBM- nor FP64-bound: ncu shows 19 cycles of long-scoreboard stall per "
+                                                "issued instruction (dependent node and coefficient gathers from L2), issue slots 33 % busy, "
+                                                "FP64 pipe 22 % (profiles/r1_query_kernel.md)"}}},
     }
     if mesh_line is not None:
         line["mesh_build"] = mesh_line
