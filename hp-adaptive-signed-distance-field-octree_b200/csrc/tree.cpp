@@ -260,7 +260,9 @@ namespace hpsdf
         if (!n) return HPSDF_OK;
         std::lock_guard<std::mutex> lock(t.queryMutex);
         HPSDF_CUDA(cudaSetDevice(t.device));
-        const size_t chunk = std::min<size_t>(n, (size_t)1 << 22);
+        // at least 8 chunks for a large call, so the H2D copy of one chunk overlaps the kernel and the D2H copy of the previous
+        // ones (a single 2^22-point chunk serialised the three: 1.55e9 points/s where the H2D engine alone allows 2.2e9)
+        const size_t chunk = std::min<size_t>(std::max<size_t>((n + 7) / 8, (size_t)1 << 16), (size_t)1 << 22);
         if (t.scratchPts < chunk)
         {
             for (int i = 0; i < 3; ++i)
