@@ -219,3 +219,56 @@ namespace SDF
 
     inline Program& Program::Tree(const Octree& t) { return push(HPSDF_PRIM_OCTREE, {}, t.handle()); }
 }
+
+// Meshing::Mesh (Include/Meshing/Mesh.h:43-99) + Meshing::BVH as an SDF source on the device. The OBJ reader stays the
+// reference's: hand over its `vertices` / `triIndices` arrays. Create() does what CreateFromObj does after parsing
+// (CreateHalfEdges, Mesh.cpp:87-131; false for a mesh that is not a closed manifold) and what BVH::Create does, on the host,
+// then uploads; SignedDistanceAtPt is the BVH overload of Mesh.cpp:54-63 (float32, bit-identical).
+namespace Meshing
+{
+    class Mesh
+    {
+    public:
+        Mesh() = default;
+        Mesh(const Mesh&) = delete;
+        Mesh& operator=(const Mesh&) = delete;
+        ~Mesh() { Clear(); }
+        void Clear() { if (h_) hpsdf_mesh_destroy(h_); h_ = nullptr; }
+
+        /// xyz_: 3 floats per vertex; triIndices_: 3 indices per triangle, counter-clockwise seen from outside
+        bool Create(const float* xyz_, size_t nVertices_, const uint32_t* triIndices_, size_t nTriangles_, int device_ = -1)
+        {
+            Clear();
+            const hpsdf_status st = hpsdf_mesh_create(xyz_, nVertices_, triIndices_, nTriangles_, device_, &h_);
+            if (st == HPSDF_ERR_MESH) return false;                         // the reference's CreateHalfEdges returns false
+            if (st != HPSDF_OK) throw SDF::Error(st, hpsdf_last_error());
+            return true;
+        }
+        /// > 0 implies outside mesh
+        float SignedDistanceAtPt(float x_, float y_, float z_) const
+        {
+            const float p[3] = { x_, y_, z_ };
+            float d = 0.0f;
+            const hpsdf_status st = hpsdf_mesh_signed_distance(need(), p, 1, &d);
+            if (st != HPSDF_OK) throw SDF::Error(st, hpsdf_last_error());
+            return d;
+        }
+        void SignedDistanceAtPts(const float* xyz_, size_t n_, float* out_) const
+        {
+            const hpsdf_status st = hpsdf_mesh_signed_distance(need(), xyz_, n_, out_);
+            if (st != HPSDF_OK) throw SDF::Error(st, hpsdf_last_error());
+        }
+        SDF::Box3f CalculateMeshAABB() const
+        {
+            SDF::Box3f b;
+            const hpsdf_status st = hpsdf_mesh_aabb(need(), b.lo, b.hi);
+            if (st != HPSDF_OK) throw SDF::Error(st, hpsdf_last_error());
+            return b;
+        }
+        const hpsdf_mesh* handle() const { return h_; }
+
+    private:
+        hpsdf_mesh* h_ = nullptr;
+        const hpsdf_mesh* need() const { if (!h_) throw SDF::Error(HPSDF_ERR_INVALID_ARG, "mesh is empty"); return h_; }
+    };
+}

@@ -126,6 +126,35 @@ int main()
         try { t.Create(baseConfig(false), [](const Vec3d&, unsigned long) { return 0.0; }); ok = false; } catch (const SDF::Error& e) { ok = ok && e.status == HPSDF_ERR_UNSUPPORTED; }
         report("Error behaviour", ok);
     }
+    {   // Meshing::Mesh as an SDF source (MeshingUnitTests-style): a regular octahedron |x|+|y|+|z| = 0.3, exact SDF known
+        const float r = 0.3f;
+        const float verts[18] = { r, 0, 0,  -r, 0, 0,  0, r, 0,  0, -r, 0,  0, 0, r,  0, 0, -r };
+        const uint32_t tris[24] = { 0, 2, 4,  2, 1, 4,  1, 3, 4,  3, 0, 4,  2, 0, 5,  1, 2, 5,  3, 1, 5,  0, 3, 5 };
+        Meshing::Mesh mesh;
+        bool ok = mesh.Create(verts, 6, tris, 8);
+        Meshing::Mesh open;
+        ok = ok && !open.Create(verts, 6, tris, 7);                         // one face missing: not a closed manifold
+        const SDF::Box3f box = mesh.CalculateMeshAABB();
+        ok = ok && box.lo[0] == -r && box.hi[2] == r;
+        ok = ok && mesh.SignedDistanceAtPt(0.0f, 0.0f, 0.0f) < 0.0f && std::fabs(mesh.SignedDistanceAtPt(0.0f, 0.0f, 0.0f) + r / std::sqrt(3.0f)) < 1e-6f;
+        ok = ok && std::fabs(mesh.SignedDistanceAtPt(0.45f, 0.0f, 0.0f) - 0.15f) < 1e-6f;          // beyond a vertex
+        SDF::Config c;
+        c.targetErrorThreshold = std::pow(10, -7);
+        c.continuity.enforce = false;
+        SDF::Program p;
+        p.Mesh(mesh.handle());
+        SDF::Octree t;
+        t.Create(c, p);
+        // away from the edges and vertices (where the SDF has kinks the polynomial pieces only approach) the tree reproduces the mesh SDF
+        double worst = 0.0;
+        std::vector<float> q(3 * 20000), d(20000);
+        const auto mp = samples(20000, -0.5, 0.5, 3);
+        for (size_t i = 0; i < 60000; ++i) q[i] = (float)mp[i];
+        mesh.SignedDistanceAtPts(q.data(), 20000, d.data());
+        for (size_t i = 0; i < 20000; ++i)
+            worst = std::max(worst, std::fabs(t.Query(Vec3d{ { (double)q[3 * i], (double)q[3 * i + 1], (double)q[3 * i + 2] } }) - (double)d[i]));
+        report("Mesh SDF source", ok && worst < 0.01);
+    }
     std::printf(failed ? "Some tests failed!\n" : "All tests passed!\n");
     return failed;
 }
