@@ -339,6 +339,46 @@ class Octree:
         _check(lib().hpsdf_query_with_gradient(self._h, a.ctypes.data, len(a), out.ctypes.data, g.ctypes.data))
         return out, g
 
+    def OutputFunctionSlice(self, fname, c, view_min, view_max, n_samples=2048):
+        """Octree::OutputFunctionSlice (Octree.cpp:1132-1205): the z = c slice of the field over viewArea as an n x n grid of
+        batched Queries (the reference loops 2048^2 scalar Queries), coloured like the reference (green outside, blue inside,
+        each rescaled to its own range) and written as `fname`.bmp when fname is not None. Returns (values, rgb image).
+        Sample positions use the reference's arithmetic: one float32 step from the x extent for both axes (:1150-1153)."""
+        self._need()
+        vmin = np.asarray(view_min, np.float32)
+        vmax = np.asarray(view_max, np.float32)
+        n = int(n_samples)
+        step = np.float32((vmax[0] - vmin[0]) / np.float32(n))
+        idx = np.arange(n, dtype=np.uint32).astype(np.float32)
+        xs = vmin[0].astype(np.float64) + (idx * step).astype(np.float64)
+        ys = vmin[1].astype(np.float64) + (idx * step).astype(np.float64)
+        pts = np.empty((n, n, 3), np.float64)
+        pts[:, :, 0] = xs[None, :]
+        pts[:, :, 1] = ys[:, None]
+        pts[:, :, 2] = float(c)
+        vals = self.Query(pts.reshape(-1, 3)).reshape(n, n)
+        eps = np.float64(np.float32(0.000001))
+        pos, v32 = vals > eps, vals.astype(np.float32)
+        pmin, pmax = (vals[pos].min(), vals[pos].max()) if pos.any() else (np.finfo(np.float64).max, 0.0)
+        nmin, nmax = (vals[~pos].min(), vals[~pos].max()) if (~pos).any() else (0.0, -np.finfo(np.float64).max)
+        img = np.zeros((n, n, 3), np.uint8)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            g = 255 * (v32.astype(np.float64) - pmax) / (pmin - pmax)
+            b = 255 * (v32.astype(np.float64) - nmin) / (nmax - nmin)
+        outside = v32 > 0.0
+        img[:, :, 1] = np.where(outside, np.nan_to_num(g, nan=0.0, posinf=255.0, neginf=0.0).clip(0, 255), 0).astype(np.uint8)
+        img[:, :, 2] = np.where(~outside, np.nan_to_num(b, nan=0.0, posinf=255.0, neginf=0.0).clip(0, 255), 0).astype(np.uint8)
+        if fname is not None:
+            row = (3 * n + 3) & ~3
+            hdr = b"BM" + (54 + row * n).to_bytes(4, "little") + bytes(4) + (54).to_bytes(4, "little") + (40).to_bytes(4, "little") + \
+                n.to_bytes(4, "little") + n.to_bytes(4, "little") + (1).to_bytes(2, "little") + (24).to_bytes(2, "little") + bytes(24)
+            with open(str(fname) + ".bmp", "wb") as f:
+                f.write(hdr)
+                pad = bytes(row - 3 * n)
+                for i in range(n - 1, -1, -1):                      # BMP rows are stored bottom-up; channels as B, G, R
+                    f.write(img[i, :, ::-1].tobytes() + pad)
+        return vals, img
+
     # -- serialisation (Octree.cpp:403-456) ----------------------------------------------------------------------------
     def ToMemoryBlock(self):
         self._need()
