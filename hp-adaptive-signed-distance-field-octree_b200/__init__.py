@@ -123,7 +123,7 @@ EXPORTS = [
     "hpsdf_query_device", "hpsdf_query_with_gradient", "hpsdf_to_memory_block", "hpsdf_from_memory_block", "hpsdf_clone",
     "hpsdf_get_root_aabb", "hpsdf_destroy", "hpsdf_get_build_stats", "hpsdf_get_decision_log", "hpsdf_get_apply_log", "hpsdf_fit_batch",
     "hpsdf_bench_frontier", "hpsdf_measure_fp64_peak", "hpsdf_comm_get_unique_id", "hpsdf_comm_init",
-    "hpsdf_comm_destroy", "hpsdf_shard_range", "hpsdf_set_jit", "hpsdf_jit_compile_check",
+    "hpsdf_comm_destroy", "hpsdf_shard_range", "hpsdf_set_jit", "hpsdf_jit_compile_check", "hpsdf_query_ray",
 ]
 
 _lib = None
@@ -164,6 +164,7 @@ def lib():
     L.hpsdf_query.argtypes = [vp, vp, sz, vp]
     L.hpsdf_query_device.argtypes = [vp, vp, sz, vp, vp]
     L.hpsdf_query_with_gradient.argtypes = [vp, vp, sz, vp, vp]
+    L.hpsdf_query_ray.argtypes = [vp, vp, vp, sz, dbl, vp, vp]
     L.hpsdf_to_memory_block.argtypes = [vp, C.POINTER(sz), C.POINTER(vp)]
     L.hpsdf_from_memory_block.argtypes = [vp, sz, i32, C.POINTER(vp)]
     L.hpsdf_clone.argtypes = [vp, C.POINTER(vp)]
@@ -338,6 +339,17 @@ class Octree:
         g = np.empty((len(a), 3), np.float64)
         _check(lib().hpsdf_query_with_gradient(self._h, a.ctypes.data, len(a), out.ctypes.data, g.ctypes.data))
         return out, g
+
+    def QueryRay(self, origins, directions, t_max):
+        """Octree::QueryRay (Octree.cpp:705-746) for a batch of rays -> (hit flags, t). Mirrors the reference statement by statement."""
+        self._need()
+        o = np.ascontiguousarray(origins, np.float64).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, np.float64).reshape(-1, 3)
+        assert len(o) == len(d)
+        hit = np.zeros(len(o), np.uint8)
+        t = np.zeros(len(o), np.float64)
+        _check(lib().hpsdf_query_ray(self._h, o.ctypes.data, d.ctypes.data, len(o), float(t_max), hit.ctypes.data, t.ctypes.data))
+        return hit.astype(bool), t
 
     def OutputFunctionSlice(self, fname, c, view_min, view_max, n_samples=2048):
         """Octree::OutputFunctionSlice (Octree.cpp:1132-1205): the z = c slice of the field over viewArea as an n x n grid of

@@ -179,6 +179,28 @@ extern "C"
         return HPSDF_OK;
     }
 
+    HPSDF_API hpsdf_status hpsdf_query_ray(const hpsdf_octree* tree, const double* origins, const double* directions, size_t n, double t_max,
+                                           unsigned char* hit, double* t)
+    {
+        if (!tree || (n && (!origins || !directions || !hit || !t))) { setLastError("null pointer"); return HPSDF_ERR_INVALID_ARG; }
+        if (!n) return HPSDF_OK;
+        HPSDF_CUDA(cudaSetDevice(tree->device));
+        double *dO = nullptr, *dD = nullptr, *dT = nullptr;
+        unsigned char* dH = nullptr;
+        HPSDF_CUDA(cudaMalloc((void**)&dO, n * 24));
+        cudaError_t e = cudaMalloc((void**)&dD, n * 24);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&dT, n * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&dH, n);
+        if (e == cudaSuccess) e = cudaMemcpy(dO, origins, n * 24, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dD, directions, n * 24, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = launchQueryRay(tree->view, dO, dD, n, t_max, dH, dT, nullptr);
+        if (e == cudaSuccess) e = cudaMemcpy(hit, dH, n, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(t, dT, n * 8, cudaMemcpyDeviceToHost);
+        cudaFree(dO); cudaFree(dD); cudaFree(dT); cudaFree(dH);
+        if (e != cudaSuccess) return failCuda(e, "hpsdf_query_ray");
+        return HPSDF_OK;
+    }
+
     HPSDF_API hpsdf_status hpsdf_to_memory_block(const hpsdf_octree* tree, size_t* size, void** ptr)
     {
         if (!tree || !size || !ptr) { setLastError("null pointer"); return HPSDF_ERR_INVALID_ARG; }

@@ -65,6 +65,14 @@ namespace hpsdf
         return cudaGetLastError();
     }
 
+    cudaError_t launchQueryRay(const DeviceTreeView& view, const double* dOrigins, const double* dDirs, size_t n, double tMax,
+                               unsigned char* dHit, double* dT, cudaStream_t stream)
+    {
+        if (!n) return cudaSuccess;
+        queryRayKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(view, dOrigins, dDirs, n, tMax, dHit, dT);
+        return cudaGetLastError();
+    }
+
     cudaError_t launchGatherSegments(const double* src, double* dst, const uint32_t* srcOff, const uint32_t* dstOff,
                                      const uint32_t* count, uint32_t nSeg, cudaStream_t stream)
     {

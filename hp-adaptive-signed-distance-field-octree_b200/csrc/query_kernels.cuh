@@ -132,4 +132,70 @@ namespace hpsdf
         double* d = dst + dstOff[seg];
         for (uint32_t i = lane; i < count[seg]; i += 32) d[i] = s[i];
     }
+
+    // Octree::QueryRay (Source/HP/Octree.cpp:705-746) + Ray::Ray / Ray::IntersectAABB (Source/HP/Ray.cpp:5-65), one ray per
+    // thread, statement by statement — including what the reference does with its own intermediate results: the origin is
+    // moved into the unit cube but the direction is not rescaled (:713); when the origin is outside the root, the vector the
+    // march starts from is the `a_` output of IntersectAABB, whose x component holds the entry PARAMETER and whose y, z
+    // components hold the slab parameters of those axes (:715-719, Ray.cpp:27-61), not a point; every sample goes through
+    // Query, which applies the root map a second time (:729, :665); `t_` receives the last field value, not a distance
+    // (:733). For the default root box and origins inside it these coincide with sphere tracing of the field.
+    __global__ void __launch_bounds__(256)
+    queryRayKernel(const DeviceTreeView view, const double* __restrict__ origins, const double* __restrict__ dirs, size_t n,
+                   const double tMax, unsigned char* __restrict__ hit, double* __restrict__ tOut)
+    {
+        const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n) return;
+        constexpr unsigned MAX_STEPS = 200;
+        constexpr double eps = 0.0001, minStep = 0.0001;
+        const RootMap& map = view.map;
+        double o[3], dir[3], inv[3];
+        int sign[3];
+        for (int a = 0; a < 3; ++a)
+        {
+            o[a] = (origins[3 * i + a] - map.centre[a]) * map.invSizes[a];                     // :713
+            dir[a] = dirs[3 * i + a];
+            inv[a] = 1.0 / dir[a];                                                              // Ray.cpp:10
+            sign[a] = inv[a] < 0.0;                                                             // Ray.cpp:11-13
+        }
+        double intMin[3] = { o[0], o[1], o[2] };
+        const float fx = (float)o[0], fy = (float)o[1], fz = (float)o[2];
+        const bool inside = fx >= -0.5f && fx <= 0.5f && fy >= -0.5f && fy <= 0.5f && fz >= -0.5f && fz <= 0.5f;      // nodes[0].aabb.contains
+        bool ok = true;
+        if (!inside)
+        {
+            const double bounds[2] = { -0.5, 0.5 };
+            double a_[3] = { o[0], o[1], o[2] }, b_[3] = { 0.0, 0.0, 0.0 };
+            a_[0] = (bounds[sign[0]] - o[0]) * inv[0];     b_[0] = (bounds[1 - sign[0]] - o[0]) * inv[0];     // Ray.cpp:27-30
+            a_[1] = (bounds[sign[1]] - o[1]) * inv[1];     b_[1] = (bounds[1 - sign[1]] - o[1]) * inv[1];
+            if ((a_[0] > b_[1]) || (a_[1] > b_[0])) ok = false;                                                // :32-35
+            if (ok)
+            {
+                if (a_[1] > a_[0]) a_[0] = a_[1];                                                              // :37-40
+                if (b_[1] < b_[0]) b_[0] = b_[1];                                                              // :42-45
+                a_[2] = (bounds[sign[2]] - o[2]) * inv[2]; b_[2] = (bounds[1 - sign[2]] - o[2]) * inv[2];     // :47-48
+                if ((a_[0] > b_[2]) || (a_[2] > b_[0])) ok = false;                                            // :50-53
+                if (ok)
+                {
+                    if (a_[2] > a_[0]) a_[0] = a_[2];                                                          // :55-58
+                    intMin[0] = a_[0]; intMin[1] = a_[1]; intMin[2] = a_[2];
+                }
+            }
+        }
+        unsigned char h = 0;
+        double t = 0.0;
+        if (ok)
+        {
+            double d = 0.0;
+            for (unsigned s = 0; s < MAX_STEPS; ++s)
+            {
+                const double v = queryPoint(view.nodes, view.coeffs, view.top, map, intMin[0] + d * dir[0], intMin[1] + d * dir[1], intMin[2] + d * dir[2]);
+                if (v < eps) { t = v; h = 1; break; }                                           // :731-736
+                d += v * 0.95 + minStep;                                                        // :739
+                if (d > tMax) break;                                                            // :741-744
+            }
+        }
+        hit[i] = h;
+        tOut[i] = t;
+    }
 }

@@ -207,6 +207,12 @@ HPSDF_API hpsdf_status hpsdf_query_device(const hpsdf_octree* tree, const double
 /* Octree::QueryWithGradient (Octree.cpp:749-789, 904-985): value + unit central-difference gradient. */
 HPSDF_API hpsdf_status hpsdf_query_with_gradient(const hpsdf_octree* tree, const double* xyz, size_t n, double* out, double* unit_grad);
 
+/* Octree::QueryRay (Octree.cpp:705-746, Ray.cpp:5-65) for n rays: origins / directions n x 3 f64, hit n bytes (1 = the march
+ * reached a field value below 1e-4 within 200 steps and t_max), t n f64 (the reference stores the last field value there).
+ * Statement-by-statement mirror of the reference, see query_kernels.cuh for what that implies outside the default root box. */
+HPSDF_API hpsdf_status hpsdf_query_ray(const hpsdf_octree* tree, const double* origins, const double* directions, size_t n, double t_max,
+                                       unsigned char* hit, double* t);
+
 /* Octree::ToMemoryBlock (Octree.cpp:424-456): *ptr is malloc()ed, the CALLER free()s it. LP64 layout. */
 HPSDF_API hpsdf_status hpsdf_to_memory_block(const hpsdf_octree* tree, size_t* size, void** ptr);
 /* Octree::FromMemoryBlock (Octree.cpp:403-421): copies; the caller keeps ownership of the block. */

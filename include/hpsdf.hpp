@@ -2,7 +2,7 @@
 //
 // Mirrors (names, argument meaning, ownership) of jw007123/hp-Adaptive-Signed-Distance-Field-Octree:
 //     SDF::Config                 Include/HP/Config.h:12-43        (same members, same 80-byte LP64 image)
-//     SDF::Octree                 Include/HP/Octree.h:36-86        Create / Query / QueryWithGradient / UnionSDF /
+//     SDF::Octree                 Include/HP/Octree.h:36-86        Create / Query / QueryWithGradient / QueryRay / UnionSDF /
 //                                                                  SubtractSDF / IntersectSDF / Clear / FromMemoryBlock /
 //                                                                  ToMemoryBlock / GetRootAABB, copy + move
 //     MemoryBlock                 Include/Utility/MemoryBlock.h:5-9
@@ -93,6 +93,9 @@ namespace SDF
     static_assert(sizeof(Config) == sizeof(hpsdf_config) && sizeof(Config) == 80, "SDF::Config must keep the reference's 80-byte layout");
 
     class Octree;
+
+    /// R(t) = O + t * D with |D| = 1 (Include/HP/Ray.h:10-24)
+    struct Ray { Vec3d origin, direction; };
 
     // Device SDF: postfix program of primitives and boolean operators (see hpsdf.h).
     class Program
@@ -192,6 +195,23 @@ namespace SDF
             check(hpsdf_query_with_gradient(need(), xyz, 1, &out, g));
             unitNormal_ = V3{ g[0], g[1], g[2] };
             return out;
+        }
+
+        /// Sphere-traces the field along a ray (Octree.cpp:705-746); `Ray` is anything with .origin and .direction (x()/y()/z()),
+        /// e.g. SDF::Ray below or the reference's own struct
+        template <class RayT> bool QueryRay(const RayT& ray_, const double tMax_, double& t_) const
+        {
+            const double o[3] = { ray_.origin.x(), ray_.origin.y(), ray_.origin.z() };
+            const double d[3] = { ray_.direction.x(), ray_.direction.y(), ray_.direction.z() };
+            unsigned char hit = 0;
+            double t = 0.0;
+            check(hpsdf_query_ray(need(), o, d, 1, tMax_, &hit, &t));
+            if (hit) t_ = t;                                             // the reference writes t_ only when it returns true (:733)
+            return hit != 0;
+        }
+        void QueryRay(const double* origins_, const double* directions_, size_t n_, double tMax_, unsigned char* hit_, double* t_) const
+        {
+            check(hpsdf_query_ray(need(), origins_, directions_, n_, tMax_, hit_, t_));
         }
 
         /// The aabb of the root node (Octree.cpp:106-109)

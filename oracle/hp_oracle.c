@@ -939,6 +939,61 @@ void hporacle_query(void* h, const double* xyz, size_t n, double* out, int threa
     for (long i = 0; i < (long)n; ++i) out[i] = query_one(t, xyz + 3 * i);
 }
 
+/* Octree::QueryRay (Octree.cpp:705-746) with Ray::Ray (Ray.cpp:5-14) and Ray::IntersectAABB (Ray.cpp:17-65), statement by
+ * statement: the origin is mapped into the unit cube, the direction is not (:713); outside the root the march starts from the
+ * a_ output of IntersectAABB (entry parameter in x, slab parameters in y and z) (:715-719); samples go through Query (:729). */
+void hporacle_query_ray(void* h, const double* origins, const double* dirs, size_t n, double tMax, unsigned char* hit, double* tOut)
+{
+    const Tree* t = (const Tree*)h;
+    for (size_t r = 0; r < n; ++r)
+    {
+        double o[3], dir[3], inv[3], intMin[3];
+        int sign[3];
+        for (int a = 0; a < 3; ++a)
+        {
+            o[a] = (origins[3 * r + a] - t->rootCentre[a]) * t->rootInvSizes[a];
+            dir[a] = dirs[3 * r + a];
+            inv[a] = 1.0 / dir[a];
+            sign[a] = inv[a] < 0.0;
+            intMin[a] = o[a];
+        }
+        const Box* root = &t->nodes[0].aabb;
+        int inside = 1, ok = 1;
+        for (int a = 0; a < 3; ++a) { const float f = (float)o[a]; if (!(root->mn[a] <= f && f <= root->mx[a])) inside = 0; }
+        if (!inside)
+        {
+            const double bounds[2][3] = { { root->mn[0], root->mn[1], root->mn[2] }, { root->mx[0], root->mx[1], root->mx[2] } };
+            double a_[3] = { o[0], o[1], o[2] }, b_[3] = { 0.0, 0.0, 0.0 };
+            a_[0] = (bounds[sign[0]][0] - o[0]) * inv[0];     b_[0] = (bounds[1 - sign[0]][0] - o[0]) * inv[0];
+            a_[1] = (bounds[sign[1]][1] - o[1]) * inv[1];     b_[1] = (bounds[1 - sign[1]][1] - o[1]) * inv[1];
+            if ((a_[0] > b_[1]) || (a_[1] > b_[0])) ok = 0;
+            if (ok)
+            {
+                if (a_[1] > a_[0]) a_[0] = a_[1];
+                if (b_[1] < b_[0]) b_[0] = b_[1];
+                a_[2] = (bounds[sign[2]][2] - o[2]) * inv[2]; b_[2] = (bounds[1 - sign[2]][2] - o[2]) * inv[2];
+                if ((a_[0] > b_[2]) || (a_[2] > b_[0])) ok = 0;
+                if (ok)
+                {
+                    if (a_[2] > a_[0]) a_[0] = a_[2];
+                    intMin[0] = a_[0]; intMin[1] = a_[1]; intMin[2] = a_[2];
+                }
+            }
+        }
+        hit[r] = 0; tOut[r] = 0.0;
+        if (!ok) continue;
+        double d = 0.0;
+        for (unsigned s = 0; s < 200; ++s)
+        {
+            const double p[3] = { intMin[0] + d * dir[0], intMin[1] + d * dir[1], intMin[2] + d * dir[2] };
+            const double v = query_one(t, p);
+            if (v < 0.0001) { tOut[r] = v; hit[r] = 1; break; }
+            d += v * 0.95 + 0.0001;
+            if (d > tMax) break;
+        }
+    }
+}
+
 void hporacle_query_gradient(void* h, const double* xyz, size_t n, double* out, double* grad, int threads)
 {
     const Tree* t = (const Tree*)h;

@@ -81,6 +81,7 @@ def lib(fast=False):
     L.hpref_block_copy.argtypes = [C.c_void_p, C.c_void_p]
     L.hpref_query.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
     L.hpref_query_gradient.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+    L.hpref_query_ray.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_void_p, C.c_void_p]
     L.hpref_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.hpref_apply_log.argtypes = [C.c_void_p, C.c_void_p]
     L.hpref_fit.restype = C.c_double
@@ -142,6 +143,14 @@ class RefTree:
         g = np.empty((len(pts), 3), dtype=np.float64)
         self.L.hpref_query_gradient(self.h, pts.ctypes.data, len(pts), out.ctypes.data, g.ctypes.data, threads)
         return out, g
+
+    def query_ray(self, origins, dirs, t_max):
+        o = np.ascontiguousarray(origins, np.float64)
+        d = np.ascontiguousarray(dirs, np.float64)
+        hit = np.zeros(len(o), np.uint8)
+        t = np.zeros(len(o), np.float64)
+        self.L.hpref_query_ray(self.h, o.ctypes.data, d.ctypes.data, len(o), float(t_max), hit.ctypes.data, t.ctypes.data)
+        return hit.astype(bool), t
 
     def stats(self):
         s = np.zeros(10)

@@ -344,6 +344,19 @@ extern "C"
             out_[i] = o.Query(Eigen::Vector3d(xyz_[3 * i], xyz_[3 * i + 1], xyz_[3 * i + 2]));
     }
 
+    // Octree::QueryRay (Octree.cpp:705-746) on the reference's own code
+    void hpref_query_ray(void* h_, const double* origins_, const double* dirs_, size_t n_, double tMax_, unsigned char* hit_, double* t_)
+    {
+        const SDF::Octree& o = ((RefTree*)h_)->oct;
+        for (size_t i = 0; i < n_; ++i)
+        {
+            const SDF::Ray ray(Eigen::Vector3d(origins_[3 * i], origins_[3 * i + 1], origins_[3 * i + 2]), Eigen::Vector3d(dirs_[3 * i], dirs_[3 * i + 1], dirs_[3 * i + 2]));
+            double t = 0.0;
+            hit_[i] = o.QueryRay(ray, tMax_, t) ? 1 : 0;
+            t_[i] = t;
+        }
+    }
+
     void hpref_query_gradient(void* h_, const double* xyz_, size_t n_, double* out_, double* grad_, int threads_)
     {
         const SDF::Octree& o = ((RefTree*)h_)->oct;

@@ -126,6 +126,14 @@ int main()
         try { t.Create(baseConfig(false), [](const Vec3d&, unsigned long) { return 0.0; }); ok = false; } catch (const SDF::Error& e) { ok = ok && e.status == HPSDF_ERR_UNSUPPORTED; }
         report("Error behaviour", ok);
     }
+    {   // QueryRay (Octree.cpp:705-746): a ray from inside the root towards the sphere stops on it, one pointing away misses
+        SDF::Octree t;
+        t.Create(baseConfig(false), sphereProg);
+        double tHit = -1.0, tMiss = -1.0;
+        const bool hit = t.QueryRay(SDF::Ray{ Vec3d{ { -0.45, 0.0, 0.0 } }, Vec3d{ { 1.0, 0.0, 0.0 } } }, 2.0, tHit);
+        const bool miss = t.QueryRay(SDF::Ray{ Vec3d{ { -0.45, 0.4, 0.4 } }, Vec3d{ { -1.0, 0.0, 0.0 } } }, 2.0, tMiss);
+        report("QueryRay", hit && tHit < 0.0001 && !miss && tMiss == -1.0);
+    }
     {   // Meshing::Mesh as an SDF source (MeshingUnitTests-style): a regular octahedron |x|+|y|+|z| = 0.3, exact SDF known
         const float r = 0.3f;
         const float verts[18] = { r, 0, 0,  -r, 0, 0,  0, r, 0,  0, -r, 0,  0, 0, r,  0, 0, -r };

@@ -339,3 +339,20 @@ def test_sdf_operations_match_min_max_of_analytic(hp):
         t.Create(cfg, hp.SdfProgram(a))
         getattr(t, op)(hp.SdfProgram(b))
         assert np.abs(t.Query(pts) - truth).max() <= 0.05, op
+
+
+@pytest.mark.parametrize("name", ["sphere_poly_1e8", "custom_domain", "c2_csg"])
+def test_query_ray_matches_oracle(hp, oracle, built, name):
+    """Octree::QueryRay mirrored statement by statement (query_kernels.cuh: queryRayKernel): hit flags equal, t within the
+    Query tolerance; a ray may differ only where a marched value sits within 1e-9 of a decision threshold (none expected)."""
+    from oracle import hpref
+    from test_oracle_vs_ref import ray_batch
+    t = built(name)
+    o = oracle.OracleTree.from_block(t.ToMemoryBlockBytes())
+    org, d = ray_batch(CASES[name]["cfg"], 50000, 5)
+    for t_max in (0.3, 10.0):
+        hg, tg = t.QueryRay(org, d, t_max)
+        ho, to = o.query_ray(org, d, t_max)
+        differ = hg != ho
+        assert differ.sum() <= 2, differ.sum()
+        assert np.abs(tg - to)[~differ].max() <= QUERY_TOL

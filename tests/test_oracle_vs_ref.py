@@ -104,3 +104,35 @@ def test_mesh_distance_bit_identical(ref, oracle):
         lo2, hi2 = mesh_root(v2)
         p2 = np.random.default_rng(1).uniform(lo2, hi2, (4000, 3)).astype(np.float32)
         assert np.array_equal(rm2.sdf(p2, True, 8), om2.sdf(p2, True, 8))
+
+
+def ray_batch(cfg_kwargs, n, seed):
+    """Rays for QueryRay: origins inside and outside the root box, unit directions (some axis-aligned: 1/0 = inf in Ray::Ray)."""
+    rng = np.random.default_rng(seed)
+    mn = np.asarray(cfg_kwargs.get("root_min", (-0.5,) * 3), np.float64)
+    mx = np.asarray(cfg_kwargs.get("root_max", (0.5,) * 3), np.float64)
+    c, e = (mn + mx) / 2, (mx - mn)
+    o = c + rng.uniform(-0.9, 0.9, (n, 3)) * e
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    d[: n // 20] = np.eye(3)[rng.integers(0, 3, n // 20)] * rng.choice([-1.0, 1.0], (n // 20, 1))
+    aim = rng.random(n) < 0.5                         # half of them aimed at the middle of the box
+    t = (c + rng.uniform(-0.2, 0.2, (n, 3)) * e) - o
+    d[aim] = (t / np.linalg.norm(t, axis=1)[:, None])[aim]
+    return o, d
+
+
+@pytest.mark.parametrize("name", ["sphere_exp_1e8", "custom_domain"])
+def test_query_ray_bit_identical(ref, oracle, name):
+    """Octree::QueryRay (Octree.cpp:705-746): the restatement against the reference's own code, hit flags and t bit for bit —
+    on the default root box and on a custom one, where the reference's double root mapping shows."""
+    cfg, prog = oracle_cfg(ref, name)
+    r = ref.RefTree.build(cfg, prog, mode=1, threads=8)
+    o = oracle.OracleTree.build(cfg, prog, threads=8)
+    org, d = ray_batch(CASES[name]["cfg"], 20000, 3)
+    for t_max in (0.3, 10.0):
+        hr, tr = r.query_ray(org, d, t_max)
+        ho, to = o.query_ray(org, d, t_max)
+        assert np.array_equal(hr, ho) and np.array_equal(tr, to)
+        if name == "sphere_exp_1e8":
+            assert 0 < hr.sum() < len(hr)          # (on the custom root box the reference's double mapping makes every ray miss)
