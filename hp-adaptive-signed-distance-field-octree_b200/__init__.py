@@ -124,6 +124,7 @@ EXPORTS = [
     "hpsdf_get_root_aabb", "hpsdf_destroy", "hpsdf_get_build_stats", "hpsdf_get_decision_log", "hpsdf_get_apply_log", "hpsdf_fit_batch",
     "hpsdf_bench_frontier", "hpsdf_measure_fp64_peak", "hpsdf_comm_get_unique_id", "hpsdf_comm_init",
     "hpsdf_comm_destroy", "hpsdf_shard_range", "hpsdf_set_jit", "hpsdf_jit_compile_check", "hpsdf_query_ray",
+    "hpsdf_get_config", "hpsdf_get_device", "hpsdf_uniform_points_device",
 ]
 
 _lib = None
@@ -171,6 +172,8 @@ def lib():
     L.hpsdf_get_root_aabb.argtypes = [vp, vp, vp]
     L.hpsdf_destroy.argtypes = [vp]
     L.hpsdf_destroy.restype = None
+    L.hpsdf_get_config.argtypes = [vp, C.POINTER(Config)]
+    L.hpsdf_get_device.argtypes = [vp, C.POINTER(i32)]
     L.hpsdf_get_build_stats.argtypes = [vp, C.POINTER(BuildStats)]
     L.hpsdf_get_decision_log.argtypes = [vp, vp, sz]
     L.hpsdf_get_decision_log.restype = sz
@@ -179,6 +182,7 @@ def lib():
     L.hpsdf_fit_batch.argtypes = [C.POINTER(Config), C.POINTER(_Program), vp, vp, sz, u32, vp, vp, i32, C.POINTER(C.c_float)]
     L.hpsdf_bench_frontier.argtypes = [C.POINTER(Config), C.POINTER(_Program), u32, u32, u32, i32, vp, C.POINTER(FrontierBench)]
     L.hpsdf_measure_fp64_peak.argtypes = [i32, vp, C.POINTER(dbl)]
+    L.hpsdf_uniform_points_device.argtypes = [C.c_uint64, C.c_uint64, sz, C.POINTER(dbl), C.POINTER(dbl), vp, vp]
     L.hpsdf_comm_get_unique_id.argtypes = [vp]
     L.hpsdf_comm_init.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
     L.hpsdf_comm_destroy.argtypes = [vp]
@@ -427,12 +431,27 @@ class Octree:
 
     # -- SDF boolean operations (Octree.cpp:355-400): re-Create from min/max of the old tree's Query and F ----------------
     def _combine(self, F, op, opts=None):
+        """opts (BuildOpts) carries max_degree / max_depth / ...; the rebuild runs on the old tree's device unless opts.device
+        names one. A failed rebuild leaves the tree as it was."""
         self._need()
         old = Octree()
         old._h, self._h = self._h, None
-        cfg = parse_block(old.ToMemoryBlockBytes())["config"]
-        prog = SdfProgram(list(F.items) + [("octree", [], old), (op, [])])
-        self.Create(cfg, prog, opts)
+        try:
+            cfg = Config()
+            _check(lib().hpsdf_get_config(old._h, C.byref(cfg)))
+            o = BuildOpts()
+            if opts is not None:
+                C.memmove(C.byref(o), C.byref(opts), C.sizeof(BuildOpts))
+            if o.device < 0:
+                dev = C.c_int()
+                _check(lib().hpsdf_get_device(old._h, C.byref(dev)))
+                o.device = dev.value
+            prog = SdfProgram(list(F.items) + [("octree", [], old), (op, [])])
+            self.Create(cfg, prog, o)
+        except Exception:
+            self.Clear()
+            self._h, old._h = old._h, None
+            raise
         old.Clear()
 
     def UnionSDF(self, F, opts=None):
@@ -518,6 +537,12 @@ def jit_compile_check(F, degree):
     n = C.c_size_t()
     _check(lib().hpsdf_jit_compile_check(C.byref(F._c), degree, buf, len(buf), C.byref(n)))
     return buf.value.decode(), n.value
+
+
+def uniform_points_device(seed, first_index, n, lo, hi, d_xyz_ptr, stream=None):
+    """Philox4x32-10 points (key = seed, counter = global point index) uniform in [lo, hi) into a device buffer of n x 3 f64."""
+    _check(lib().hpsdf_uniform_points_device(seed, first_index, n, (C.c_double * 3)(*[float(v) for v in lo]),
+                                             (C.c_double * 3)(*[float(v) for v in hi]), d_xyz_ptr, stream))
 
 
 def measure_fp64_peak(device=-1, stream=None):

@@ -122,6 +122,7 @@ namespace hpsdf
             int         rank_ = 0, world_ = 1;
             double      sdfFlops_ = 0.0;
             double      launchMs_ = 0.0;           // host time spent in upload / launch calls (diagnostics)
+            size_t      strictSteps_ = 0, levelCalls_ = 0;   // diagnostics: strictly sequential pops; guaranteed-level computations
             bool        progHasExt_ = false;       // the program samples a mesh or another octree
             hpsdf_decision_log_entry lastApplied_{};      // last job applied before the termination cut
             double      lastTotal_ = 0.0, totalBeforeLast_ = 0.0;
@@ -465,6 +466,7 @@ namespace hpsdf
             const double tSel0 = nowMs();
             const double inf = std::numeric_limits<double>::infinity();
             const double thr = cfg_.target_error_threshold;
+            ++levelCalls_;
             levelLogStart_ = t_.applyLog.size();
             applyLevel_ = inf;
             double remaining = checkValue();
@@ -655,6 +657,7 @@ namespace hpsdf
                     const std::pair<uint64_t, double> top = queue_.top();                                // Octree.cpp:231: the overall maximum
                     hPop();
                     applyJob(top.first, top.second);          // strict step; the state after it is a sequential-greedy state
+                    ++strictSteps_;
                     applyLevel_ = inf;                        // a level is only valid for the state it was computed in
                     levelTried_ = false;
                     continue;
@@ -801,7 +804,7 @@ namespace hpsdf
                 if (pendCount_ == 0) { setLastError("internal: replay stalled with nothing to evaluate"); st = HPSDF_ERR_CUDA; break; }
                 if (++stallGuard > 100000) { setLastError("internal: build does not converge"); st = HPSDF_ERR_CUDA; break; }
             }
-            if (getenv("HPSDF_DEBUG_ROUNDS")) fprintf(stderr, "launch calls %.3f ms\n", launchMs_);
+            if (getenv("HPSDF_DEBUG_ROUNDS")) fprintf(stderr, "launch calls %.3f ms, strict steps %zu, level computations %zu, applied %zu\n", launchMs_, strictSteps_, levelCalls_, t_.applyLog.size());
             const double tPack0 = nowMs();
             if (st == HPSDF_OK) st = pack();
             t_.stats.pack_ms = nowMs() - tPack0;

@@ -156,6 +156,10 @@ extern "C"
     HPSDF_API hpsdf_status hpsdf_query_device(const hpsdf_octree* tree, const double* d_xyz, size_t n, double* d_out, void* stream)
     {
         if (!tree || (n && (!d_xyz || !d_out))) { setLastError("null pointer"); return HPSDF_ERR_INVALID_ARG; }
+        // the kernel reads the tree's device pointers: it must run on the tree's device (the caller's stream belongs to it)
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != tree->device)
+        { setLastError("hpsdf_query_device: the current CUDA device is not the tree's device"); return HPSDF_ERR_INVALID_ARG; }
         HPSDF_CUDA(launchQuery(tree->view, d_xyz, n, d_out, tree->ctx->smCount, (cudaStream_t)stream));
         return HPSDF_OK;
     }
@@ -250,6 +254,20 @@ extern "C"
         return HPSDF_OK;
     }
 
+    HPSDF_API hpsdf_status hpsdf_get_config(const hpsdf_octree* tree, hpsdf_config* cfg)
+    {
+        if (!tree || !cfg) { setLastError("null pointer"); return HPSDF_ERR_INVALID_ARG; }
+        *cfg = tree->cfg;
+        return HPSDF_OK;
+    }
+
+    HPSDF_API hpsdf_status hpsdf_get_device(const hpsdf_octree* tree, int* device)
+    {
+        if (!tree || !device) { setLastError("null pointer"); return HPSDF_ERR_INVALID_ARG; }
+        *device = tree->device;
+        return HPSDF_OK;
+    }
+
     HPSDF_API void hpsdf_destroy(hpsdf_octree* tree) { delete tree; }
 
     HPSDF_API hpsdf_status hpsdf_get_build_stats(const hpsdf_octree* tree, hpsdf_build_stats* stats)
@@ -301,6 +319,9 @@ extern "C"
         SdfProgramDev dp;
         if ((st = resolveProgram(prog, ctx->device, dp)) != HPSDF_OK) return st;
         if (!n) return HPSDF_OK;
+        for (size_t i = 0; i < n; ++i)            // c_nl has kMaxDepth + 1 columns; a cell needs a positive size
+            if (depth[i] > (uint8_t)kMaxDepth || !(cells[4 * i + 3] > 0.0f))
+            { setLastError("hpsdf_fit_batch: depth above TREE_MAX_DEPTH or non-positive half size"); return HPSDF_ERR_INVALID_ARG; }
         RootMap map;
         setRootMap(*cfg, map);
         const size_t nc = (size_t)coeffCount((int)degree);
@@ -420,6 +441,15 @@ extern "C"
         out->sdf_flops_per_eval = cF;
         out->algorithmic_flops = (double)nH * fitFlops((int)degree) + (double)nP * fitFlops((int)degree + 1) + cF * (double)out->sdf_evals;
         for (const FitRecord& r : recs) out->checksum += r.rawErr;
+        return HPSDF_OK;
+    }
+
+    HPSDF_API hpsdf_status hpsdf_uniform_points_device(uint64_t seed, uint64_t first_index, size_t n, const double lo[3], const double hi[3],
+                                                       double* d_xyz, void* stream)
+    {
+        if (n && (!lo || !hi || !d_xyz)) { setLastError("null pointer"); return HPSDF_ERR_INVALID_ARG; }
+        if (hpsdf_device_count() == 0) { setLastError("no CUDA device available: this library has no CPU path"); return HPSDF_ERR_NO_DEVICE; }
+        HPSDF_CUDA(launchUniformPoints(seed, first_index, n, lo, hi, d_xyz, (cudaStream_t)stream));
         return HPSDF_OK;
     }
 

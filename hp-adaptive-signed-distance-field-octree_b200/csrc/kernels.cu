@@ -17,6 +17,7 @@ namespace hpsdf
 #include "fit_kernels.cuh"
 #include "query_kernels.cuh"
 #include "continuity_kernels.cuh"
+#include "points_kernel.cuh"
 
 namespace hpsdf
 {

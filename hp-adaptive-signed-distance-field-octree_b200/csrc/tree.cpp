@@ -231,7 +231,7 @@ namespace hpsdf
             }
             else
             {
-                if (n.child + 8 > nn || n.child <= i) { setLastError("MemoryBlock: child index out of range"); return HPSDF_ERR_BAD_BLOCK; }
+                if (n.child >= nn || nn - n.child < 8 || n.child <= i) { setLastError("MemoryBlock: child index out of range"); return HPSDF_ERR_BAD_BLOCK; }
                 for (uint32_t c = 0; c < 8; ++c)
                 {
                     float mn[3], mx[3];

@@ -221,6 +221,10 @@ HPSDF_API hpsdf_status hpsdf_from_memory_block(const void* ptr, size_t size, int
 HPSDF_API hpsdf_status hpsdf_clone(const hpsdf_octree* tree, hpsdf_octree** out);
 /* Octree::GetRootAABB (Octree.cpp:106-109). */
 HPSDF_API hpsdf_status hpsdf_get_root_aabb(const hpsdf_octree* tree, float mn[3], float mx[3]);
+/* The Config the tree was created with (what the reference keeps in Octree::config, Octree.h:91, and writes at the end of a
+ * MemoryBlock) and the CUDA device its storage lives on. */
+HPSDF_API hpsdf_status hpsdf_get_config(const hpsdf_octree* tree, hpsdf_config* cfg);
+HPSDF_API hpsdf_status hpsdf_get_device(const hpsdf_octree* tree, int* device);
 /* Octree::~Octree / Clear (Octree.cpp:15-21, 459-471). */
 HPSDF_API void hpsdf_destroy(hpsdf_octree* tree);
 
@@ -320,6 +324,12 @@ HPSDF_API hpsdf_status hpsdf_bench_frontier(const hpsdf_config* cfg, const hpsdf
  * source_out (may be NULL) receives the generated translation unit, cubin_bytes (may be NULL) the size of the cubin. */
 HPSDF_API hpsdf_status hpsdf_jit_compile_check(const hpsdf_sdf_program* prog, uint32_t degree, char* source_out, size_t source_cap,
                                                size_t* cubin_bytes);
+
+/* The synthetic Query workload of BASELINE config 5: n points uniform in [lo, hi) written to d_xyz (n x 3 f64,
+ * DEVICE pointer, current device, asynchronous on `stream`), point i = Philox4x32-10(key = seed, counter = first_index + i),
+ * 53-bit mantissas. A point depends only on (seed, global index): any sharding or chunking evaluates the same set. */
+HPSDF_API hpsdf_status hpsdf_uniform_points_device(uint64_t seed, uint64_t first_index, size_t n, const double lo[3], const double hi[3],
+                                                   double* d_xyz, void* stream);
 
 /* FP64 FMA peak of the device measured with a register-resident DFMA chain (TFLOP/s); the roofline
  * denominator for fitting, which MEASURED_PEAKS.json does not hold. */

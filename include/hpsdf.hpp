@@ -153,9 +153,11 @@ namespace SDF
         }
 
         /// Resultant SDF = Min(oldF, F_) / Max(F_, -oldF) / Max(oldF, F_)   (Octree.cpp:355-400)
-        void UnionSDF(const Program& F_)     { combine(F_, HPSDF_OP_UNION); }
-        void SubtractSDF(const Program& F_)  { combine(F_, HPSDF_OP_SUBTRACT); }
-        void IntersectSDF(const Program& F_) { combine(F_, HPSDF_OP_INTERSECT); }
+        /// opts_ (optional) carries what the reference fixes at compile time (max degree / depth, ...); the rebuild runs on the
+        /// old tree's device unless opts_->device names one. If the rebuild fails the tree is left as it was.
+        void UnionSDF(const Program& F_, const hpsdf_build_opts* opts_ = nullptr)     { combine(F_, HPSDF_OP_UNION, opts_); }
+        void SubtractSDF(const Program& F_, const hpsdf_build_opts* opts_ = nullptr)  { combine(F_, HPSDF_OP_SUBTRACT, opts_); }
+        void IntersectSDF(const Program& F_, const hpsdf_build_opts* opts_ = nullptr) { combine(F_, HPSDF_OP_INTERSECT, opts_); }
 
         /// Resets the tree (Octree.cpp:459-471)
         void Clear() { if (h_) hpsdf_destroy(h_); h_ = nullptr; }
@@ -223,17 +225,26 @@ namespace SDF
     private:
         hpsdf_octree* h_ = nullptr;
         const hpsdf_octree* need() const { if (!h_) throw Error(HPSDF_ERR_INVALID_ARG, "octree is empty"); return h_; }
-        void combine(const Program& F_, uint32_t op_)
+        void combine(const Program& F_, uint32_t op_, const hpsdf_build_opts* opts_)
         {
             Octree oldTree = std::move(*this);                          // keeps the old tree alive until Create returns (Octree.cpp:366)
-            MemoryBlock b = oldTree.ToMemoryBlock();
-            Config cfg;
-            std::memcpy(static_cast<void*>(&cfg), (const char*)b.ptr + b.size - sizeof(Config), sizeof(Config));
-            free(b.ptr);
-            Program p;
-            p.Append(F_).Tree(oldTree);
-            if (op_ == HPSDF_OP_UNION) p.Union(); else if (op_ == HPSDF_OP_INTERSECT) p.Intersect(); else p.Subtract();
-            Create(cfg, p);
+            try
+            {
+                Config cfg;
+                check(hpsdf_get_config(oldTree.need(), reinterpret_cast<hpsdf_config*>(&cfg)));
+                hpsdf_build_opts o;
+                if (opts_) o = *opts_; else hpsdf_build_opts_default(&o);
+                if (o.device < 0) check(hpsdf_get_device(oldTree.need(), &o.device));
+                Program p;
+                p.Append(F_).Tree(oldTree);
+                if (op_ == HPSDF_OP_UNION) p.Union(); else if (op_ == HPSDF_OP_INTERSECT) p.Intersect(); else p.Subtract();
+                Create(cfg, p, &o);
+            }
+            catch (...)
+            {
+                *this = std::move(oldTree);                             // a failed rebuild leaves the tree as it was
+                throw;
+            }
         }
     };
 

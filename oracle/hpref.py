@@ -87,6 +87,8 @@ def lib(fast=False):
     L.hpref_fit.restype = C.c_double
     L.hpref_fit.argtypes = [C.POINTER(Config), C.POINTER(Instr), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                             C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.hpref_fit_chain_batch.argtypes = [C.POINTER(Config), C.POINTER(Instr), C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.hpref_tables.argtypes = [C.c_void_p] * 7
     L.hpref_continuity_triplets.restype = C.c_size_t
     L.hpref_continuity_triplets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -192,6 +194,22 @@ def ref_fit(cfg, prog, aabb_min, aabb_max, degree, depth, degree_in=0, coeffs_in
     err = L.hpref_fit(C.byref(cfg), prog, len(prog), mn.ctypes.data, mx.ctypes.data, degree_in, cin.ctypes.data,
                       degree, depth, out.ctypes.data)
     return out, err
+
+
+def ref_fit_chain_batch(cfg, prog, aabb_min, aabb_max, d0, d1, depth, threads=1, fast=False, kept_degree=None):
+    """Leaf histories replayed with the reference's FitPolynomial (OpenMP over leaves): from scratch at d0[i], then kept-shell
+    fits up to d1[i]. Returns (list of coefficient arrays, raw errors of the last fits)."""
+    L = lib(fast)
+    mn = np.ascontiguousarray(aabb_min, np.float32).reshape(-1, 3)
+    mx = np.ascontiguousarray(aabb_max, np.float32).reshape(-1, 3)
+    n = len(mn)
+    a0, a1, dp = (np.ascontiguousarray(x, np.uint32) for x in (d0, d1, depth))
+    out = np.zeros((n, 455))
+    err = np.zeros(n)
+    kd = np.ascontiguousarray(kept_degree, np.uint32) if kept_degree is not None else None
+    L.hpref_fit_chain_batch(C.byref(cfg), prog, len(prog), n, mn.ctypes.data, mx.ctypes.data, a0.ctypes.data, a1.ctypes.data,
+                            dp.ctypes.data, kd.ctypes.data if kd is not None else None, out.ctypes.data, err.ctypes.data, threads)
+    return [out[i, :NCOEF[int(a1[i])]].copy() for i in range(n)], err
 
 
 def ref_tables(fast=False):

@@ -85,13 +85,17 @@ namespace
     #endif
     }
 
+    // threadIdx_ the reference hands to F (Octree.h:50): its own pool threads are std::threads, not OpenMP threads, and
+    // Mesh::SignedDistanceAtPt needs a distinct per-thread BVH queue (BVH.cpp:253-258)
+    thread_local int g_callerThread = -1;
+
     double extEval(uint32_t op, const void* handle, const double x[3])
     {
         if (op == HPSDF_PRIM_MESH)
         {
             RefMesh* m = (RefMesh*)handle;
             const Eigen::Vector3f p((float)x[0], (float)x[1], (float)x[2]);
-            return m->hasBvh ? (double)m->mesh.SignedDistanceAtPt(p, m->bvh, (u32)currentThread())
+            return m->hasBvh ? (double)m->mesh.SignedDistanceAtPt(p, m->bvh, (u32)(g_callerThread >= 0 ? g_callerThread : currentThread()))
                              : (double)m->mesh.SignedDistanceAtPt(p);
         }
         if (op == HPSDF_PRIM_OCTREE)
@@ -106,9 +110,10 @@ namespace
     {
         const hpsdf_sdf_instr* instr = prog.data();
         const uint32_t n = (uint32_t)prog.size();
-        return [instr, n](const Eigen::Vector3d& pt_, const u32) -> f64
+        return [instr, n](const Eigen::Vector3d& pt_, const u32 threadIdx_) -> f64
         {
             const double x[3] = { pt_.x(), pt_.y(), pt_.z() };
+            g_callerThread = (int)threadIdx_;
             return hporacle_sdf_eval(instr, n, x, extEval);
         };
     }
@@ -414,6 +419,46 @@ extern "C"
         if (degreeIn_ > 0) memcpy(coeffsOut_, coeffsIn_, sizeof(f64) * LegendreCoeffientCount[degreeIn_]);
         const Eigen::AlignedBox3f aabb(Eigen::Vector3f(aabbMin_[0], aabbMin_[1], aabbMin_[2]), Eigen::Vector3f(aabbMax_[0], aabbMax_[1], aabbMax_[2]));
         return o.FitPolynomial(b, aabb, (u8)degree_, depth_, 0);
+    }
+
+    // The history of n leaves replayed with the reference's own FitPolynomial, one leaf per OpenMP thread: a from-scratch fit at
+    // degree d0_[i] (Octree.cpp:820 child fit / :840 coarse fit), then one kept-shell fit per degree up to d1_[i] (:846-851).
+    // coeffsOut_: n x 455 doubles (row i holds N_{d1[i]} coefficients), errOut_: raw top-shell energy of the last fit.
+    // keptDegree_ (may be null): where non-zero, the first fit of leaf i is itself a kept-shell fit on top of the degree
+    // keptDegree_[i] coefficients already in row i (a p-fit on its own, as a timing sample of EstimatePImprovement, :829-856).
+    void hpref_fit_chain_batch(const hpsdf_config* cfg_, const hpsdf_sdf_instr* prog_, uint32_t nInstr_, size_t n_,
+                               const float* aabbMin_, const float* aabbMax_, const uint32_t* d0_, const uint32_t* d1_,
+                               const uint32_t* depth_, const uint32_t* keptDegree_, double* coeffsOut_, double* errOut_, int threads_)
+    {
+        using namespace SDF;
+        RefTree t;
+        t.prog.assign(prog_, prog_ + nInstr_);
+        Octree& o = t.oct;
+        o.config = toConfig(cfg_);
+        o.config.nearnessWeighting.type = Config::NearnessWeighting::None;
+        const Eigen::Vector3d centre     = o.config.root.center().cast<f64>();
+        const Eigen::Vector3d rootBounds = o.config.root.sizes().cast<f64>();
+        auto userF = makeF(t.prog);
+        o.F = [userF, centre, rootBounds](const Eigen::Vector3d& pt_, const u32 threadIdx_) -> f64
+        {
+            return userF(pt_.cwiseProduct(rootBounds) + centre, threadIdx_);
+        };
+        #pragma omp parallel for schedule(dynamic, 1) num_threads(threads_) if (threads_ > 1)
+        for (long i = 0; i < (long)n_; ++i)
+        {
+            Node::Basis b;
+            b.coeffs = coeffsOut_ + 455 * (size_t)i;
+            b.degree = keptDegree_ ? (u8)keptDegree_[i] : (u8)0;
+            const Eigen::AlignedBox3f aabb(Eigen::Vector3f(aabbMin_[3 * i], aabbMin_[3 * i + 1], aabbMin_[3 * i + 2]),
+                                           Eigen::Vector3f(aabbMax_[3 * i], aabbMax_[3 * i + 1], aabbMax_[3 * i + 2]));
+            double e = 0.0;
+            for (uint32_t d = d0_[i]; d <= d1_[i]; ++d)
+            {
+                e = o.FitPolynomial(b, aabb, (u8)d, depth_[i], (u32)currentThread());
+                b.degree = (u8)d;
+            }
+            errOut_[i] = e;
+        }
     }
 
     // Reference constant tables (Include/HP/Utility.h, Include/HP/Legendre.h) for pinning the restatement's own tables.

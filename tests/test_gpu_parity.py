@@ -267,6 +267,12 @@ def test_bad_blocks_are_rejected(hp, built):
     raw2[off:off + 8] = np.uint64(10 ** 9).tobytes()                    # child index out of range
     with pytest.raises(hp.HpsdfError):
         hp.Octree().FromMemoryBlock(hp.MemoryBlock.frombytes(bytes(raw2)))
+    for wrap in (2 ** 64 - 8, 2 ** 64 - 2):                             # child + 8 wraps around in u64: still rejected, not indexed
+        raw3 = bytearray(raw)
+        raw3[off:off + 8] = np.uint64(wrap).tobytes()
+        with pytest.raises(hp.HpsdfError) as e:
+            hp.Octree().FromMemoryBlock(hp.MemoryBlock.frombytes(bytes(raw3)))
+        assert e.value.status == hp.ERR_BAD_BLOCK
 
 
 def test_query_edge_cases(hp, oracle, built):
@@ -325,20 +331,72 @@ def test_large_batch_properties(hp, oracle, built):
     assert float(out.abs().max()) < 2.0                                 # all inside the root: no DBL_MAX
 
 
-def test_sdf_operations_match_min_max_of_analytic(hp):
-    """Octree::UnionSDF / IntersectSDF / SubtractSDF (Octree.cpp:355-400) with the reference's own test tolerance
-    (HPUnitTests.cpp:207-282: |d| <= 0.05 against min/max of the analytic spheres, nearness None)."""
+def compare_with_oracle_tree(hp, t, o, cfg_kwargs, n_pts=100000, seed=5):
+    """GPU tree `t` against oracle tree `o`: identical canonical topology (outside the logged tie group at the cut),
+    per-leaf coefficients to COEFF_TOL, Query to QUERY_TOL. Returns (worst coefficient error, divergent cells)."""
+    from oracle import hpref
+    a, b = hp.parse_block(t.ToMemoryBlockBytes()), hpref.parse_block(o.block())
+    assert a["n_nodes"] == b["n_nodes"] and a["n_coeffs"] == b["n_coeffs"], (a["n_nodes"], b["n_nodes"], a["n_coeffs"], b["n_coeffs"])
+    pa, da, ga, ca = leaf_table(a, hp.COEFF_COUNT)
+    pb, db, gb, cb = leaf_table(b, hp.COEFF_COUNT)
+    ma = {(path_code(p), int(d)): i for i, (p, d) in enumerate(zip(pa, da))}
+    mb = {(path_code(p), int(d)): i for i, (p, d) in enumerate(zip(pb, db))}
+    div = divergent_cells({k: int(ga[i]) for k, i in ma.items()}, {k: int(gb[i]) for k, i in mb.items()})
+    allowed, _ = logged_cut_group(t)
+    for code, d in div:
+        assert cell_of(code, d) in allowed, ("unlogged divergence", cell_of(code, d), t.decision_log()[-6:])
+    assert np.array_equal(np.bincount(ga, minlength=13), np.bincount(gb, minlength=13))
+    worst = max(rel_inf(ca[i], cb[mb[k]]) for k, i in ma.items() if k in mb and k not in div)
+    assert worst <= COEFF_TOL, worst
+    pts = root_points(cfg_kwargs, n_pts, seed=seed, margin=0.01)
+    qa, qb = t.Query(pts), o.query(pts, 8)
+    assert np.array_equal(qa == hp.DBL_MAX, qb == hp.DBL_MAX)
+    ok = (qb != hp.DBL_MAX) & ~points_in_cells(pts, cfg_kwargs, allowed if div else set())
+    assert np.abs(qa - qb)[ok].max() <= QUERY_TOL
+    return worst, len(div)
+
+
+@pytest.mark.parametrize("op", ["UnionSDF", "IntersectSDF", "SubtractSDF"])
+def test_sdf_operations_match_oracle(hp, oracle, op):
+    """Octree::UnionSDF / IntersectSDF / SubtractSDF (Octree.cpp:355-400) = re-Create from min / max of the old tree's
+    Query and the new F. The configuration is the reference's own test (HPUnitTests.cpp:207-282: two radius-0.5 spheres at
+    x = +-0.25, threshold 1e-8, nearness None, continuity off). The CPU oracle rebuilds from the SAME old tree (the
+    GPU-built one, read through FromMemoryBlock) as its OCTREE primitive, so both sides approximate the same function:
+    identical topology, coefficients to 1e-10, Query to 1e-9; the reference's 0.05 bound against the analytic min / max
+    is kept as well."""
+    from oracle import hpref
+    kw = dict(threshold=1e-8, nearness=0, strength=0.0, continuity=False)
     cfg = hp.Config(target_error_threshold=1e-8, continuity_enforce=0)
     a = [("sphere", [0.25, 0.0, 0.0, 0.5])]
-    b = [("sphere", [-0.25, 0.0, 0.0, 0.3])]
+    b = [("sphere", [-0.25, 0.0, 0.0, 0.5])]
+    t = hp.Octree()
+    t.Create(cfg, hp.SdfProgram(a))
+    old = oracle.OracleTree.from_block(t.ToMemoryBlockBytes())
+    name = dict(UnionSDF="union", IntersectSDF="intersect", SubtractSDF="subtract")[op]
+    o = oracle.OracleTree.build(hpref.make_config(threads=8, **kw), hpref.make_program(b + [("octree", [], old.h), (name, [])]), threads=8)
+    getattr(t, op)(hp.SdfProgram(b))
+    worst, ndiv = compare_with_oracle_tree(hp, t, o, kw)
     pts = np.random.default_rng(2).uniform(-0.5, 0.5, (100000, 3))
     fa = np.linalg.norm(pts - [0.25, 0, 0], axis=1) - 0.5
-    fb = np.linalg.norm(pts - [-0.25, 0, 0], axis=1) - 0.3
-    for op, truth in (("UnionSDF", np.minimum(fa, fb)), ("IntersectSDF", np.maximum(fa, fb)), ("SubtractSDF", np.maximum(fb, -fa))):
-        t = hp.Octree()
-        t.Create(cfg, hp.SdfProgram(a))
-        getattr(t, op)(hp.SdfProgram(b))
-        assert np.abs(t.Query(pts) - truth).max() <= 0.05, op
+    fb = np.linalg.norm(pts + [0.25, 0, 0], axis=1) - 0.5
+    truth = dict(UnionSDF=np.minimum(fa, fb), IntersectSDF=np.maximum(fa, fb), SubtractSDF=np.maximum(-fa, fb))[op]
+    assert np.abs(t.Query(pts) - truth).max() <= 0.05
+    print(op, "nodes", t.stats()["n_nodes"], "coeffs", t.stats()["n_coeffs"], "worst", worst, "divergent (logged)", ndiv)
+
+
+def test_sdf_operation_keeps_build_options_and_survives_failure(hp):
+    """The rebuild honours the caller's BuildOpts (max degree) and a failed rebuild leaves the tree as it was."""
+    cfg = hp.Config(target_error_threshold=1e-6, continuity_enforce=0)
+    t = hp.Octree()
+    t.Create(cfg, hp.SdfProgram([("sphere", [0.25, 0.0, 0.0, 0.5])]), hp.BuildOpts(max_degree=3))
+    t.UnionSDF(hp.SdfProgram([("sphere", [-0.25, 0.0, 0.0, 0.5])]), hp.BuildOpts(max_degree=3))
+    blk = hp.parse_block(t.ToMemoryBlockBytes())
+    leaf = blk["nodes"]["child"] == np.uint64(0xFFFFFFFFFFFFFFFF)
+    assert blk["nodes"]["deg"][leaf].max() <= 3
+    before = t.ToMemoryBlockBytes()
+    with pytest.raises(hp.HpsdfError):
+        t.UnionSDF(hp.SdfProgram([("torus", [0, 0, 0, 0.3, 0.1, 7])]))      # bad axis: the program does not resolve
+    assert t.ToMemoryBlockBytes() == before
 
 
 @pytest.mark.parametrize("name", ["sphere_poly_1e8", "custom_domain", "c2_csg"])
