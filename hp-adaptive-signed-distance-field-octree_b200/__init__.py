@@ -64,7 +64,7 @@ class BuildOpts(C.Structure):
                 ("nearness_mode", C.c_uint32), ("total_mode", C.c_uint32), ("cg_max_iterations", C.c_uint32),
                 ("cg_tolerance", C.c_double), ("device", C.c_int32), ("speculate", C.c_uint32),
                 ("strict_order", C.c_uint32), ("comm", C.c_void_p), ("stream", C.c_void_p),
-                ("jit", C.c_uint32), ("min_round_jobs", C.c_uint32)]
+                ("jit", C.c_uint32), ("min_round_jobs", C.c_uint32), ("scheduler", C.c_uint32)]
 
     def __init__(self, **kw):
         super().__init__()

@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include "octree.h"
 #include "comm.h"
+#include "build_common.h"
 
 namespace hpsdf
 {
@@ -675,79 +676,15 @@ namespace hpsdf
             return done;
         }
 
-        // Near-threshold divergence log (BASELINE north_star): the greedy loop stops in the middle of a run of leaves whose
-        // errors are equal to rounding (mirror-symmetric cells have errors equal to the last bits). WHICH of them were
-        // refined before the cut depends on the last bits, so another implementation of the same algorithm may refine
-        // other members of the group. Log the whole group: kind 2 = refined before the cut, kind 3 = left unrefined.
         void Builder::logCutTies()
         {
-            if (t_.applyLog.empty() || (queue_.empty() && pendCount_ == 0)) return;
-            // the sequential loop's last pop is the smallest-error entry applied since the last sequential state
-            double eLast = t_.applyLog.back().initial_err;
-            for (size_t k = std::min(levelLogStart_, t_.applyLog.size() - 1); k < t_.applyLog.size(); ++k) eLast = std::min(eLast, t_.applyLog[k].initial_err);
-            if (!(eLast > 0.0) || std::abs(eLast - kInitialErr) < 1e-9) return;
-            // errors of the members of a symmetric group agree to ~1e-10 relative (they are sums of squares of top-shell
-            // coefficients that carry ~1e-16 |c000| of rounding each); the same noise separates two implementations
-            const double band = 3e-9 * eLast;
-            auto entry = [&](uint64_t idx, uint32_t degree, uint32_t kind, double err)
-            {
-                hpsdf_decision_log_entry e{};
-                e.node_idx = idx; e.depth = nodes_[idx].depth; e.degree = degree; e.kind = kind; e.chose_p = 0;
-                for (int a = 0; a < 3; ++a) e.centre[a] = (nodes_[idx].mn[a] + nodes_[idx].mx[a]) / 2.0f;
-                e.relative_margin = std::fabs(err - eLast) / eLast;
-                t_.decisionLog.push_back(e);
-            };
-            size_t refined = 0, unrefined = 0;
-            for (size_t k = t_.applyLog.size(); k-- > 0;)
-            {
-                const hpsdf_apply_log_entry& a = t_.applyLog[k];
-                if (std::fabs(a.initial_err - eLast) > band) continue;
-                entry(a.node_idx, a.degree, 2u, a.initial_err);
-                t_.decisionLog.back().chose_p = a.kind == 0;
-                ++refined;
-            }
-            for (uint64_t idx = 0; idx < nodes_.size(); ++idx)
-                if (nodes_[idx].child == kNoChild && std::fabs(errOf_[idx] - eLast) <= band) { entry(idx, nodes_[idx].degree, 3u, errOf_[idx]); ++unrefined; }
-            if (unrefined == 0)
-            {
-                // nothing was left behind: the cut does not fall inside a tie group, drop the kind-2 entries again
-                t_.decisionLog.resize(t_.decisionLog.size() - refined);
-            }
+            logCutTieGroup(t_, errOf_, levelLogStart_, queue_.empty() && pendCount_ == 0);
         }
 
         // ReallocCoeffs (Octree.cpp:474-555): DFS from the root's children by child slot; leaves packed in visiting order.
         hpsdf_status Builder::pack()
         {
-            std::vector<uint32_t> srcOff, dstOff, count;
-            size_t cur = 0;
-            std::vector<uint64_t> stack;
-            for (int i = 7; i >= 0; --i) stack.push_back(nodes_[0].child + (uint64_t)i);
-            while (!stack.empty())
-            {
-                const uint64_t idx = stack.back(); stack.pop_back();
-                HostNode& n = nodes_[idx];
-                if (n.child == kNoChild)
-                {
-                    const uint32_t c = (uint32_t)coeffCount(n.degree);
-                    srcOff.push_back(n.slot); dstOff.push_back((uint32_t)cur); count.push_back(c);
-                    n.cstart = cur; cur += c;
-                }
-                else for (int i = 7; i >= 0; --i) stack.push_back(n.child + (uint64_t)i);
-            }
-            t_.nCoeffs = cur;
-            const uint32_t nSeg = (uint32_t)srcOff.size();
-            hpsdf_status st = allocTreeBlob(t_);
-            if (st != HPSDF_OK) return st;
-            HPSDF_CUDA(ws_.segs.reserve(3 * (size_t)nSeg + 16));
-            HPSDF_CUDA(ws_.hSegs.reserve(3 * (size_t)nSeg + 16));
-            memcpy(ws_.hSegs.p, srcOff.data(), nSeg * 4);
-            memcpy(ws_.hSegs.p + nSeg, dstOff.data(), nSeg * 4);
-            memcpy(ws_.hSegs.p + 2 * (size_t)nSeg, count.data(), nSeg * 4);
-            HPSDF_CUDA(cudaMemcpyAsync(ws_.segs.p, ws_.hSegs.p, 3 * (size_t)nSeg * 4, cudaMemcpyHostToDevice, stream_));
-            HPSDF_CUDA(launchGatherSegments(pool_.p, t_.dCoeffs, ws_.segs.p, ws_.segs.p + nSeg, ws_.segs.p + 2 * (size_t)nSeg, nSeg, stream_));
-            t_.stats.kernel_launches++;
-            HPSDF_CUDA(cudaStreamSynchronize(stream_));       // the pinned segment staging is reused by finalizeQueryStructures
-            return HPSDF_OK;
+            return packCoefficients(t_, pool_.p, stream_);
         }
 
         hpsdf_status Builder::run()
@@ -844,7 +781,9 @@ namespace hpsdf
         }
     }
 
-    hpsdf_status buildOctree(hpsdf_octree& t, const hpsdf_build_opts& opts, const SdfProgramDev& prog)
+    // Octree::Create with the greedy loop replayed on the host (hpsdf_build_opts.scheduler = 1, or strict_order): the round-1
+    // implementation, kept as the cross-check of the device-resident scheduler (build_device.cpp) and for strict node numbering.
+    hpsdf_status buildOctreeHost(hpsdf_octree& t, const hpsdf_build_opts& opts, const SdfProgramDev& prog)
     {
         Builder b(t, opts, prog);
         return b.run();

@@ -70,6 +70,7 @@ namespace hpsdf
         cudaStream_t         stream = nullptr;
         cudaEvent_t          ev0 = nullptr, ev1 = nullptr;
         size_t               lastNodeCount = 0;          // nodes of the previous build (vector reservations of the next)
+        void*                sched = nullptr;            // SchedWorkspace of the device-resident scheduler (build_device.cpp)
         // the fit launches of a round (one per degree) are independent: they fan out over these and join again
         cudaStream_t         aux[4] = { nullptr, nullptr, nullptr, nullptr };
         cudaEvent_t          evFork = nullptr, evJoin[4] = { nullptr, nullptr, nullptr, nullptr };

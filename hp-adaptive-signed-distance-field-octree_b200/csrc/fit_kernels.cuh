@@ -181,6 +181,44 @@ namespace hpsdf
         tasks[pos] = o;
     }
 
+    // the same with the round layout read from device memory (written by the device-resident scheduler, sched_kernels.cuh)
+    __global__ void expandJobsDevKernel(const JobDesc* __restrict__ jobs, uint32_t nJobs, const RoundLayout* __restrict__ lay, FitTask* __restrict__ tasks)
+    {
+        const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+        const uint32_t ji = t / 9u, c = t - ji * 9u;
+        if (ji >= nJobs) return;
+        const JobDesc j = jobs[ji];
+        FitTask o;
+        int d;
+        uint32_t pos;
+        if (c < 8u)
+        {
+            if (!(j.flags & 1u)) return;
+            const float q = j.half * 0.5f;
+            d = j.degree; pos = j.hPos + c;
+            o.cx = j.cx + ((c & 1u) ? q : -q); o.cy = j.cy + ((c & 2u) ? q : -q); o.cz = j.cz + ((c & 4u) ? q : -q); o.half = q;
+            o.src = kNoSrc; o.depth = (uint8_t)(j.depth + 1); o.degreeIn = 0;
+        }
+        else
+        {
+            if (!(j.flags & 6u)) return;
+            const bool coarse = (j.flags & 4u) != 0;
+            d = coarse ? kCoarseDegree : j.degree + 1; pos = j.pPos;
+            o.cx = j.cx; o.cy = j.cy; o.cz = j.cz; o.half = j.half;
+            o.src = coarse ? kNoSrc : j.src; o.depth = j.depth; o.degreeIn = coarse ? 0 : j.degree;
+        }
+        o.out = lay->groupPool[d] + (pos - lay->groupBegin[d]) * (uint32_t)coeffCount(d);
+        o.degree = (uint8_t)d; o.pad = 0; o.rec = pos;
+        tasks[pos] = o;
+    }
+
+    cudaError_t launchExpandJobsDev(const JobDesc* dJobs, uint32_t nJobs, const RoundLayout* dLayout, FitTask* dTasks, cudaStream_t stream)
+    {
+        if (!nJobs) return cudaSuccess;
+        expandJobsDevKernel<<<(nJobs * 9u + 255u) / 256u, 256, 0, stream>>>(dJobs, nJobs, dLayout, dTasks);
+        return cudaGetLastError();
+    }
+
     cudaError_t launchExpandJobs(const JobDesc* dJobs, uint32_t nJobs, const RoundLayout& layout, FitTask* dTasks, cudaStream_t stream)
     {
         if (!nJobs) return cudaSuccess;

@@ -18,6 +18,7 @@ namespace hpsdf
 #include "query_kernels.cuh"
 #include "continuity_kernels.cuh"
 #include "points_kernel.cuh"
+#include "sched_kernels.cuh"
 
 namespace hpsdf
 {
@@ -191,6 +192,21 @@ namespace hpsdf
         if (e == cudaSuccess) e = cudaMemcpyAsync(hostResult, P.result, 16, cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         return e;
+    }
+
+    cudaError_t launchSchedRound(const SchedDev& S, const uint16_t* coarseOrder, cudaStream_t stream)
+    {
+        static bool attrSet[16] = { false };
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attrSet[dev & 15])
+        {
+            const cudaError_t e = cudaFuncSetAttribute(schedRoundKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSchedDynSmem);
+            if (e != cudaSuccess) return e;
+            attrSet[dev & 15] = true;
+        }
+        schedRoundKernel<<<1, kSchedThreads, kSchedDynSmem, stream>>>(S, coarseOrder);
+        return cudaGetLastError();
     }
 
     cudaError_t launchMeshDistance(const DeviceMeshView* dView, const float* dXyz, size_t n, float* dOut, cudaStream_t stream)

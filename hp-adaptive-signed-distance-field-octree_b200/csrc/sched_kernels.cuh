@@ -1,0 +1,955 @@
+// sched_kernels.cuh — the greedy build loop of Octree::Create on the device (state: sched.h, host driver: build_device.cpp).
+//
+// Reference: RunBuildThreadPool (Source/HP/Octree.cpp:194-309) + the decision of TickBuildThread (:558-659) with
+// EstimateHImprovement / EstimatePImprovement (:804-856). One launch of schedRoundKernel per round (a single CTA of 1024
+// threads: every step is a scan, a compaction or a histogram walk over a few thousand entries, and block-wide barriers cost
+// 100x less than grid-wide ones):
+//
+//   ingest   the fit records of the round -> weighted errors of the 8 child fits and the p-fit of every evaluated job
+//   passes   repeat: (a) from a sequential-greedy state, find the GUARANTEED LEVEL with the error histogram — taking the
+//            queue in decreasing order e1 >= e2 >= ..., entry k is certain to be popped before termination if
+//            total - (e1 + ... + e_{k-1}) >= threshold, because popping an entry and any of its descendants lowers the total
+//            by at most that entry's error; descendants with a larger error are popped even earlier — and apply every
+//            cached job at or above it in one data-parallel step (decision, child allocation by prefix sum, error
+//            bookkeeping); (b) where the histogram guarantees nothing more, sort the head of the queue (up to 1024 entries)
+//            and walk it exactly: with all head jobs cached and no new child overtaking the rest of the head, the prefix sums
+//            of the exact decreases reproduce the sequential loop, including the step at which it terminates
+//   select   warp-aggregated compaction of the open list; leaves at or above the level (plus the next-largest pending errors
+//            up to min_round_jobs) become the jobs of the next round, grouped by degree with deterministic task positions
+//
+// Determinism: allocation offsets come from prefix sums in list order, histogram updates are integer atomics, floating-point
+// reductions have a fixed shape — so the ranks of a multi-GPU build, which all run this kernel on replicated data, stay
+// bit-identical without exchanging anything but fit results.
+#pragma once
+#include <cfloat>
+#include "hp_common.h"
+#include "sched.h"
+
+namespace hpsdf
+{
+    // ---- keys and histogram buckets -----------------------------------------------------------------------------------
+    __device__ __forceinline__ unsigned long long errKey(double e) { return e > 0.0 ? (unsigned long long)__double_as_longlong(e) : 0ull; }
+    __device__ __forceinline__ int subOfKey(unsigned long long key) { return ((int)(key >> 52) + 78) * kSubPerOctave + (int)((key >> 48) & 15ull); }
+    __device__ __forceinline__ double subLowerEdge(int sub)
+    {
+        const long long E = (long long)(sub / kSubPerOctave) - 78;
+        if (E < 0) return 0.0;
+        return __longlong_as_double((long long)(((unsigned long long)E << 52) | ((unsigned long long)(sub % kSubPerOctave) << 48)));
+    }
+    // integer upper bound of an error in units of 2^(max(E,1) - 1054): 32 significant bits, rounded up
+    __device__ __forceinline__ unsigned long long errUnits(unsigned long long key)
+    {
+        const unsigned long long m = (key & 0xFFFFFFFFFFFFFull) | ((key >> 52) ? (1ull << 52) : 0ull);
+        return (m >> 21) + 1ull;
+    }
+    __device__ __forceinline__ double subUnit(int sub)
+    {
+        const int E = sub / kSubPerOctave - 78;
+        return ldexp(1.0, (E < 1 ? 1 : E) - 1054);
+    }
+
+    struct SchedShared
+    {
+        // working copies of the counters (written back at the end of the launch)
+        uint32_t nNodes, nOpen, nJobs, nCached, poolUsed, done, topSub, nLog, nDecision, appliedP, appliedH, retired, nearTies;
+        uint32_t passes, windowPasses, lastPassLogStart;
+        double   total, exactSum, totalBeforeLast, lastTotal;
+        unsigned long long levelKey;   // guaranteed level in force (error key; ~0 = sequential-greedy state, no level) ...
+        uint32_t levelNode;            // ... and, for a level that splits a group of equal keys, the last node index included (kNone: all)
+        int      aboveLevel;           // open entries at or above the level that are not refined yet
+        // block-wide scratch
+        double   warpD[32];
+        uint32_t warpU[32];
+        unsigned long long warpL[32];
+        uint32_t tmpU[8];
+        double   tmpD[4];
+        int      tmpI[4];
+    };
+
+    // ---- block-wide primitives (1024 threads, fixed shape => deterministic floating-point results) -------------------------
+    __device__ __forceinline__ uint32_t blockExclScanU(uint32_t v, uint32_t* sWarp, uint32_t& total)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        uint32_t x = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) sWarp[warp] = x;
+        __syncthreads();
+        if (warp == 0)
+        {
+            uint32_t w = sWarp[lane];
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o); if (lane >= o) w += y; }
+            sWarp[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t base = warp ? sWarp[warp - 1] : 0u;
+        total = sWarp[31];
+        __syncthreads();
+        return base + x - v;
+    }
+
+    __device__ __forceinline__ double blockInclScanD(double v, double* sWarp, double& total)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        double x = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) sWarp[warp] = x;
+        __syncthreads();
+        if (warp == 0)
+        {
+            double w = sWarp[lane];
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(0xFFFFFFFFu, w, o); if (lane >= o) w += y; }
+            sWarp[lane] = w;
+        }
+        __syncthreads();
+        const double base = warp ? sWarp[warp - 1] : 0.0;
+        total = sWarp[31];
+        __syncthreads();
+        return base + x;
+    }
+
+    __device__ __forceinline__ uint32_t blockMinU(uint32_t v, uint32_t* sWarp)
+    {
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+        if ((threadIdx.x & 31) == 0) sWarp[threadIdx.x >> 5] = v;
+        __syncthreads();
+        uint32_t r = sWarp[threadIdx.x & 31];
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r = min(r, __shfl_xor_sync(0xFFFFFFFFu, r, o));
+        __syncthreads();
+        return r;
+    }
+
+    __device__ __forceinline__ int blockSumI(int v, uint32_t* sWarp)
+    {
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if ((threadIdx.x & 31) == 0) sWarp[threadIdx.x >> 5] = (uint32_t)v;
+        __syncthreads();
+        int r = (int)sWarp[threadIdx.x & 31];
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, o);
+        __syncthreads();
+        return r;
+    }
+
+    constexpr unsigned long long kNoLevel = ~0ull;
+    __device__ __forceinline__ bool atOrAbove(const SchedShared& sh, unsigned long long key, uint32_t node)
+    {
+        return sh.levelKey != kNoLevel && (key > sh.levelKey || (key == sh.levelKey && node <= sh.levelNode));
+    }
+
+    // ---- histogram updates (integer atomics only) -------------------------------------------------------------------------
+    __device__ __forceinline__ void histAdd(const SchedDev& S, SchedShared& sh, double e, bool pending)
+    {
+        const unsigned long long key = errKey(e);
+        const int sub = subOfKey(key);
+        atomicAdd(S.allCnt + sub, 1u);
+        atomicAdd(S.allSum + sub, errUnits(key));
+        if (pending) atomicAdd(S.pendCnt + sub, 1u);
+        atomicMax(&sh.topSub, (uint32_t)sub);
+    }
+    __device__ __forceinline__ void histRemove(const SchedDev& S, double e)
+    {
+        const unsigned long long key = errKey(e);
+        const int sub = subOfKey(key);
+        atomicSub(S.allCnt + sub, 1u);
+        atomicAdd(S.allSum + sub, 0ull - errUnits(key));
+    }
+
+    // Nearness weight from the exact cell mean c000 * NL[0][depth]^3 (Octree.cpp:1209-1247 in the limit of many samples; the
+    // expressions of build.cpp / the CPU checker, evaluated with CUDA's exp / pow: <= 2 ulp from the host libm, i.e. below the
+    // 1e-15 relative difference the GPU fit itself has against the CPU one)
+    __device__ __forceinline__ double nearnessWeightDev(const SchedDev& S, double c0, uint32_t depth)
+    {
+        if (S.nearnessType == HPSDF_NEARNESS_NONE) return 1.0;
+        const double nl = c_nl[0][depth];
+        const double m = fabs(__dmul_rn(c0, __dmul_rn(__dmul_rn(nl, nl), nl)));
+        const double d = sqrt(3.0);
+        if (S.nearnessType == HPSDF_NEARNESS_POLYNOMIAL)
+        {
+            const double k = pow(__dsub_rn(1.0, __ddiv_rn(m, d)), S.nearnessStrength);
+            const double kk = (k < 0.0) ? 0.0 : k;              // std::max<double>(k, 0.0)
+            return (kk < 1.0) ? kk : 1.0;                        // std::min<double>(1.0, .)
+        }
+        return exp(__ddiv_rn(__dmul_rn(__dmul_rn(-1.0, S.nearnessStrength), m), d));
+    }
+
+    // The h-vs-p decision of one cached job (Octree.cpp:600-601, 825, 854 with BASIS_MAX_DEGREE-1 -> maxDegree,
+    // TREE_MAX_DEPTH -> maxDepth): kind 0 = the node leaves the queue, 1 = p-refinement, 2 = h-refinement.
+    struct Decision
+    {
+        int    kind;
+        double delta;       // decrease of the total: err - (sum of the new errors)
+        double maxNew;      // largest new error
+        double pImp, hImp;
+        bool   nearTie;
+        double margin;
+    };
+
+    __device__ __forceinline__ Decision decideJob(const SchedDev& S, uint32_t j, double err, uint32_t p, uint32_t depth)
+    {
+        Decision D;
+        const double* E = S.jobErr + 9 * (size_t)j;
+        const uint8_t flags = S.jobFlags[j];
+        const bool doH = flags & 1u, doP = flags & 2u;
+        double maxNew = 0.0, sumH = 0.0;
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) { const double h = doH ? E[i] : 0.0; maxNew = (maxNew < h) ? h : maxNew; sumH = __dadd_rn(sumH, h); }
+        const double pErr = doP ? E[8] : 0.0;
+        D.hImp = doH ? __dmul_rn(__ddiv_rn(1.0, __dmul_rn(7.0, (double)coeffCount((int)p))), __dsub_rn(err, __dmul_rn(8.0, maxNew))) : 0.0;
+        D.pImp = doP ? __dmul_rn(__ddiv_rn(1.0, (double)(coeffCount((int)p + 1) - coeffCount((int)p))), __dsub_rn(err, __dmul_rn(8.0, pErr))) : 0.0;
+        const bool refineP = p < S.maxDegree && (depth == S.maxDepth || D.pImp > D.hImp);
+        const bool refineH = depth < S.maxDepth && !refineP;
+        D.kind = refineP ? 1 : (refineH ? 2 : 0);
+        D.delta = refineP ? __dsub_rn(err, pErr) : (refineH ? __dsub_rn(err, sumH) : 0.0);
+        D.maxNew = refineP ? pErr : (refineH ? maxNew : 0.0);
+        D.nearTie = false; D.margin = 0.0;
+        if (doH && doP)
+        {
+            const double mag = fmax(fabs(D.pImp), fabs(D.hImp));
+            D.margin = mag > 0.0 ? fabs(D.pImp - D.hImp) / mag : 0.0;
+            D.nearTie = D.margin <= 1e-9;
+        }
+        return D;
+    }
+
+    // Apply the cached jobs list[0 .. n) in list order (all threads call this). Body of the reference's output-drain loop
+    // (Octree.cpp:245-297): degree / slot / error updates for P, Subdivide + 8 children for H, total bookkeeping, log.
+    __device__ void applyJobs(const SchedDev& S, SchedShared& sh, const uint32_t* list, uint32_t n)
+    {
+        const int tid = threadIdx.x;
+        for (uint32_t base = 0; base < n; base += kSchedThreads)
+        {
+            const uint32_t i = base + tid;
+            const bool active = i < n;
+            uint32_t j = kNone, node = 0, p = 0, depth = 0;
+            double err = 0.0;
+            Decision D;
+            D.kind = 0; D.delta = 0.0; D.maxNew = 0.0; D.pImp = D.hImp = 0.0; D.nearTie = false; D.margin = 0.0;
+            if (active)
+            {
+                j = list[i];
+                node = S.jobNode[j]; p = S.degree[node]; depth = S.depth[node]; err = S.err[node];
+                D = decideJob(S, j, err, p, depth);
+            }
+            uint32_t totalChildren = 0, totalLogged = 0;
+            const uint32_t childOff = blockExclScanU(active && D.kind == 2 ? 8u : 0u, sh.warpU, totalChildren);
+            const uint32_t logOff = blockExclScanU(active && D.kind != 0 ? 1u : 0u, sh.warpU, totalLogged);
+            double chunkDelta = 0.0;
+            const double inclDelta = blockInclScanD(active ? D.delta : 0.0, sh.warpD, chunkDelta);
+            const bool fits = sh.nNodes + totalChildren <= S.capNodes && sh.nOpen + totalChildren <= S.capNodes &&
+                              sh.nLog + totalLogged <= S.capLog;
+            if (!fits) { if (tid == 0) sh.done = 2u; __syncthreads(); return; }
+            int aboveDelta = 0;
+            if (active)
+            {
+                const double* E = S.jobErr + 9 * (size_t)j;
+                S.jobFlags[j] |= 128u;
+                S.jobOf[node] = kNone;
+                histRemove(S, err);
+                if (atOrAbove(sh, errKey(err), node)) --aboveDelta;
+                if (D.kind == 1)
+                {
+                    const double pErr = E[8];
+                    S.slot[node] = S.jobPSlot[j];                                              // Octree.cpp:286
+                    S.degree[node] = (uint8_t)(p + 1);
+                    S.err[node] = pErr;
+                    S.state[node] = kStPending;                                                // back into the queue (Octree.cpp:289-290)
+                    histAdd(S, sh, pErr, true);
+                    if (atOrAbove(sh, errKey(pErr), node)) ++aboveDelta;
+                }
+                else if (D.kind == 2)
+                {
+                    const uint32_t c0 = sh.nNodes + childOff;                                  // Subdivide (Octree.cpp:1115-1128)
+                    S.child[node] = c0;
+                    S.degree[node] = kInternalTag;                                             // Octree.cpp:265-272
+                    S.state[node] = kStInternal;
+                    const float4 pc = S.cell[node];
+                    const float q = pc.w * 0.5f;
+                    const uint32_t hs = S.jobHSlot[j], nc = (uint32_t)coeffCount((int)p), code = S.code[node];
+                    #pragma unroll
+                    for (uint32_t c = 0; c < 8; ++c)
+                    {
+                        const uint32_t k = c0 + c;
+                        S.cell[k] = make_float4(pc.x + ((c & 1u) ? q : -q), pc.y + ((c & 2u) ? q : -q), pc.z + ((c & 4u) ? q : -q), q);
+                        S.child[k] = kNone;
+                        S.slot[k] = hs + c * nc;                                               // Octree.cpp:275-290
+                        S.err[k] = E[c];
+                        S.code[k] = code | (c << (27 - 3 * (int)depth));
+                        S.jobOf[k] = kNone;
+                        S.depth[k] = (uint8_t)(depth + 1);
+                        S.degree[k] = (uint8_t)p;
+                        S.state[k] = kStPending;
+                        S.open[sh.nOpen + childOff + c] = k;
+                        histAdd(S, sh, E[c], true);
+                        if (atOrAbove(sh, errKey(E[c]), k)) ++aboveDelta;
+                    }
+                }
+                else S.state[node] = kStRetired;                                               // Octree.cpp:643-655
+                if (D.kind != 0)
+                {
+                    hpsdf_apply_log_entry& L = S.log[sh.nLog + logOff];
+                    L.node_idx = node; L.kind = D.kind == 1 ? 0u : 1u; L.degree = p; L.initial_err = err; L.new_err = D.maxNew;
+                    L.p_improvement = D.pImp; L.h_improvement = D.hImp;
+                    L.total_after = (S.totalMode == HPSDF_TOTAL_EXACT_SUM ? sh.exactSum : sh.total) - inclDelta;
+                    if (logOff + 1 == totalLogged)                     // the last job of this chunk: the margins of the termination cut
+                    {
+                        sh.tmpD[0] = (S.totalMode == HPSDF_TOTAL_EXACT_SUM ? sh.exactSum : sh.total) - (inclDelta - D.delta);
+                        sh.tmpD[1] = L.total_after;
+                    }
+                }
+                if (D.nearTie)
+                {
+                    const uint32_t k = atomicAdd(&sh.nDecision, 1u);
+                    if (k < S.capDecisions)
+                    {
+                        hpsdf_decision_log_entry& e = S.decisions[k];
+                        const float4 pc = S.cell[node];
+                        e.node_idx = node; e.depth = depth; e.degree = p; e.centre[0] = pc.x; e.centre[1] = pc.y; e.centre[2] = pc.z;
+                        e.chose_p = D.kind == 1; e.kind = 0; e.p_improvement = D.pImp; e.h_improvement = D.hImp; e.relative_margin = D.margin;
+                    }
+                    atomicAdd(&sh.nearTies, 1u);
+                }
+            }
+            const int nP = blockSumI(active && D.kind == 1 ? 1 : 0, sh.warpU);
+            const int nR = blockSumI(active && D.kind == 0 ? 1 : 0, sh.warpU);
+            const int above = blockSumI(aboveDelta, sh.warpU);
+            if (tid == 0)
+            {
+                sh.total -= chunkDelta; sh.exactSum -= chunkDelta;
+                sh.nNodes += totalChildren; sh.nOpen += totalChildren; sh.nLog += totalLogged;
+                sh.appliedP += (uint32_t)nP; sh.appliedH += totalChildren / 8u; sh.retired += (uint32_t)nR;
+                sh.aboveLevel += above;
+                if (totalLogged) { sh.totalBeforeLast = sh.tmpD[0]; sh.lastTotal = sh.tmpD[1]; }
+            }
+            __syncthreads();
+        }
+    }
+
+    // Guaranteed level from the histogram (see the header comment). Returns the level (0 = everything, +inf = nothing);
+    // countAbove = open entries at or above it.
+    __device__ double histLevel(const SchedDev& S, SchedShared& sh, double value, uint32_t& countAbove)
+    {
+        const int tid = threadIdx.x;
+        double remaining = value;
+        uint32_t cntAbove = 0;
+        for (int hi = (int)sh.topSub; hi >= 0; hi -= kSchedThreads)
+        {
+            const int idx = hi - tid;
+            const uint32_t cnt = idx >= 0 ? S.allCnt[idx] : 0u;
+            const double bound = cnt ? (double)S.allSum[idx] * subUnit(idx) * (1.0 + 1e-12) : 0.0;
+            double chunkTotal = 0.0;
+            const double incl = blockInclScanD(bound, sh.warpD, chunkTotal);
+            const bool fail = cnt > 0u && !(remaining - incl >= S.threshold);
+            const uint32_t firstFail = blockMinU(fail ? (uint32_t)tid : (uint32_t)kSchedThreads, sh.warpU);
+            uint32_t total = 0;
+            blockExclScanU((uint32_t)tid < firstFail ? cnt : 0u, sh.warpU, total);
+            cntAbove += total;
+            if (firstFail < (uint32_t)kSchedThreads)
+            {
+                countAbove = cntAbove;
+                return subLowerEdge(hi - (int)firstFail + 1);            // upper edge of the sub-bucket the bound runs out in
+            }
+            remaining -= chunkTotal;
+        }
+        countAbove = cntAbove;
+        return 0.0;
+    }
+
+    // ---- exact walk of the head of the queue ---------------------------------------------------------------------------
+    struct WindowShared
+    {
+        unsigned long long key[kWindow];
+        uint32_t           node[kWindow];
+        uint32_t           hist[256];
+        uint32_t           count;
+    };
+
+    // Smallest key such that at most kWindow open entries have key >= it, found with the sub-bucket histogram and, inside the
+    // sub-bucket where the count crosses kWindow, by 8-bit refinement steps over the candidates of that sub-bucket. `limit`
+    // (output) is kNone, or — when more than kWindow entries share the largest remaining key exactly — the number of those
+    // to take in open-list order.
+    __device__ unsigned long long windowCutoff(const SchedDev& S, SchedShared& sh, WindowShared& W, uint32_t& tieLimit)
+    {
+        const int tid = threadIdx.x;
+        tieLimit = kNone;
+        // 1. whole sub-buckets from the top
+        uint32_t above = 0;
+        int crossing = -1;
+        for (int hi = (int)sh.topSub; hi >= 0 && crossing < 0; hi -= kSchedThreads)
+        {
+            const int idx = hi - tid;
+            const uint32_t cnt = idx >= 0 ? S.allCnt[idx] : 0u;
+            uint32_t total = 0;
+            const uint32_t excl = blockExclScanU(cnt, sh.warpU, total);
+            const bool over = cnt > 0u && above + excl + cnt > (uint32_t)kWindow;
+            const uint32_t first = blockMinU(over ? (uint32_t)tid : (uint32_t)kSchedThreads, sh.warpU);
+            if (first < (uint32_t)kSchedThreads)
+            {
+                if ((uint32_t)tid == first) { sh.tmpU[0] = above + excl; sh.tmpI[0] = idx; }
+                __syncthreads();
+                above = sh.tmpU[0]; crossing = sh.tmpI[0];
+                __syncthreads();
+            }
+            else above += total;
+        }
+        if (crossing < 0) return 0ull;                                   // the whole queue fits into the window
+        unsigned long long lowKey = errKey(subLowerEdge(crossing + 1));  // everything above the crossing sub-bucket is in
+        if (above >= (uint32_t)kWindow / 4u) return lowKey;
+        // 2. candidates of the crossing sub-bucket -> scratch
+        if (tid == 0) W.count = 0;
+        __syncthreads();
+        for (uint32_t base = 0; base < sh.nOpen; base += kSchedThreads)
+        {
+            const uint32_t i = base + tid;
+            bool in = false;
+            uint32_t node = 0;
+            if (i < sh.nOpen)
+            {
+                node = S.open[i];
+                const uint8_t st = S.state[node];
+                in = (st == kStPending || st == kStEval || st == kStCached) && subOfKey(errKey(S.err[node])) == crossing;
+            }
+            uint32_t total = 0;
+            const uint32_t off = blockExclScanU(in ? 1u : 0u, sh.warpU, total);
+            if (in) S.scratch[W.count + off] = node;                      // open-list order
+            __syncthreads();
+            if (tid == 0) W.count += total;
+            __syncthreads();
+        }
+        const uint32_t nCand = W.count;
+        // 3. refine 8 bits at a time: prefix = the bits of the crossing bin fixed so far
+        unsigned long long prefix = errKey(subLowerEdge(crossing)) >> 48;    // exponent + 4 mantissa bits
+        for (int shift = 40; shift >= 0; shift -= 8)
+        {
+            if (tid < 256) W.hist[tid] = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < nCand; i += kSchedThreads)
+            {
+                const unsigned long long k = errKey(S.err[S.scratch[i]]);
+                if ((k >> (shift + 8)) == prefix) atomicAdd(&W.hist[(uint32_t)(k >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0)
+            {
+                int bin = 255;
+                uint32_t cum = 0;
+                while (bin >= 0 && above + cum + W.hist[bin] <= (uint32_t)kWindow) { cum += W.hist[bin]; --bin; }
+                sh.tmpI[0] = bin;            // first bin that does not fit (-1: all fit)
+                sh.tmpU[0] = cum;
+            }
+            __syncthreads();
+            const int bin = sh.tmpI[0];
+            const uint32_t cum = sh.tmpU[0];
+            __syncthreads();
+            if (bin < 0) return prefix << (shift + 8);
+            above += cum;
+            lowKey = ((prefix << 8) | (unsigned long long)(bin + 1)) << shift;       // keys above the crossing bin
+            if (above >= (uint32_t)kWindow / 4u) return lowKey;
+            prefix = (prefix << 8) | (unsigned long long)bin;
+        }
+        // more than kWindow - above entries share the key `prefix` exactly: take the first few in open-list order
+        tieLimit = (uint32_t)kWindow - above;
+        return prefix;
+    }
+
+    // One exact pass over the sorted head of the queue. Returns the number of jobs applied; sets sh.done on termination.
+    __device__ uint32_t windowPass(const SchedDev& S, SchedShared& sh, WindowShared& W, double* sB /*[kWindow]*/, uint32_t* sList /*[kWindow]*/)
+    {
+        const int tid = threadIdx.x;
+        const double value = S.totalMode == HPSDF_TOTAL_EXACT_SUM ? sh.exactSum : sh.total;
+        uint32_t tieLimit = kNone;
+        const unsigned long long lowKey = windowCutoff(S, sh, W, tieLimit);
+        // gather the head: entries with key >= lowKey (ties at lowKey limited to tieLimit, in open-list order)
+        if (tid == 0) { W.count = 0; sh.tmpU[1] = 0; }
+        __syncthreads();
+        for (uint32_t base = 0; base < sh.nOpen; base += kSchedThreads)
+        {
+            const uint32_t i = base + tid;
+            bool in = false, tie = false;
+            uint32_t node = 0;
+            unsigned long long key = 0;
+            if (i < sh.nOpen)
+            {
+                node = S.open[i];
+                const uint8_t st = S.state[node];
+                if (st == kStPending || st == kStEval || st == kStCached)
+                {
+                    key = errKey(S.err[node]);
+                    in = key >= lowKey;
+                    tie = tieLimit != kNone && key == lowKey;
+                }
+            }
+            uint32_t tieTotal = 0;
+            const uint32_t tieOff = blockExclScanU(tie ? 1u : 0u, sh.warpU, tieTotal);
+            if (tie && sh.tmpU[1] + tieOff >= tieLimit) in = false;
+            uint32_t total = 0;
+            const uint32_t off = blockExclScanU(in ? 1u : 0u, sh.warpU, total);
+            if (in && W.count + off < (uint32_t)kWindow)
+            {
+                W.key[W.count + off] = key; W.node[W.count + off] = node;
+            }
+            __syncthreads();
+            if (tid == 0) { W.count = min(W.count + total, (uint32_t)kWindow); sh.tmpU[1] += tieTotal; }
+            __syncthreads();
+        }
+        const uint32_t n = W.count;
+        if (n == 0)
+        {
+            if (tid == 0) sh.done = 1u;                                      // nodeQueue.empty() (Octree.cpp:216)
+            __syncthreads();
+            return 0;
+        }
+        if ((uint32_t)tid >= n) { W.key[tid] = 0ull; W.node[tid] = kNone; }
+        __syncthreads();
+        // bitonic sort, descending by (key, then ascending node index): the reference's max-heap order; ties are its heap's accident
+        for (uint32_t k = 2; k <= (uint32_t)kWindow; k <<= 1)
+            for (uint32_t jj = k >> 1; jj > 0; jj >>= 1)
+            {
+                const uint32_t other = (uint32_t)tid ^ jj;
+                if (other > (uint32_t)tid)
+                {
+                    const unsigned long long ka = W.key[tid], kb = W.key[other];
+                    const uint32_t na = W.node[tid], nb = W.node[other];
+                    const bool aFirst = ka > kb || (ka == kb && na < nb);          // a belongs before b in the final order
+                    const bool up = ((uint32_t)tid & k) == 0;
+                    if (up ? !aFirst : aFirst) { W.key[tid] = kb; W.key[other] = ka; W.node[tid] = nb; W.node[other] = na; }
+                }
+                __syncthreads();
+            }
+        // per entry: exact decrease if its job is cached and none of its new errors reaches the smallest key of the head
+        const unsigned long long lastKey = W.key[n - 1];
+        bool cachedHere = false, exactHere = false;
+        double B = 0.0;
+        uint32_t job = kNone;
+        if ((uint32_t)tid < n)
+        {
+            const uint32_t node = W.node[tid];
+            const double err = S.err[node];
+            B = err;
+            if (S.state[node] == kStCached)
+            {
+                job = S.jobOf[node];
+                cachedHere = true;
+                const Decision D = decideJob(S, job, err, S.degree[node], S.depth[node]);
+                if (errKey(D.maxNew) < lastKey || D.kind == 0) { B = D.delta; exactHere = true; }
+            }
+        }
+        double totalB = 0.0;
+        const double inclB = blockInclScanD((uint32_t)tid < n ? B : 0.0, sh.warpD, totalB);
+        const double before = value - (inclB - B);                                   // total before this entry is popped
+        const bool ok = (uint32_t)tid < n && before >= S.threshold;
+        const uint32_t firstStop = blockMinU(ok ? (uint32_t)kSchedThreads : (uint32_t)tid, sh.warpU);      // first entry that is not certain (n if all are)
+        const uint32_t certain = min(firstStop, n);
+        const uint32_t firstInexact = blockMinU(((uint32_t)tid < n && !exactHere) ? (uint32_t)tid : (uint32_t)kSchedThreads, sh.warpU);
+        // termination: every entry before `certain` was handled exactly and the total is below the threshold there (Octree.cpp:216)
+        const bool terminates = certain < n && firstInexact >= certain;
+        // apply the certain cached entries in sorted order
+        const bool take = (uint32_t)tid < certain && cachedHere;
+        uint32_t nTake = 0;
+        const uint32_t off = blockExclScanU(take ? 1u : 0u, sh.warpU, nTake);
+        if (take) sList[off] = job;
+        // the certain entries whose jobs are not cached yet keep the level in force until they are evaluated and applied
+        const uint32_t waiting = certain - nTake;
+        __syncthreads();
+        if (tid == 0)
+        {
+            sh.windowPasses++;
+            if (waiting) { sh.levelKey = W.key[certain - 1]; sh.levelNode = W.node[certain - 1]; sh.aboveLevel = (int)certain; }
+        }
+        __syncthreads();
+        if (nTake)
+        {
+            if (tid == 0) sh.lastPassLogStart = sh.nLog;
+            __syncthreads();
+            applyJobs(S, sh, sList, nTake);
+        }
+        if (tid == 0)
+        {
+            if (!waiting) { sh.levelKey = kNoLevel; sh.levelNode = kNone; sh.aboveLevel = 0; }
+            if (terminates && sh.done == 0u) sh.done = 1u;
+        }
+        __syncthreads();
+        return nTake;
+    }
+
+    // ---- coarse stage (round 0) -----------------------------------------------------------------------------------------
+    // All 16^3 cells sit in the reference's queue with err = 100 (Octree.cpp:176-177); each is popped, fitted at degree 2 and
+    // pushed back with its real error (:228-238, :836-843). totalCoeffError starts at 8^4 * 100 (:212), so the first errors
+    // added are rounded at ulp(4e5) = 5.8e-11 and the running total depends on the POP ORDER at the 1e-9 level.
+    // That order is a property of std::priority_queue alone: every comparison the heap makes involves at least one key of
+    // 100, or two re-pushed keys below 100 whose exchange moves no unfitted entry (build_device.cpp: coarsePopOrder derives it
+    // once by running libstdc++'s push_heap / pop_heap on dummy keys) — so one thread replays the additions in that order.
+    __device__ void coarseStage(const SchedDev& S, SchedShared& sh, const uint16_t* __restrict__ gOrder, double* sErr /*[4096]*/, double* sRun /*[4096]*/,
+                                uint16_t* order /*[4096], shared*/)
+    {
+        const int tid = threadIdx.x;
+        const uint32_t nJobs = 4096u;
+        for (uint32_t k = tid; k < nJobs; k += kSchedThreads) order[k] = gOrder[k];
+        bool bad = false;
+        double localSum = 0.0;
+        for (uint32_t j = tid; j < nJobs; j += kSchedThreads)
+        {
+            const uint32_t node = S.jobNode[j];
+            const FitRecord r = S.recs[S.jobPPos[j]];
+            const double e = r.rawErr * nearnessWeightDev(S, r.c0, S.depth[node]);
+            sErr[j] = e;
+            bad |= !(e < kInitialErr);
+            S.jobFlags[j] |= 128u;
+            S.slot[node] = S.jobPSlot[j];
+            S.degree[node] = (uint8_t)kCoarseDegree;
+            S.err[node] = e;
+            S.state[node] = kStPending;
+            S.jobOf[node] = kNone;
+            S.open[j] = node;
+            histAdd(S, sh, e, true);
+            localSum += e;
+        }
+        double tot = 0.0;
+        blockInclScanD(localSum, sh.warpD, tot);
+        const int anyBad = blockSumI(bad ? 1 : 0, sh.warpU);
+        if (tid == 0)
+        {
+            double t = 4096.0 * kInitialErr;                                              // Octree.cpp:212
+            for (uint32_t k = 0; k < nJobs; ++k) { t += (sErr[order[k]] - kInitialErr); sRun[k] = t; }   // Octree.cpp:257
+            sh.total = t; sh.exactSum = tot; sh.lastTotal = t; sh.totalBeforeLast = nJobs > 1 ? sRun[nJobs - 2] : t;
+            sh.nOpen = nJobs; sh.appliedP += nJobs; sh.nLog = nJobs;
+            if (anyBad) sh.done = 3u;                                                     // an error >= 100 or NaN: the host scheduler takes over
+        }
+        __syncthreads();
+        for (uint32_t k = tid; k < nJobs; k += kSchedThreads)
+        {
+            const uint32_t j = order[k];
+            hpsdf_apply_log_entry& L = S.log[k];
+            L.node_idx = S.jobNode[j]; L.kind = 0u; L.degree = 0u; L.initial_err = kInitialErr; L.new_err = sErr[j];
+            L.p_improvement = sErr[j]; L.h_improvement = 0.0;                             // Octree.cpp:806-810, 836-843
+            L.total_after = S.totalMode == HPSDF_TOTAL_EXACT_SUM ? INFINITY : sRun[k];
+        }
+        __syncthreads();
+    }
+
+    // ---- the round kernel ---------------------------------------------------------------------------------------------------
+    constexpr size_t kSchedDynSmem = 2 * 4096 * sizeof(double) + 4096 * sizeof(uint16_t);   // coarse stage: errors + running totals + pop order; window: B + list
+
+    __global__ void __launch_bounds__(kSchedThreads, 1) schedRoundKernel(const SchedDev S, const uint16_t* __restrict__ coarseOrder)
+    {
+        extern __shared__ double dyn[];
+        __shared__ SchedShared sh;
+        __shared__ WindowShared W;
+        const int tid = threadIdx.x;
+        SchedCounters& C = *S.ctr;
+        if (tid == 0)
+        {
+            sh.nNodes = C.nNodes; sh.nOpen = C.nOpen; sh.nJobs = C.nJobs; sh.nCached = C.nCached; sh.poolUsed = C.poolUsed; sh.done = C.done;
+            sh.topSub = C.topSub; sh.nLog = C.nLog; sh.nDecision = C.nDecision; sh.appliedP = C.appliedP; sh.appliedH = C.appliedH;
+            sh.retired = C.retired; sh.nearTies = C.nearTies; sh.passes = C.passes; sh.windowPasses = C.windowPasses;
+            sh.lastPassLogStart = C.lastPassLogStart;
+            sh.total = C.total; sh.exactSum = C.exactSum; sh.totalBeforeLast = C.totalBeforeLast; sh.lastTotal = C.lastTotal;
+            sh.levelKey = C.levelKey; sh.levelNode = C.levelNode; sh.aboveLevel = C.aboveLevel;
+        }
+        __syncthreads();
+        const uint32_t round = C.round;
+
+        // ---- ingest ------------------------------------------------------------------------------------------------------
+        if (round == 0) coarseStage(S, sh, coarseOrder, dyn, dyn + 4096, reinterpret_cast<uint16_t*>(dyn + 8192));
+        else
+        {
+            const uint32_t j0 = C.roundJob0, nj = C.roundJobs;
+            for (uint32_t k = tid; k < nj; k += kSchedThreads)
+            {
+                const uint32_t j = j0 + k, node = S.jobNode[j];
+                const uint32_t depth = S.depth[node];
+                const uint8_t flags = S.jobFlags[j];
+                double* E = S.jobErr + 9 * (size_t)j;
+                if (flags & 1u)
+                    for (uint32_t c = 0; c < 8; ++c)
+                    {
+                        const FitRecord r = S.recs[S.jobHPos[j] + c];
+                        E[c] = r.rawErr * nearnessWeightDev(S, r.c0, depth + 1);
+                    }
+                if (flags & 2u)
+                {
+                    const FitRecord r = S.recs[S.jobPPos[j]];
+                    E[8] = r.rawErr * nearnessWeightDev(S, r.c0, depth);
+                }
+                S.state[node] = kStCached;
+                S.cached[sh.nCached + k] = j;
+            }
+            __syncthreads();
+            if (tid == 0) sh.nCached += nj;
+            __syncthreads();
+        }
+
+        // ---- passes ----------------------------------------------------------------------------------------------------
+        double* sB = dyn;
+        uint32_t* sList = reinterpret_cast<uint32_t*>(dyn + kWindow);
+        uint32_t* bulk = S.scratch + S.capNodes;                            // second half of the scratch: the jobs of a bulk pass
+        for (uint32_t iter = 0; sh.done == 0u; ++iter)
+        {
+            if (tid == 0) { sh.passes++; if (iter > 1000000u) sh.done = 4u; }       // (a pass applies at least one job or ends the loop)
+            __syncthreads();
+            if (sh.done != 0u) break;
+            if (sh.levelKey == kNoLevel)
+            {
+                // sequential-greedy state (Octree.cpp:216): terminated?
+                const double value = S.totalMode == HPSDF_TOTAL_EXACT_SUM ? sh.exactSum : sh.total;
+                if (!(value >= S.threshold) || sh.nOpen == 0u) { if (tid == 0) sh.done = 1u; __syncthreads(); break; }
+                uint32_t cntAbove = 0;
+                const double L = histLevel(S, sh, value, cntAbove);
+                if (cntAbove > 0u)
+                {
+                    if (tid == 0) { sh.levelKey = errKey(L); sh.levelNode = kNone; sh.aboveLevel = (int)cntAbove; }
+                    __syncthreads();
+                }
+                else
+                {
+                    // the histogram bound runs out inside the top sub-bucket: exact walk of the head
+                    const uint32_t applied = windowPass(S, sh, W, sB, sList);
+                    if (sh.done != 0u || applied == 0u) break;                  // terminated, or the head waits for evaluation
+                    continue;
+                }
+            }
+            // a level is in force: apply every cached job at or above it (any order gives the same tree)
+            uint32_t nBulk = 0;
+            for (uint32_t base = 0; base < sh.nCached; base += kSchedThreads)
+            {
+                const uint32_t i = base + tid;
+                bool take = false;
+                uint32_t j = 0;
+                if (i < sh.nCached)
+                {
+                    j = S.cached[i];
+                    const uint32_t node = S.jobNode[j];
+                    take = !(S.jobFlags[j] & 128u) && atOrAbove(sh, errKey(S.err[node]), node);
+                }
+                uint32_t total = 0;
+                const uint32_t off = blockExclScanU(take ? 1u : 0u, sh.warpU, total);
+                if (take) bulk[nBulk + off] = j;
+                nBulk += total;
+            }
+            __syncthreads();
+            if (nBulk)
+            {
+                if (tid == 0) sh.lastPassLogStart = sh.nLog;
+                __syncthreads();
+                applyJobs(S, sh, bulk, nBulk);
+            }
+            if (sh.done != 0u) break;
+            if (sh.aboveLevel <= 0)
+            {
+                if (tid == 0) { sh.levelKey = kNoLevel; sh.levelNode = kNone; sh.aboveLevel = 0; }     // everything at or above the level is refined: sequential state again
+                __syncthreads();
+                continue;
+            }
+            if (nBulk == 0u) break;                                            // the rest of the level waits for evaluation
+        }
+        __syncthreads();
+
+        // ---- select the next round + compact the lists ---------------------------------------------------------------------
+        uint32_t cnt[kMaxDegree + 2];
+        #pragma unroll
+        for (int d = 0; d <= kMaxDegree + 1; ++d) cnt[d] = 0;
+        uint32_t nSel = 0;
+        const uint32_t job0 = sh.nJobs;
+        if (sh.done == 0u)
+        {
+            // compact the cached list (drop applied jobs)
+            uint32_t keep = 0;
+            for (uint32_t base = 0; base < sh.nCached; base += kSchedThreads)
+            {
+                const uint32_t i = base + tid;
+                uint32_t j = 0;
+                bool live = false;
+                if (i < sh.nCached) { j = S.cached[i]; live = !(S.jobFlags[j] & 128u); }
+                uint32_t total = 0;
+                const uint32_t off = blockExclScanU(live ? 1u : 0u, sh.warpU, total);
+                __syncthreads();
+                if (live) S.cached[keep + off] = j;
+                keep += total;
+                __syncthreads();
+            }
+            if (tid == 0) sh.nCached = keep;
+            __syncthreads();
+
+            // (a level that splits a group of equal keys selects the whole group: evaluating a leaf early changes nothing)
+            double selLevel = sh.levelKey != kNoLevel ? __longlong_as_double((long long)sh.levelKey) : 0.0;
+            for (uint32_t k = 0; k < S.speculate; ++k) selLevel *= 0.125;
+            // top-up: sub-bucket in which the pending count reaches minRoundJobs
+            int cutSub = -1;
+            uint32_t needInCut = 0;
+            if (S.minRoundJobs > 1u)
+            {
+                uint32_t above = 0;
+                for (int hi = (int)sh.topSub; hi >= 0 && cutSub < 0; hi -= kSchedThreads)
+                {
+                    const int idx = hi - tid;
+                    const uint32_t pc = idx >= 0 ? S.pendCnt[idx] : 0u;
+                    uint32_t total = 0;
+                    const uint32_t excl = blockExclScanU(pc, sh.warpU, total);
+                    const bool reach = pc > 0u && above + excl + pc >= S.minRoundJobs;
+                    const uint32_t first = blockMinU(reach ? (uint32_t)tid : (uint32_t)kSchedThreads, sh.warpU);
+                    if (first < (uint32_t)kSchedThreads)
+                    {
+                        if ((uint32_t)tid == first) { sh.tmpI[0] = idx; sh.tmpU[0] = S.minRoundJobs - (above + excl); }
+                        __syncthreads();
+                        cutSub = sh.tmpI[0]; needInCut = sh.tmpU[0];
+                        __syncthreads();
+                    }
+                    else above += total;
+                }
+                if (cutSub < 0) { cutSub = 0; needInCut = 0xFFFFFFFFu; }          // fewer pending leaves than minRoundJobs: all of them
+            }
+            // pass A over the open list: compaction + selection (warp-aggregated ballots inside the block-wide scans)
+            uint32_t keepOpen = 0, takenInCut = 0;
+            for (uint32_t base = 0; base < sh.nOpen; base += kSchedThreads)
+            {
+                const uint32_t i = base + tid;
+                uint32_t node = 0;
+                bool live = false, sel = false, inCut = false;
+                double e = 0.0;
+                if (i < sh.nOpen)
+                {
+                    node = S.open[i];
+                    const uint8_t st = S.state[node];
+                    live = st == kStPending || st == kStEval || st == kStCached;
+                    if (st == kStPending)
+                    {
+                        e = S.err[node];
+                        const int sub = subOfKey(errKey(e));
+                        sel = e >= selLevel || (cutSub >= 0 && sub > cutSub);
+                        inCut = !sel && cutSub >= 0 && sub == cutSub;
+                    }
+                }
+                uint32_t cutTotal = 0;
+                const uint32_t cutOff = blockExclScanU(inCut ? 1u : 0u, sh.warpU, cutTotal);
+                if (inCut && takenInCut + cutOff < needInCut) sel = true;
+                takenInCut += cutTotal;
+                uint32_t liveTotal = 0, selTotal = 0;
+                const uint32_t liveOff = blockExclScanU(live ? 1u : 0u, sh.warpU, liveTotal);
+                const uint32_t selOff = blockExclScanU(sel ? 1u : 0u, sh.warpU, selTotal);
+                __syncthreads();
+                if (live) S.open[keepOpen + liveOff] = node;
+                if (sel)
+                {
+                    const uint32_t j = job0 + nSel + selOff;
+                    if (j < S.capJobs)
+                    {
+                        const uint32_t p = S.degree[node], depth = S.depth[node];
+                        const uint8_t flags = (uint8_t)((depth < S.maxDepth ? 1u : 0u) | (p < S.maxDegree ? 2u : 0u));    // Octree.cpp:600-601: fits that can never be used are skipped
+                        S.jobNode[j] = node; S.jobFlags[j] = flags;
+                        S.jobOf[node] = j;
+                        S.state[node] = kStEval;
+                        atomicSub(S.pendCnt + subOfKey(errKey(e)), 1u);
+                    }
+                }
+                keepOpen += liveTotal; nSel += selTotal;
+                __syncthreads();
+            }
+            if (tid == 0) sh.nOpen = keepOpen;
+            if (job0 + nSel > S.capJobs) { if (tid == 0) sh.done = 2u; nSel = 0; }
+            __syncthreads();
+
+            // per-degree counts
+            for (uint32_t base = 0; base < nSel; base += kSchedThreads)
+            {
+                const uint32_t k = base + tid;
+                uint32_t p = 0; uint8_t flags = 0;
+                if (k < nSel) { const uint32_t j = job0 + k; p = S.degree[S.jobNode[j]]; flags = S.jobFlags[j]; }
+                for (int d = 1; d <= kMaxDegree; ++d)
+                {
+                    const uint32_t c = (k < nSel) ? (((flags & 1u) && p == (uint32_t)d ? 8u : 0u) + ((flags & 2u) && p + 1u == (uint32_t)d ? 1u : 0u)) : 0u;
+                    if (__syncthreads_or(c != 0u))
+                    {
+                        uint32_t total = 0;
+                        blockExclScanU(c, sh.warpU, total);
+                        cnt[d] += total;
+                    }
+                }
+            }
+            // layout: tasks in degree order, slots allocated in task order (contiguous per degree: a rank's shard of a degree
+            // group is one contiguous pool range)
+            uint32_t groupBegin[kMaxDegree + 2], groupPool[kMaxDegree + 2];
+            uint32_t nTasks = 0;
+            unsigned long long poolNeed = sh.poolUsed;
+            groupBegin[0] = 0; groupPool[0] = sh.poolUsed;
+            for (int d = 1; d <= kMaxDegree; ++d)
+            {
+                groupBegin[d] = nTasks; groupPool[d] = (uint32_t)poolNeed;
+                nTasks += cnt[d]; poolNeed += (unsigned long long)cnt[d] * (unsigned long long)coeffCount(d);
+            }
+            groupBegin[kMaxDegree + 1] = nTasks; groupPool[kMaxDegree + 1] = (uint32_t)poolNeed;
+            if (poolNeed >= 0xFFFFFFF0ull) { if (tid == 0) sh.done = 2u; nSel = 0; }
+            __syncthreads();
+            // positions of every job's fits inside its groups, in job order; job records for expandJobsKernel
+            uint32_t cursor[kMaxDegree + 2];
+            for (int d = 0; d <= kMaxDegree + 1; ++d) cursor[d] = groupBegin[d];
+            for (uint32_t base = 0; base < nSel; base += kSchedThreads)
+            {
+                const uint32_t k = base + tid;
+                uint32_t j = 0, node = 0, p = 0, hPos = 0, pPos = 0;
+                uint8_t flags = 0;
+                if (k < nSel) { j = job0 + k; node = S.jobNode[j]; p = S.degree[node]; flags = S.jobFlags[j]; }
+                for (int d = 1; d <= kMaxDegree; ++d)
+                {
+                    if (!cnt[d]) continue;
+                    const bool h = k < nSel && (flags & 1u) && p == (uint32_t)d, q = k < nSel && (flags & 2u) && p + 1u == (uint32_t)d;
+                    uint32_t total = 0;
+                    const uint32_t off = blockExclScanU(h ? 8u : (q ? 1u : 0u), sh.warpU, total);
+                    if (h) hPos = cursor[d] + off;
+                    if (q) pPos = cursor[d] + off;
+                    cursor[d] += total;
+                }
+                if (k < nSel)
+                {
+                    const uint32_t depth = S.depth[node];
+                    S.jobHPos[j] = hPos; S.jobPPos[j] = pPos;
+                    S.jobHSlot[j] = (flags & 1u) ? groupPool[p] + (hPos - groupBegin[p]) * (uint32_t)coeffCount((int)p) : 0u;
+                    S.jobPSlot[j] = (flags & 2u) ? groupPool[p + 1] + (pPos - groupBegin[p + 1]) * (uint32_t)coeffCount((int)p + 1) : 0u;
+                    const float4 c = S.cell[node];
+                    JobDesc o;
+                    o.cx = c.x; o.cy = c.y; o.cz = c.z; o.half = c.w;
+                    o.hPos = hPos; o.pPos = pPos; o.src = S.slot[node];
+                    o.depth = (uint8_t)depth; o.degree = (uint8_t)p; o.flags = flags; o.pad = 0;
+                    S.jobsOut[k] = o;
+                }
+            }
+            if (tid == 0)
+            {
+                RoundLayout lay;
+                for (int d = 0; d <= kMaxDegree + 1; ++d) { lay.groupBegin[d] = groupBegin[d]; lay.groupPool[d] = groupPool[d]; }
+                *S.layout = lay;
+                if (sh.done == 0u) { sh.poolUsed = (uint32_t)poolNeed; sh.nJobs = job0 + nSel; }
+                if (nSel == 0u && sh.done == 0u) sh.done = 4u;               // nothing to evaluate and not terminated: internal error
+            }
+            __syncthreads();
+        }
+
+        // ---- write back + header -------------------------------------------------------------------------------------------
+        if (tid == 0)
+        {
+            uint32_t nTasks = 0;
+            for (int d = 1; d <= kMaxDegree; ++d) nTasks += cnt[d];
+            C.nNodes = sh.nNodes; C.nOpen = sh.nOpen; C.nJobs = sh.nJobs; C.nCached = sh.nCached; C.poolUsed = sh.poolUsed; C.done = sh.done;
+            C.topSub = sh.topSub; C.nLog = sh.nLog; C.nDecision = sh.nDecision; C.appliedP = sh.appliedP; C.appliedH = sh.appliedH;
+            C.retired = sh.retired; C.nearTies = sh.nearTies; C.passes = sh.passes; C.windowPasses = sh.windowPasses;
+            C.lastPassLogStart = sh.lastPassLogStart;
+            C.total = sh.total; C.exactSum = sh.exactSum; C.totalBeforeLast = sh.totalBeforeLast; C.lastTotal = sh.lastTotal;
+            C.roundJob0 = job0; C.roundJobs = sh.done == 0u ? nSel : 0u;
+            C.jobsEvaluated += sh.done == 0u ? nSel : 0u; C.fitsEvaluated += sh.done == 0u ? nTasks : 0u;
+            C.round = round + 1;
+            C.levelKey = sh.levelKey; C.levelNode = sh.levelNode; C.aboveLevel = sh.aboveLevel;
+            RoundHeader* H = S.hostHdr;
+            H->done = sh.done; H->nJobs = sh.done == 0u ? nSel : 0u; H->nTasks = sh.done == 0u ? nTasks : 0u;
+            for (int d = 0; d <= kMaxDegree + 1; ++d) H->cnt[d] = sh.done == 0u ? cnt[d] : 0u;
+            H->nNodes = sh.nNodes; H->nOpen = sh.nOpen; H->nCached = sh.nCached; H->poolUsed = sh.poolUsed;
+            __threadfence_system();
+            H->seq = round + 1;
+            __threadfence_system();
+        }
+    }
+}
