@@ -26,7 +26,7 @@ namespace hpsdf
             }
             else for (int i = 7; i >= 0; --i) stack.push_back(n.child + (uint64_t)i);
         }
-        t.nCoeffs = cur;
+        t.nCoeffs = cur; t.nNodes = nodes.size(); t.nCoeffsPad = paddedCoeffCount(t);
         const uint32_t nSeg = (uint32_t)srcOff.size();
         hpsdf_status st = allocTreeBlob(t);
         if (st != HPSDF_OK) return st;
@@ -40,6 +40,39 @@ namespace hpsdf
         t.stats.kernel_launches++;
         HPSDF_CUDA(cudaStreamSynchronize(stream));       // the pinned segment staging is reused by finalizeQueryStructures
         return HPSDF_OK;
+    }
+
+    void ensureApplyLog(hpsdf_octree& t)
+    {
+        if (!t.logOnDevice) return;
+        t.logOnDevice = false;
+        t.applyLog.resize(t.nLogDev);
+        cudaSetDevice(t.device);
+        if (t.nLogDev && cudaMemcpy(t.applyLog.data(), t.dApplyLog, t.nLogDev * sizeof(hpsdf_apply_log_entry), cudaMemcpyDeviceToHost) != cudaSuccess)
+        { cudaGetLastError(); t.applyLog.clear(); }
+    }
+
+    void ensureDecisionLog(hpsdf_octree& t)
+    {
+        if (!t.cutLogPending) return;
+        t.cutLogPending = false;
+        ensureApplyLog(t);
+        if (ensureHostNodes(t) != HPSDF_OK) return;
+        std::vector<double> errOf(t.nNodes);
+        if (cudaMemcpy(errOf.data(), t.dLeafErr, t.nNodes * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return; }
+        const double thr = t.cfg.target_error_threshold;
+        if (t.applyLog.size() > 4096)
+        {
+            // the last job applied before the termination cut, with how far the total was from the threshold around it
+            const hpsdf_apply_log_entry& a = t.applyLog.back();
+            hpsdf_decision_log_entry e{};
+            e.node_idx = a.node_idx; e.depth = t.nodes[a.node_idx].depth; e.degree = a.degree; e.chose_p = a.kind == 0; e.kind = 1;
+            e.p_improvement = a.p_improvement; e.h_improvement = a.h_improvement;
+            for (int k = 0; k < 3; ++k) e.centre[k] = (t.nodes[a.node_idx].mn[k] + t.nodes[a.node_idx].mx[k]) / 2.0f;
+            e.relative_margin = std::min(std::fabs(t.cutTotalBeforeLast - thr), std::fabs(thr - t.cutCheck)) / thr;
+            t.decisionLog.push_back(e);
+        }
+        logCutTieGroup(t, errOf, t.cutLogStart, t.cutQueueEmpty);
     }
 
     void logCutTieGroup(hpsdf_octree& t, const std::vector<double>& errOf, size_t levelLogStart, bool queueEmpty)

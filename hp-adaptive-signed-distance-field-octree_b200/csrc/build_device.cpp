@@ -25,6 +25,16 @@ namespace hpsdf
 {
     cudaError_t launchSchedRound(const SchedDev& S, const uint16_t* coarseOrder, cudaStream_t stream);                    // kernels.cu
     cudaError_t launchExpandJobsDev(const JobDesc* dJobs, uint32_t nJobs, const RoundLayout* dLayout, FitTask* dTasks, cudaStream_t stream);
+    struct FinishHeader { volatile uint32_t seq; uint32_t nLeaves, nCoeffs, nCoeffsPad; SchedCounters counters; };     // finish_kernels.cuh
+    cudaError_t launchSchedInit(const SchedDev& S, const SchedTemplates& T, const SchedCounters& c0, const RoundLayout& lay, cudaStream_t stream);
+    size_t      finishSortTempBytes(uint32_t capNodes);
+    cudaError_t launchFinishOrder(const SchedDev& S, uint32_t nNodes, uint32_t* keys, uint32_t* vals, uint32_t* keysAlt, uint32_t* valsAlt,
+                                  uint32_t* counter, void* tmp, size_t tmpBytes, uint32_t* cstartOf, uint32_t* padOf, FinishHeader* hdr, uint32_t seq,
+                                  cudaStream_t stream);
+    cudaError_t launchEmitTree(const SchedDev& S, uint32_t nNodes, const uint32_t* cstartOf, const uint32_t* padOf, const double* pool,
+                               double* packed, QNode* qnodes, unsigned char* image, cudaStream_t stream);
+    cudaError_t launchPadCoefficients(const SchedDev& S, uint32_t nNodes, const uint32_t* cstartOf, const uint32_t* padOf, const double* packed,
+                                      double* padded, cudaStream_t stream);
 
     namespace
     {
@@ -66,6 +76,14 @@ namespace hpsdf
             uint32_t* tJobNode = nullptr; uint32_t* tJobPSlot = nullptr; uint32_t* tJobPPos = nullptr; uint8_t* tJobFlags = nullptr;
             JobDesc*  tJobs = nullptr;
             uint16_t* coarseOrder = nullptr;
+            uint32_t* tTop = nullptr;            // 16^3 entry table of the Query kernel (fixed by the uniform start)
+            SchedTemplates tpl{};
+            // finish: DFS order of the leaves
+            uint32_t* sortKeys = nullptr; uint32_t* sortVals = nullptr; uint32_t* sortKeysAlt = nullptr; uint32_t* sortValsAlt = nullptr;
+            uint32_t* cstartOf = nullptr; uint32_t* padOf = nullptr; uint32_t* leafCounter = nullptr;
+            void*     sortTmp = nullptr; size_t sortTmpBytes = 0;
+            FinishHeader* hostFin = nullptr; FinishHeader* devFin = nullptr;
+            uint32_t  finSeq = 0;
             std::vector<cudaEvent_t> ev;         // pairs around the fit launches of a round
             // pinned staging for the final read-back
             PinnedBuf<char> hBack;
@@ -126,7 +144,16 @@ namespace hpsdf
                 o.depth = (uint8_t)kCoarseDepth; o.degree = 0; o.flags = 4u; o.pad = 0;
             }
             const std::vector<uint16_t> order = coarsePopOrder();
-            const size_t bytes = alignUp(kCoarseNodes * 16) + 2 * alignUp(kCoarseNodes * 4) + 3 * alignUp(kCoarseNodes) + 3 * alignUp(kCoarseCells * 4) +
+            // depth-4 entry table: node of cell (ix, iy, iz) of the 16^3 grid at index ix + 16 iy + 256 iz
+            std::vector<uint32_t> top(4096);
+            for (uint32_t codeIdx = 0; codeIdx < 4096; ++codeIdx)
+            {
+                const uint32_t ix = codeIdx & 15, iy = (codeIdx >> 4) & 15, iz = codeIdx >> 8;
+                uint32_t cur = 0;
+                for (int l = 3; l >= 0; --l) cur = child[cur] + ((ix >> l) & 1) + 2 * ((iy >> l) & 1) + 4 * ((iz >> l) & 1);
+                top[codeIdx] = cur;
+            }
+            const size_t bytes = alignUp(4096 * 4) + alignUp(kCoarseNodes * 16) + 2 * alignUp(kCoarseNodes * 4) + 3 * alignUp(kCoarseNodes) + 3 * alignUp(kCoarseCells * 4) +
                                  alignUp(kCoarseCells) + alignUp(kCoarseCells * sizeof(JobDesc)) + alignUp(kCoarseCells * 2);
             HPSDF_CUDA(cudaMalloc((void**)&w.tmpl, bytes));
             char* p = w.tmpl;
@@ -143,9 +170,15 @@ namespace hpsdf
             w.tJobFlags = (uint8_t*)put(jobFlags.data(), kCoarseCells);
             w.tJobs = (JobDesc*)put(jobs.data(), kCoarseCells * sizeof(JobDesc));
             w.coarseOrder = (uint16_t*)put(order.data(), kCoarseCells * 2);
-            HPSDF_CUDA(cudaHostAlloc((void**)&w.hostHdr, sizeof(RoundHeader), cudaHostAllocMapped));
+            w.tTop = (uint32_t*)put(top.data(), 4096 * 4);
+            HPSDF_CUDA(cudaHostAlloc((void**)&w.hostHdr, sizeof(RoundHeader) + 64 + sizeof(FinishHeader) + 64, cudaHostAllocMapped));
             HPSDF_CUDA(cudaHostGetDevicePointer((void**)&w.devHdr, w.hostHdr, 0));
-            memset((void*)w.hostHdr, 0, sizeof(RoundHeader));
+            memset((void*)w.hostHdr, 0, sizeof(RoundHeader) + 64 + sizeof(FinishHeader) + 64);
+            w.tpl.cell = w.tCell; w.tpl.child = w.tChild; w.tpl.code = w.tCode; w.tpl.depth = w.tDepth; w.tpl.degree = w.tDegree; w.tpl.state = w.tState;
+            w.tpl.jobNode = w.tJobNode; w.tpl.jobPSlot = w.tJobPSlot; w.tpl.jobPPos = w.tJobPPos; w.tpl.jobFlags = w.tJobFlags;
+            w.tpl.nNodes = kCoarseNodes; w.tpl.nJobs = kCoarseCells;
+            w.hostFin = (FinishHeader*)((char*)w.hostHdr + sizeof(RoundHeader) + 64);
+            w.devFin = (FinishHeader*)((char*)w.devHdr + sizeof(RoundHeader) + 64);
             return HPSDF_OK;
         }
 
@@ -160,7 +193,8 @@ namespace hpsdf
                 n * 4, n * 4, 2 * n * 4,                                             // open, cached, scratch
                 (size_t)kSubBuckets * 4, (size_t)kSubBuckets * 8, (size_t)kSubBuckets * 4,
                 n * sizeof(JobDesc), sizeof(RoundLayout), n * sizeof(hpsdf_apply_log_entry), 4096 * sizeof(hpsdf_decision_log_entry),
-                sizeof(SchedCounters) };
+                sizeof(SchedCounters),
+                n * 4, n * 4, n * 4, n * 4, n * 4, n * 4, 256, finishSortTempBytes(cap) };   // finish: sort keys / values (x2), cstart, padded start, leaf counter, CUB temp
             size_t total = 0;
             for (size_t s : sizes) total += alignUp(s);
             cudaError_t e = cudaMalloc((void**)&w.arena, total);
@@ -177,6 +211,9 @@ namespace hpsdf
             d.allCnt = (uint32_t*)take(); d.allSum = (unsigned long long*)take(); d.pendCnt = (uint32_t*)take();
             d.jobsOut = (JobDesc*)take(); d.layout = (RoundLayout*)take(); d.log = (hpsdf_apply_log_entry*)take();
             d.decisions = (hpsdf_decision_log_entry*)take(); d.ctr = (SchedCounters*)take();
+            w.sortKeys = (uint32_t*)take(); w.sortVals = (uint32_t*)take(); w.sortKeysAlt = (uint32_t*)take(); w.sortValsAlt = (uint32_t*)take();
+            w.cstartOf = (uint32_t*)take(); w.padOf = (uint32_t*)take(); w.leafCounter = (uint32_t*)take();
+            w.sortTmpBytes = sizes[k]; w.sortTmp = take();
             d.capNodes = cap; d.capJobs = cap; d.capLog = cap; d.capDecisions = 4096;
             w.cap = cap;
             return HPSDF_OK;
@@ -198,6 +235,7 @@ namespace hpsdf
             bool                    progHasExt_ = false;
             double                  sdfFlops_ = 0.0, fitMs_ = 0.0;
             size_t                  evUsed_ = 0;
+            uint32_t                nNodesFinal_ = 0;
 
             hpsdf_status launchRoundFits(SchedWorkspace& w, const uint32_t cnt[kMaxDegree + 2], const uint32_t groupBegin[kMaxDegree + 2],
                                          const uint32_t groupPool[kMaxDegree + 2], uint32_t nTasks);
@@ -322,23 +360,11 @@ namespace hpsdf
             t_.stats.sdf_flops_per_eval = sdfFlops_;
 
             // ---- uniform start (CreateRoot + UniformlyRefine) from the templates; counters ------------------------------------------
-            HPSDF_CUDA(cudaMemcpyAsync(S.cell, w.tCell, kCoarseNodes * 16, cudaMemcpyDeviceToDevice, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(S.child, w.tChild, kCoarseNodes * 4, cudaMemcpyDeviceToDevice, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(S.code, w.tCode, kCoarseNodes * 4, cudaMemcpyDeviceToDevice, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(S.depth, w.tDepth, kCoarseNodes, cudaMemcpyDeviceToDevice, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(S.degree, w.tDegree, kCoarseNodes, cudaMemcpyDeviceToDevice, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(S.state, w.tState, kCoarseNodes, cudaMemcpyDeviceToDevice, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(S.jobNode, w.tJobNode, kCoarseCells * 4, cudaMemcpyDeviceToDevice, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(S.jobPSlot, w.tJobPSlot, kCoarseCells * 4, cudaMemcpyDeviceToDevice, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(S.jobPPos, w.tJobPPos, kCoarseCells * 4, cudaMemcpyDeviceToDevice, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(S.jobFlags, w.tJobFlags, kCoarseCells, cudaMemcpyDeviceToDevice, stream_));
-            HPSDF_CUDA(cudaMemsetAsync(S.allCnt, 0, (char*)S.jobsOut - (char*)S.allCnt, stream_));            // the three histograms are adjacent
             SchedCounters c0;
             memset(&c0, 0, sizeof(c0));
             c0.nNodes = kCoarseNodes; c0.nJobs = kCoarseCells; c0.poolUsed = kCoarseCells * (uint32_t)coeffCount(kCoarseDegree);
             c0.roundJob0 = 0; c0.roundJobs = kCoarseCells; c0.levelKey = ~0ull; c0.levelNode = kNone;
             c0.jobsEvaluated = kCoarseCells; c0.fitsEvaluated = kCoarseCells;
-            HPSDF_CUDA(cudaMemcpyAsync(S.ctr, &c0, sizeof(c0), cudaMemcpyHostToDevice, stream_));
             w.hostHdr->seq = 0;
 
             // ---- round 0: the 4096 coarse fits at degree 2 (Octree.cpp:836-843) -------------------------------------------------
@@ -347,7 +373,8 @@ namespace hpsdf
             for (int d = kCoarseDegree + 1; d <= kMaxDegree + 1; ++d) { groupBegin[d] = kCoarseCells; groupPool[d] = c0.poolUsed; }
             RoundLayout lay;
             for (int d = 0; d <= kMaxDegree + 1; ++d) { lay.groupBegin[d] = groupBegin[d]; lay.groupPool[d] = groupPool[d]; }
-            HPSDF_CUDA(cudaMemcpyAsync(S.layout, &lay, sizeof(lay), cudaMemcpyHostToDevice, stream_));
+            HPSDF_CUDA(launchSchedInit(S, w.tpl, c0, lay, stream_));
+            t_.stats.kernel_launches++;
             HPSDF_CUDA(ws_.pool.reserve((size_t)c0.poolUsed + 1024, stream_, 0));
             HPSDF_CUDA(ws_.tasks.reserve(kCoarseCells));
             HPSDF_CUDA(ws_.recs.reserve(kCoarseCells));
@@ -368,7 +395,7 @@ namespace hpsdf
                 memcpy(&h, (const void*)w.hostHdr, sizeof(h));
                 if (getenv("HPSDF_DEBUG_ROUNDS"))
                     fprintf(stderr, "round %u: done %u, next jobs %u tasks %u, nodes %u open %u cached %u pool %u\n", round, h.done, h.nJobs, h.nTasks, h.nNodes, h.nOpen, h.nCached, h.poolUsed);
-                if (h.done) { doneCode = h.done; break; }
+                if (h.done) { doneCode = h.done; nNodesFinal_ = h.nNodes; break; }
                 if (round > 100000) { setLastError("internal: build does not converge"); return HPSDF_ERR_CUDA; }
                 // next round: tasks in degree order, slots allocated in task order
                 uint32_t nTasks = 0;
@@ -392,63 +419,72 @@ namespace hpsdf
             return HPSDF_OK;
         }
 
-        // Read the tree back once: node arrays -> t.nodes (SDF::Node, Include/HP/Node.h:10-33), logs, counters.
+        // ReallocCoeffs + Query / MemoryBlock structures on the device (finish_kernels.cuh), the optional continuity solve, and
+        // what comes back to the host: counters, the apply log, the near-tie log and the leaf errors (for the cut-tie log).
         hpsdf_status DeviceBuilder::finish(SchedWorkspace& w)
         {
             SchedDev& S = w.dev;
+            const double tPack0 = nowMs();
+            const uint32_t nN = nNodesFinal_;
+            const uint32_t seq = ++w.finSeq;
+            HPSDF_CUDA(launchFinishOrder(S, nN, w.sortKeys, w.sortVals, w.sortKeysAlt, w.sortValsAlt, w.leafCounter, w.sortTmp, w.sortTmpBytes,
+                                         w.cstartOf, w.padOf, w.devFin, seq, stream_));
+            t_.stats.kernel_launches += 6;
+            // wait for the totals + counters (mapped memory), then size the tree's storage
+            {
+                const double t0 = nowMs();
+                for (uint64_t spin = 0; w.hostFin->seq != seq; ++spin)
+                    if ((spin & 0xFFF) == 0xFFF)
+                    {
+                        const cudaError_t q = cudaStreamQuery(stream_);
+                        if (q != cudaSuccess && q != cudaErrorNotReady) return failCuda(q, "finish kernels");
+                        if (nowMs() - t0 > 120000.0) { setLastError("internal: finish kernels did not answer within 120 s"); return HPSDF_ERR_CUDA; }
+                    }
+                std::atomic_thread_fence(std::memory_order_acquire);
+            }
+            const uint32_t nLeaves = w.hostFin->nLeaves;
             SchedCounters c;
-            HPSDF_CUDA(cudaMemcpyAsync(&c, S.ctr, sizeof(c), cudaMemcpyDeviceToHost, stream_));
+            memcpy(&c, (const void*)&w.hostFin->counters, sizeof(c));
+            const size_t nL = c.nLog, nD = std::min<size_t>(c.nDecision, S.capDecisions);
+            t_.nNodes = nN; t_.nCoeffs = w.hostFin->nCoeffs; t_.nCoeffsPad = w.hostFin->nCoeffsPad; t_.nLogDev = nL;
+            t_.nodes.clear(); t_.applyLog.clear(); t_.decisionLog.clear();
+            hpsdf_status st = allocTreeBlob(t_);
+            if (st != HPSDF_OK) return st;
+            HPSDF_CUDA(launchEmitTree(S, nN, w.cstartOf, w.padOf, ws_.pool.p, t_.dCoeffs, t_.dNodes, t_.dNodeImage, stream_));
+            t_.imageValid = true;
+            t_.stats.kernel_launches++;
+            // the apply log and the leaf errors stay on the device (inside the tree's allocation) until they are read
+            if (nL) HPSDF_CUDA(cudaMemcpyAsync(t_.dApplyLog, S.log, nL * sizeof(hpsdf_apply_log_entry), cudaMemcpyDeviceToDevice, stream_));
+            if (nL) HPSDF_CUDA(cudaMemcpyAsync(t_.dLeafErr, S.err, (size_t)nN * 8, cudaMemcpyDeviceToDevice, stream_));
+            t_.logOnDevice = nL != 0;
+            if (nD)
+            {
+                t_.decisionLog.resize(nD);
+                HPSDF_CUDA(cudaMemcpyAsync(t_.decisionLog.data(), S.decisions, nD * sizeof(hpsdf_decision_log_entry), cudaMemcpyDeviceToHost, stream_));
+            }
+            t_.stats.pack_ms = nowMs() - tPack0;
+            if (t_.cfg.continuity_enforce)
+            {
+                const double c0 = nowMs();
+                st = continuityPostProcess(t_, o_, stream_);                                          // Octree.cpp:341-344
+                if (st != HPSDF_OK) return st;
+                t_.stats.continuity_ms = nowMs() - c0;
+            }
+            const double tFin0 = nowMs();
+            HPSDF_CUDA(launchPadCoefficients(S, nN, w.cstartOf, w.padOf, t_.dCoeffs, t_.dCoeffsPad, stream_));
+            HPSDF_CUDA(cudaMemcpyAsync(t_.dTop, w.tTop, 4096 * 4, cudaMemcpyDeviceToDevice, stream_));
+            t_.view.nodes = t_.dNodes; t_.view.coeffs = t_.dCoeffsPad; t_.view.top = t_.dTop; t_.view.map = t_.map; t_.view.nNodes = nN;
+            HPSDF_CUDA(cudaMemcpyAsync(t_.dView, &t_.view, sizeof(DeviceTreeView), cudaMemcpyHostToDevice, stream_));
+            t_.stats.kernel_launches++;
             HPSDF_CUDA(cudaStreamSynchronize(stream_));
-            const size_t nN = c.nNodes, nL = c.nLog, nD = std::min<size_t>(c.nDecision, S.capDecisions);
-            const size_t bCell = alignUp(nN * 16), bU32 = alignUp(nN * 4), bErr = alignUp(nN * 8), bU8 = alignUp(nN);
-            const size_t bLog = alignUp(nL * sizeof(hpsdf_apply_log_entry)), bDec = alignUp(nD * sizeof(hpsdf_decision_log_entry) + 8);
-            HPSDF_CUDA(w.hBack.reserve(bCell + 2 * bU32 + bErr + 2 * bU8 + bLog + bDec));
-            char* p = w.hBack.p;
-            float4* hCell = (float4*)p; p += bCell;
-            uint32_t* hChild = (uint32_t*)p; p += bU32;
-            uint32_t* hSlot = (uint32_t*)p; p += bU32;
-            double* hErr = (double*)p; p += bErr;
-            uint8_t* hDepth = (uint8_t*)p; p += bU8;
-            uint8_t* hDegree = (uint8_t*)p; p += bU8;
-            hpsdf_apply_log_entry* hLog = (hpsdf_apply_log_entry*)p; p += bLog;
-            hpsdf_decision_log_entry* hDec = (hpsdf_decision_log_entry*)p;
-            HPSDF_CUDA(cudaMemcpyAsync(hCell, S.cell, nN * 16, cudaMemcpyDeviceToHost, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(hChild, S.child, nN * 4, cudaMemcpyDeviceToHost, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(hSlot, S.slot, nN * 4, cudaMemcpyDeviceToHost, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(hErr, S.err, nN * 8, cudaMemcpyDeviceToHost, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(hDepth, S.depth, nN, cudaMemcpyDeviceToHost, stream_));
-            HPSDF_CUDA(cudaMemcpyAsync(hDegree, S.degree, nN, cudaMemcpyDeviceToHost, stream_));
-            if (nL) HPSDF_CUDA(cudaMemcpyAsync(hLog, S.log, nL * sizeof(hpsdf_apply_log_entry), cudaMemcpyDeviceToHost, stream_));
-            if (nD) HPSDF_CUDA(cudaMemcpyAsync(hDec, S.decisions, nD * sizeof(hpsdf_decision_log_entry), cudaMemcpyDeviceToHost, stream_));
-            HPSDF_CUDA(cudaStreamSynchronize(stream_));
+            t_.stats.finalize_ms = nowMs() - tFin0;
             for (size_t k = 0; k + 1 < evUsed_; k += 2)
             {
                 float ms = 0.0f;
                 if (cudaEventElapsedTime(&ms, w.ev[k], w.ev[k + 1]) == cudaSuccess) fitMs_ += ms;
             }
             t_.stats.fit_kernel_ms = fitMs_;
-
-            std::vector<HostNode>& nodes = t_.nodes;
-            nodes.resize(nN);
-            std::vector<double> errOf(nN);
-            uint64_t leaves = 0;
-            for (size_t i = 0; i < nN; ++i)
-            {
-                HostNode& n = nodes[i];
-                const float4 c = hCell[i];
-                n.child = hChild[i] == kNone ? kNoChild : (uint64_t)hChild[i];
-                n.mn[0] = c.x - c.w; n.mn[1] = c.y - c.w; n.mn[2] = c.z - c.w;          // dyadic: exact, = CornerAABB (Octree.cpp:1096-1112)
-                n.mx[0] = c.x + c.w; n.mx[1] = c.y + c.w; n.mx[2] = c.z + c.w;
-                n.cstart = 0; n.slot = hSlot[i]; n.degree = hDegree[i]; n.depth = hDepth[i];
-                errOf[i] = hErr[i];
-                leaves += n.child == kNoChild;
-            }
-            t_.applyLog.assign(hLog, hLog + nL);
-            t_.decisionLog.clear();
-            std::vector<hpsdf_decision_log_entry> ties(hDec, hDec + nD);
-            std::sort(ties.begin(), ties.end(), [](const hpsdf_decision_log_entry& a, const hpsdf_decision_log_entry& b) { return a.node_idx < b.node_idx; });
-            t_.decisionLog = ties;
-
+            if (nD) std::sort(t_.decisionLog.begin(), t_.decisionLog.end(), [](const hpsdf_decision_log_entry& a, const hpsdf_decision_log_entry& b) { return a.node_idx < b.node_idx; });
             hpsdf_build_stats& s = t_.stats;
             s.jobs_evaluated += kCoarseCells;
             s.jobs_applied_p = c.appliedP; s.jobs_applied_h = c.appliedH; s.near_tie_decisions = c.nearTies;
@@ -458,22 +494,13 @@ namespace hpsdf
             const double check = o_.total_mode == HPSDF_TOTAL_EXACT_SUM ? c.exactSum : c.total;
             s.cut_margin = (thr - check) / thr;
             s.host_replay_ms = 0.0;
-            if (nL > kCoarseCells)
-            {
-                // the last job applied before the termination cut, with how far the total was from the threshold around it
-                const hpsdf_apply_log_entry& a = t_.applyLog.back();
-                hpsdf_decision_log_entry e{};
-                e.node_idx = a.node_idx; e.depth = nodes[a.node_idx].depth; e.degree = a.degree; e.chose_p = a.kind == 0; e.kind = 1;
-                e.p_improvement = a.p_improvement; e.h_improvement = a.h_improvement;
-                for (int k = 0; k < 3; ++k) e.centre[k] = (nodes[a.node_idx].mn[k] + nodes[a.node_idx].mx[k]) / 2.0f;
-                e.relative_margin = std::min(std::fabs(c.totalBeforeLast - thr), std::fabs(thr - check)) / thr;
-                t_.decisionLog.push_back(e);
-            }
-            logCutTieGroup(t_, errOf, c.lastPassLogStart, c.nOpen == 0);
-            s.n_nodes = nN; s.n_leaves = leaves; ws_.lastNodeCount = nN;
+            // the equal-error group the cut falls into is worked out when the log is read (it needs the node array on the host)
+            t_.cutLogStart = c.lastPassLogStart; t_.cutQueueEmpty = c.nOpen == 0; t_.cutLogPending = nL != 0;
+            t_.cutTotalBeforeLast = c.totalBeforeLast; t_.cutCheck = check;
+            s.n_nodes = nN; s.n_leaves = nLeaves; s.n_coeffs = t_.nCoeffs; ws_.lastNodeCount = nN;
             if (getenv("HPSDF_DEBUG_ROUNDS"))
-                fprintf(stderr, "device scheduler: rounds %llu, passes %u (exact head walks %u), applied P %u H %u, retired %u, nodes %zu\n",
-                        (unsigned long long)s.rounds, c.passes, c.windowPasses, c.appliedP, c.appliedH, c.retired, nN);
+                fprintf(stderr, "device scheduler: rounds %llu, passes %u (exact head walks %u), applied P %u H %u, retired %u, nodes %u; kernel time ingest %.1f us, passes %.1f us, select %.1f us\n",
+                        (unsigned long long)s.rounds, c.passes, c.windowPasses, c.appliedP, c.appliedH, c.retired, nN, c.nsIngest * 1e-3, c.nsPasses * 1e-3, c.nsSelect * 1e-3);
             return HPSDF_OK;
         }
 
@@ -514,20 +541,6 @@ namespace hpsdf
                 return HPSDF_ERR_CUDA;
             }
             if ((st = finish(w)) != HPSDF_OK) return st;
-            const double tPack0 = nowMs();
-            st = packCoefficients(t_, ws_.pool.p, stream_);
-            t_.stats.pack_ms = nowMs() - tPack0;
-            if (st == HPSDF_OK && t_.cfg.continuity_enforce)
-            {
-                const double c0 = nowMs();
-                st = continuityPostProcess(t_, o_, stream_);                                          // Octree.cpp:341-344
-                t_.stats.continuity_ms = nowMs() - c0;
-            }
-            const double tFin0 = nowMs();
-            if (st == HPSDF_OK) st = finalizeQueryStructures(t_, stream_);
-            t_.stats.finalize_ms = nowMs() - tFin0;
-            if (st == HPSDF_OK) t_.stats.n_coeffs = t_.nCoeffs;
-            cudaStreamSynchronize(stream_);
             t_.stats.total_ms = nowMs() - t0;
             return st;
         }

@@ -233,9 +233,15 @@ extern "C"
         if (!tree || !out) { setLastError("null pointer"); return HPSDF_ERR_INVALID_ARG; }
         *out = nullptr;
         HPSDF_CUDA(cudaSetDevice(tree->device));
+        hpsdf_octree* src = const_cast<hpsdf_octree*>(tree);
+        hpsdf_status hs = ensureHostNodes(*src);
+        if (hs != HPSDF_OK) return hs;
+        ensureDecisionLog(*src);
+        ensureApplyLog(*src);
         hpsdf_octree* t = new hpsdf_octree();
         t->device = tree->device; t->ctx = tree->ctx; t->cfg = tree->cfg; t->map = tree->map;
-        t->nodes = tree->nodes; t->nCoeffs = tree->nCoeffs; t->stats = tree->stats; t->decisionLog = tree->decisionLog; t->applyLog = tree->applyLog;
+        t->nodes = tree->nodes; t->nNodes = tree->nNodes; t->nCoeffs = tree->nCoeffs; t->nCoeffsPad = tree->nCoeffsPad;
+        t->stats = tree->stats; t->decisionLog = tree->decisionLog; t->applyLog = tree->applyLog;
         hpsdf_status st = allocTreeBlob(*t);
         if (st != HPSDF_OK) { delete t; return st; }
         cudaError_t e = cudaMemcpy(t->dCoeffs, tree->dCoeffs, t->nCoeffs * 8, cudaMemcpyDeviceToDevice);
@@ -280,6 +286,7 @@ extern "C"
     HPSDF_API size_t hpsdf_get_decision_log(const hpsdf_octree* tree, hpsdf_decision_log_entry* out, size_t capacity)
     {
         if (!tree) return 0;
+        ensureDecisionLog(*const_cast<hpsdf_octree*>(tree));
         const size_t n = tree->decisionLog.size();
         if (out) memcpy(out, tree->decisionLog.data(), std::min(n, capacity) * sizeof(hpsdf_decision_log_entry));
         return n;
@@ -288,6 +295,7 @@ extern "C"
     HPSDF_API size_t hpsdf_get_apply_log(const hpsdf_octree* tree, hpsdf_apply_log_entry* out, size_t capacity)
     {
         if (!tree) return 0;
+        ensureApplyLog(*const_cast<hpsdf_octree*>(tree));
         const size_t n = tree->applyLog.size();
         if (out) memcpy(out, tree->applyLog.data(), std::min(n, capacity) * sizeof(hpsdf_apply_log_entry));
         return n;

@@ -97,6 +97,7 @@ namespace hpsdf
         const uint32_t n = (uint32_t)t.nCoeffs;
         if (!n) return HPSDF_OK;
         if (t.nCoeffs >= 0xFFFFFFFFull) { setLastError("continuity: more than 2^32 unknowns"); return HPSDF_ERR_UNSUPPORTED; }
+        { const hpsdf_status hs = ensureHostNodes(t); if (hs != HPSDF_OK) return hs; }          // the face walk below runs on the host
         const double tEnum0 = nowMs();
         std::vector<FaceJobDev> faces;
         faces.reserve(4 * t.nodes.size());

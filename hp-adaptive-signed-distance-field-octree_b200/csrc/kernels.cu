@@ -19,6 +19,7 @@ namespace hpsdf
 #include "continuity_kernels.cuh"
 #include "points_kernel.cuh"
 #include "sched_kernels.cuh"
+#include "finish_kernels.cuh"
 
 namespace hpsdf
 {
@@ -194,6 +195,30 @@ namespace hpsdf
         return e;
     }
 
+    // Uniform depth-4 start of a build (CreateRoot + UniformlyRefine, Octree.cpp:792-801, 112-191) from the per-device templates,
+    // the 4096 coarse jobs, the counters and the layout of round 0: one launch instead of a dozen small copies.
+    __global__ void schedInitKernel(const SchedDev S, const SchedTemplates T, const SchedCounters c0, const RoundLayout lay)
+    {
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < T.nNodes)
+        {
+            S.cell[i] = T.cell[i]; S.child[i] = T.child[i]; S.code[i] = T.code[i]; S.depth[i] = T.depth[i]; S.degree[i] = T.degree[i]; S.state[i] = T.state[i];
+        }
+        if (i < T.nJobs)
+        {
+            S.jobNode[i] = T.jobNode[i]; S.jobPSlot[i] = T.jobPSlot[i]; S.jobPPos[i] = T.jobPPos[i]; S.jobFlags[i] = T.jobFlags[i];
+        }
+        if (i == 0) { *S.ctr = c0; *S.layout = lay; }
+    }
+
+    cudaError_t launchSchedInit(const SchedDev& S, const SchedTemplates& T, const SchedCounters& c0, const RoundLayout& lay, cudaStream_t stream)
+    {
+        cudaError_t e = cudaMemsetAsync(S.allCnt, 0, (char*)S.jobsOut - (char*)S.allCnt, stream);        // the three histograms are adjacent
+        if (e != cudaSuccess) return e;
+        schedInitKernel<<<(T.nNodes + 255) / 256, 256, 0, stream>>>(S, T, c0, lay);
+        return cudaGetLastError();
+    }
+
     cudaError_t launchSchedRound(const SchedDev& S, const uint16_t* coarseOrder, cudaStream_t stream)
     {
         static bool attrSet[16] = { false };
@@ -206,6 +231,43 @@ namespace hpsdf
             attrSet[dev & 15] = true;
         }
         schedRoundKernel<<<1, kSchedThreads, kSchedDynSmem, stream>>>(S, coarseOrder);
+        return cudaGetLastError();
+    }
+
+    size_t finishSortTempBytes(uint32_t capNodes)
+    {
+        size_t bytes = 0;
+        cub::DoubleBuffer<uint32_t> kb((uint32_t*)nullptr, (uint32_t*)nullptr), vb((uint32_t*)nullptr, (uint32_t*)nullptr);
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, kb, vb, (int)capNodes, 0, 31, (cudaStream_t)0);
+        return bytes + 256;
+    }
+
+    // DFS order of the leaves and their coefficient offsets (finish_kernels.cuh); the totals arrive in *hdr (mapped host memory)
+    cudaError_t launchFinishOrder(const SchedDev& S, uint32_t nNodes, uint32_t* keys, uint32_t* vals, uint32_t* keysAlt, uint32_t* valsAlt,
+                                  uint32_t* counter, void* tmp, size_t tmpBytes, uint32_t* cstartOf, uint32_t* padOf, FinishHeader* hdr, uint32_t seq,
+                                  cudaStream_t stream)
+    {
+        cudaError_t e = cudaMemsetAsync(counter, 0, 4, stream);
+        if (e != cudaSuccess) return e;
+        leafKeysKernel<<<(nNodes + 255) / 256, 256, 0, stream>>>(S.state, S.code, nNodes, keys, vals, counter);
+        cub::DoubleBuffer<uint32_t> kb(keys, keysAlt), vb(vals, valsAlt);
+        e = cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, kb, vb, (int)nNodes, 0, 31, stream);
+        if (e != cudaSuccess) return e;
+        leafOffsetsKernel<<<1, 1024, 0, stream>>>(vb.Current(), counter, S.degree, cstartOf, padOf, S.ctr, hdr, seq);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchEmitTree(const SchedDev& S, uint32_t nNodes, const uint32_t* cstartOf, const uint32_t* padOf, const double* pool,
+                               double* packed, QNode* qnodes, unsigned char* image, cudaStream_t stream)
+    {
+        emitTreeKernel<<<(nNodes + 255) / 256, 256, 0, stream>>>(S, nNodes, cstartOf, padOf, pool, packed, qnodes, image);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launchPadCoefficients(const SchedDev& S, uint32_t nNodes, const uint32_t* cstartOf, const uint32_t* padOf, const double* packed,
+                                      double* padded, cudaStream_t stream)
+    {
+        padCoefficientsKernel<<<(nNodes + 255) / 256, 256, 0, stream>>>(S.state, S.degree, nNodes, cstartOf, padOf, packed, padded);
         return cudaGetLastError();
     }
 

@@ -40,7 +40,9 @@ struct hpsdf_octree
     hpsdf::DeviceCtx*   ctx = nullptr;
     hpsdf_config        cfg{};
     hpsdf::RootMap      map{};
-    std::vector<hpsdf::HostNode> nodes;
+    std::vector<hpsdf::HostNode> nodes;          // host copy of the node array; EMPTY after a device-scheduled Create until something
+                                                 // needs it (ensureHostNodes reads the device image back)
+    size_t              nNodes = 0;              // node count (authoritative; nodes.size() may be 0)
     size_t              nCoeffs = 0;
 
     size_t              dBlobBytes = 0;          // capacity of dBlob (it comes from the device's blob cache)
@@ -52,10 +54,21 @@ struct hpsdf_octree
     uint32_t*           dTop = nullptr;          // 16^3 table, or nullptr when the tree is not complete to depth 4
     hpsdf::DeviceTreeView  view{};
     hpsdf::DeviceTreeView* dView = nullptr;      // device copy of `view` (handle of an OCTREE primitive)
+    unsigned char*      dNodeImage = nullptr;    // 56-byte SDF::Node records as ToMemoryBlock writes them (valid when imageValid)
+    bool                imageValid = false;
+    // diagnostics of a device-scheduled build stay on the device until somebody reads them
+    size_t              nLogDev = 0;             // apply-log entries in dApplyLog (fetched by ensureApplyLog)
+    hpsdf_apply_log_entry* dApplyLog = nullptr;
+    double*             dLeafErr = nullptr;      // current error per node at termination (input of the cut-tie log)
+    bool                logOnDevice = false;
 
     hpsdf_build_stats   stats{};
     std::vector<hpsdf_decision_log_entry> decisionLog;
     std::vector<hpsdf_apply_log_entry>    applyLog;
+    // inputs of the cut-tie log of a device-scheduled build; the group is worked out when the decision log is first read
+    size_t              cutLogStart = 0;
+    double              cutTotalBeforeLast = 0.0, cutCheck = 0.0;
+    bool                cutLogPending = false, cutQueueEmpty = false;
 
     // scratch of the host-pointer Query path
     std::mutex          queryMutex;
@@ -70,8 +83,16 @@ struct hpsdf_octree
 namespace hpsdf
 {
     void          setRootMap(const hpsdf_config& cfg, RootMap& map);
-    // One device allocation for everything a finished tree owns; needs t.nodes (with degrees) and t.nCoeffs.
+    // One device allocation for everything a finished tree owns; sized by t.nNodes, t.nCoeffs and t.nCoeffsPad.
     hpsdf_status  allocTreeBlob(hpsdf_octree& t);
+    // t.nCoeffsPad from the host nodes (every leaf starts at an even index of the Query store)
+    size_t        paddedCoeffCount(const hpsdf_octree& t);
+    // Host copy of the node array, read back from the device image if the build left it on the device.
+    hpsdf_status  ensureHostNodes(hpsdf_octree& t);
+    // Completes the decision log of a device-scheduled build (the equal-error group at the termination cut).
+    void          ensureDecisionLog(hpsdf_octree& t);
+    // Fetches the apply log of a device-scheduled build.
+    void          ensureApplyLog(hpsdf_octree& t);
     // Build QNodes, the padded coefficient store and the top table from nodes + dCoeffs.
     hpsdf_status  finalizeQueryStructures(hpsdf_octree& t, cudaStream_t stream);
     // SDF program with handles resolved to device views; fails on malformed programs.

@@ -55,6 +55,7 @@ namespace hpsdf
         unsigned long long levelKey;
         uint32_t levelNode;
         int32_t  aboveLevel;                 // open entries at or above the level that are not refined yet
+        unsigned long long nsIngest, nsPasses, nsSelect;   // time inside the scheduler kernel by phase (diagnostics)
     };
 
     // What the host reads after every scheduler launch (mapped pinned memory).
@@ -67,6 +68,14 @@ namespace hpsdf
         uint32_t cnt[kMaxDegree + 2];        // fits per degree of the next round
         uint32_t nNodes, nOpen, nCached, poolUsed;
         uint32_t pad[6];
+    };
+
+    // Device templates of the uniform depth-4 start (built once per device).
+    struct SchedTemplates
+    {
+        const float4*   cell; const uint32_t* child; const uint32_t* code; const uint8_t* depth; const uint8_t* degree; const uint8_t* state;
+        const uint32_t* jobNode; const uint32_t* jobPSlot; const uint32_t* jobPPos; const uint8_t* jobFlags;
+        uint32_t nNodes, nJobs;
     };
 
     // Everything the scheduler kernels touch. Passed by value.

@@ -64,7 +64,16 @@ namespace hpsdf
         uint32_t tmpU[8];
         double   tmpD[4];
         int      tmpI[4];
+        uint32_t degCnt[kMaxDegree + 2];     // fits per degree of the round being selected
+        unsigned long long tPhase[4];        // globaltimer at the phase boundaries (diagnostics)
     };
+
+    __device__ __forceinline__ unsigned long long globalTimerNs()
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        return t;
+    }
 
     // ---- block-wide primitives (1024 threads, fixed shape => deterministic floating-point results) -------------------------
     __device__ __forceinline__ uint32_t blockExclScanU(uint32_t v, uint32_t* sWarp, uint32_t& total)
@@ -131,6 +140,19 @@ namespace hpsdf
         if ((threadIdx.x & 31) == 0) sWarp[threadIdx.x >> 5] = (uint32_t)v;
         __syncthreads();
         int r = (int)sWarp[threadIdx.x & 31];
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, o);
+        __syncthreads();
+        return r;
+    }
+
+    __device__ __forceinline__ unsigned long long blockSumL(unsigned long long v, unsigned long long* sWarp)
+    {
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if ((threadIdx.x & 31) == 0) sWarp[threadIdx.x >> 5] = v;
+        __syncthreads();
+        unsigned long long r = sWarp[threadIdx.x & 31];
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, o);
         __syncthreads();
@@ -237,9 +259,10 @@ namespace hpsdf
                 node = S.jobNode[j]; p = S.degree[node]; depth = S.depth[node]; err = S.err[node];
                 D = decideJob(S, j, err, p, depth);
             }
-            uint32_t totalChildren = 0, totalLogged = 0;
-            const uint32_t childOff = blockExclScanU(active && D.kind == 2 ? 8u : 0u, sh.warpU, totalChildren);
-            const uint32_t logOff = blockExclScanU(active && D.kind != 0 ? 1u : 0u, sh.warpU, totalLogged);
+            uint32_t packedTotal = 0;
+            const uint32_t packedOff = blockExclScanU((active && D.kind == 2 ? 8u : 0u) | (active && D.kind != 0 ? 1u << 16 : 0u), sh.warpU, packedTotal);
+            const uint32_t childOff = packedOff & 0xFFFFu, logOff = packedOff >> 16;
+            const uint32_t totalChildren = packedTotal & 0xFFFFu, totalLogged = packedTotal >> 16;
             double chunkDelta = 0.0;
             const double inclDelta = blockInclScanD(active ? D.delta : 0.0, sh.warpD, chunkDelta);
             const bool fits = sh.nNodes + totalChildren <= S.capNodes && sh.nOpen + totalChildren <= S.capNodes &&
@@ -316,9 +339,10 @@ namespace hpsdf
                     atomicAdd(&sh.nearTies, 1u);
                 }
             }
-            const int nP = blockSumI(active && D.kind == 1 ? 1 : 0, sh.warpU);
-            const int nR = blockSumI(active && D.kind == 0 ? 1 : 0, sh.warpU);
-            const int above = blockSumI(aboveDelta, sh.warpU);
+            // three counts in one reduction: P jobs | retired | (aboveDelta + 1) per thread
+            const unsigned long long packedSum = blockSumL((unsigned long long)(active && D.kind == 1 ? 1u : 0u) | ((unsigned long long)(active && D.kind == 0 ? 1u : 0u) << 16) |
+                                                           ((unsigned long long)(aboveDelta + 1) << 32), sh.warpL);
+            const int nP = (int)(packedSum & 0xFFFFull), nR = (int)((packedSum >> 16) & 0xFFFFull), above = (int)(packedSum >> 32) - kSchedThreads;
             if (tid == 0)
             {
                 sh.total -= chunkDelta; sh.exactSum -= chunkDelta;
@@ -613,10 +637,22 @@ namespace hpsdf
         double tot = 0.0;
         blockInclScanD(localSum, sh.warpD, tot);
         const int anyBad = blockSumI(bad ? 1 : 0, sh.warpU);
+        // the addends in pop order, computed by everybody; then one thread runs the dependent chain of 4096 additions
+        for (uint32_t k = tid; k < nJobs; k += kSchedThreads) sRun[k] = sErr[order[k]] - kInitialErr;        // Octree.cpp:257: (pErr - err)
+        __syncthreads();
         if (tid == 0)
         {
             double t = 4096.0 * kInitialErr;                                              // Octree.cpp:212
-            for (uint32_t k = 0; k < nJobs; ++k) { t += (sErr[order[k]] - kInitialErr); sRun[k] = t; }   // Octree.cpp:257
+            for (uint32_t k0 = 0; k0 < nJobs; k0 += 8)
+            {
+                double x[8];
+                #pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = sRun[k0 + u];
+                #pragma unroll
+                for (int u = 0; u < 8; ++u) { t += x[u]; x[u] = t; }
+                #pragma unroll
+                for (int u = 0; u < 8; ++u) sRun[k0 + u] = x[u];
+            }
             sh.total = t; sh.exactSum = tot; sh.lastTotal = t; sh.totalBeforeLast = nJobs > 1 ? sRun[nJobs - 2] : t;
             sh.nOpen = nJobs; sh.appliedP += nJobs; sh.nLog = nJobs;
             if (anyBad) sh.done = 3u;                                                     // an error >= 100 or NaN: the host scheduler takes over
@@ -654,31 +690,37 @@ namespace hpsdf
         }
         __syncthreads();
         const uint32_t round = C.round;
+        if (tid == 0) sh.tPhase[0] = globalTimerNs();
 
         // ---- ingest ------------------------------------------------------------------------------------------------------
         if (round == 0) coarseStage(S, sh, coarseOrder, dyn, dyn + 4096, reinterpret_cast<uint16_t*>(dyn + 8192));
         else
         {
             const uint32_t j0 = C.roundJob0, nj = C.roundJobs;
-            for (uint32_t k = tid; k < nj; k += kSchedThreads)
+            for (uint32_t item = tid; item < 9u * nj; item += kSchedThreads)          // one thread per (job, fit): 9 independent record reads per job
             {
+                const uint32_t k = item / 9u, c = item - 9u * k;
                 const uint32_t j = j0 + k, node = S.jobNode[j];
                 const uint32_t depth = S.depth[node];
                 const uint8_t flags = S.jobFlags[j];
-                double* E = S.jobErr + 9 * (size_t)j;
-                if (flags & 1u)
-                    for (uint32_t c = 0; c < 8; ++c)
+                if (c < 8u)
+                {
+                    if (flags & 1u)
                     {
                         const FitRecord r = S.recs[S.jobHPos[j] + c];
-                        E[c] = r.rawErr * nearnessWeightDev(S, r.c0, depth + 1);
+                        S.jobErr[9 * (size_t)j + c] = r.rawErr * nearnessWeightDev(S, r.c0, depth + 1);
                     }
-                if (flags & 2u)
-                {
-                    const FitRecord r = S.recs[S.jobPPos[j]];
-                    E[8] = r.rawErr * nearnessWeightDev(S, r.c0, depth);
                 }
-                S.state[node] = kStCached;
-                S.cached[sh.nCached + k] = j;
+                else
+                {
+                    if (flags & 2u)
+                    {
+                        const FitRecord r = S.recs[S.jobPPos[j]];
+                        S.jobErr[9 * (size_t)j + 8] = r.rawErr * nearnessWeightDev(S, r.c0, depth);
+                    }
+                    S.state[node] = kStCached;
+                    S.cached[sh.nCached + k] = j;
+                }
             }
             __syncthreads();
             if (tid == 0) sh.nCached += nj;
@@ -686,6 +728,7 @@ namespace hpsdf
         }
 
         // ---- passes ----------------------------------------------------------------------------------------------------
+        if (tid == 0) sh.tPhase[3] = globalTimerNs();
         double* sB = dyn;
         uint32_t* sList = reinterpret_cast<uint32_t*>(dyn + kWindow);
         uint32_t* bulk = S.scratch + S.capNodes;                            // second half of the scratch: the jobs of a bulk pass
@@ -716,20 +759,26 @@ namespace hpsdf
             }
             // a level is in force: apply every cached job at or above it (any order gives the same tree)
             uint32_t nBulk = 0;
-            for (uint32_t base = 0; base < sh.nCached; base += kSchedThreads)
+            for (uint32_t base = 0; base < sh.nCached; base += kSchedThreads * 4u)
             {
-                const uint32_t i = base + tid;
-                bool take = false;
-                uint32_t j = 0;
-                if (i < sh.nCached)
+                uint32_t jv[4], mask = 0, cntHere = 0;
+                #pragma unroll
+                for (uint32_t r = 0; r < 4u; ++r)
                 {
-                    j = S.cached[i];
-                    const uint32_t node = S.jobNode[j];
-                    take = !(S.jobFlags[j] & 128u) && atOrAbove(sh, errKey(S.err[node]), node);
+                    const uint32_t i = base + tid * 4u + r;
+                    jv[r] = i < sh.nCached ? S.cached[i] : kNone;
+                }
+                #pragma unroll
+                for (uint32_t r = 0; r < 4u; ++r)
+                {
+                    if (jv[r] == kNone || (S.jobFlags[jv[r]] & 128u)) continue;
+                    const uint32_t node = S.jobNode[jv[r]];
+                    if (atOrAbove(sh, errKey(S.err[node]), node)) { mask |= 1u << r; ++cntHere; }
                 }
                 uint32_t total = 0;
-                const uint32_t off = blockExclScanU(take ? 1u : 0u, sh.warpU, total);
-                if (take) bulk[nBulk + off] = j;
+                uint32_t off = nBulk + blockExclScanU(cntHere, sh.warpU, total);
+                #pragma unroll
+                for (uint32_t r = 0; r < 4u; ++r) if (mask & (1u << r)) bulk[off++] = jv[r];
                 nBulk += total;
             }
             __syncthreads();
@@ -751,6 +800,7 @@ namespace hpsdf
         __syncthreads();
 
         // ---- select the next round + compact the lists ---------------------------------------------------------------------
+        if (tid == 0) sh.tPhase[1] = globalTimerNs();
         uint32_t cnt[kMaxDegree + 2];
         #pragma unroll
         for (int d = 0; d <= kMaxDegree + 1; ++d) cnt[d] = 0;
@@ -758,34 +808,44 @@ namespace hpsdf
         const uint32_t job0 = sh.nJobs;
         if (sh.done == 0u)
         {
+            constexpr uint32_t IT = 8;                              // list entries per thread and chunk: one block-wide scan per 8192 entries
             // compact the cached list (drop applied jobs)
             uint32_t keep = 0;
-            for (uint32_t base = 0; base < sh.nCached; base += kSchedThreads)
+            for (uint32_t base = 0; base < sh.nCached; base += kSchedThreads * IT)
             {
-                const uint32_t i = base + tid;
-                uint32_t j = 0;
-                bool live = false;
-                if (i < sh.nCached) { j = S.cached[i]; live = !(S.jobFlags[j] & 128u); }
+                uint32_t jv[IT];
+                uint32_t liveMask = 0, nl = 0;
+                #pragma unroll
+                for (uint32_t r = 0; r < IT; ++r)
+                {
+                    const uint32_t i = base + tid * IT + r;
+                    jv[r] = i < sh.nCached ? S.cached[i] : kNone;
+                }
+                #pragma unroll
+                for (uint32_t r = 0; r < IT; ++r)
+                    if (jv[r] != kNone && !(S.jobFlags[jv[r]] & 128u)) { liveMask |= 1u << r; ++nl; }
                 uint32_t total = 0;
-                const uint32_t off = blockExclScanU(live ? 1u : 0u, sh.warpU, total);
-                __syncthreads();
-                if (live) S.cached[keep + off] = j;
+                uint32_t off = keep + blockExclScanU(nl, sh.warpU, total);
+                #pragma unroll
+                for (uint32_t r = 0; r < IT; ++r) if (liveMask & (1u << r)) S.cached[off++] = jv[r];
                 keep += total;
                 __syncthreads();
             }
             if (tid == 0) sh.nCached = keep;
+            if (tid < kMaxDegree + 2) sh.degCnt[tid] = 0;
             __syncthreads();
 
             // (a level that splits a group of equal keys selects the whole group: evaluating a leaf early changes nothing)
             double selLevel = sh.levelKey != kNoLevel ? __longlong_as_double((long long)sh.levelKey) : 0.0;
             for (uint32_t k = 0; k < S.speculate; ++k) selLevel *= 0.125;
-            // top-up: sub-bucket in which the pending count reaches minRoundJobs
-            int cutSub = -1;
-            uint32_t needInCut = 0;
+            // top-up: the sub-bucket in which the count of pending leaves reaches minRoundJobs; it is taken whole (its errors
+            // lie within 6 % of each other: the greedy loop is about to reach all of them)
+            int cutSub = 0x7FFFFFFF;
             if (S.minRoundJobs > 1u)
             {
                 uint32_t above = 0;
-                for (int hi = (int)sh.topSub; hi >= 0 && cutSub < 0; hi -= kSchedThreads)
+                bool found = false;
+                for (int hi = (int)sh.topSub; hi >= 0 && !found; hi -= kSchedThreads)
                 {
                     const int idx = hi - tid;
                     const uint32_t pc = idx >= 0 ? S.pendCnt[idx] : 0u;
@@ -793,84 +853,68 @@ namespace hpsdf
                     const uint32_t excl = blockExclScanU(pc, sh.warpU, total);
                     const bool reach = pc > 0u && above + excl + pc >= S.minRoundJobs;
                     const uint32_t first = blockMinU(reach ? (uint32_t)tid : (uint32_t)kSchedThreads, sh.warpU);
-                    if (first < (uint32_t)kSchedThreads)
-                    {
-                        if ((uint32_t)tid == first) { sh.tmpI[0] = idx; sh.tmpU[0] = S.minRoundJobs - (above + excl); }
-                        __syncthreads();
-                        cutSub = sh.tmpI[0]; needInCut = sh.tmpU[0];
-                        __syncthreads();
-                    }
+                    if (first < (uint32_t)kSchedThreads) { cutSub = hi - (int)first; found = true; }
                     else above += total;
                 }
-                if (cutSub < 0) { cutSub = 0; needInCut = 0xFFFFFFFFu; }          // fewer pending leaves than minRoundJobs: all of them
+                if (!found) cutSub = 0;                             // fewer pending leaves than minRoundJobs: all of them
             }
-            // pass A over the open list: compaction + selection (warp-aggregated ballots inside the block-wide scans)
-            uint32_t keepOpen = 0, takenInCut = 0;
-            for (uint32_t base = 0; base < sh.nOpen; base += kSchedThreads)
+            // pass A over the open list: compaction (dead entries out) + selection. Offsets come from one block-wide scan of
+            // packed per-thread counts (warp shuffles + one exchange through shared memory), so list order is preserved.
+            uint32_t keepOpen = 0;
+            for (uint32_t base = 0; base < sh.nOpen; base += kSchedThreads * IT)
             {
-                const uint32_t i = base + tid;
-                uint32_t node = 0;
-                bool live = false, sel = false, inCut = false;
-                double e = 0.0;
-                if (i < sh.nOpen)
+                uint32_t nv[IT];
+                double ev[IT];
+                uint32_t liveMask = 0, selMask = 0, nl = 0, ns = 0;
+                #pragma unroll
+                for (uint32_t r = 0; r < IT; ++r)
                 {
-                    node = S.open[i];
-                    const uint8_t st = S.state[node];
-                    live = st == kStPending || st == kStEval || st == kStCached;
+                    const uint32_t i = base + tid * IT + r;
+                    nv[r] = i < sh.nOpen ? S.open[i] : kNone;
+                }
+                #pragma unroll
+                for (uint32_t r = 0; r < IT; ++r)
+                {
+                    ev[r] = 0.0;
+                    if (nv[r] == kNone) continue;
+                    const uint8_t st = S.state[nv[r]];
+                    if (st == kStPending || st == kStEval || st == kStCached) { liveMask |= 1u << r; ++nl; }
                     if (st == kStPending)
                     {
-                        e = S.err[node];
-                        const int sub = subOfKey(errKey(e));
-                        sel = e >= selLevel || (cutSub >= 0 && sub > cutSub);
-                        inCut = !sel && cutSub >= 0 && sub == cutSub;
+                        ev[r] = S.err[nv[r]];
+                        if (ev[r] >= selLevel || subOfKey(errKey(ev[r])) >= cutSub) { selMask |= 1u << r; ++ns; }
                     }
                 }
-                uint32_t cutTotal = 0;
-                const uint32_t cutOff = blockExclScanU(inCut ? 1u : 0u, sh.warpU, cutTotal);
-                if (inCut && takenInCut + cutOff < needInCut) sel = true;
-                takenInCut += cutTotal;
-                uint32_t liveTotal = 0, selTotal = 0;
-                const uint32_t liveOff = blockExclScanU(live ? 1u : 0u, sh.warpU, liveTotal);
-                const uint32_t selOff = blockExclScanU(sel ? 1u : 0u, sh.warpU, selTotal);
-                __syncthreads();
-                if (live) S.open[keepOpen + liveOff] = node;
-                if (sel)
+                uint32_t total = 0;
+                const uint32_t excl = blockExclScanU(nl | (ns << 16), sh.warpU, total);
+                uint32_t lo = keepOpen + (excl & 0xFFFFu), so = nSel + (excl >> 16);
+                #pragma unroll
+                for (uint32_t r = 0; r < IT; ++r)
                 {
-                    const uint32_t j = job0 + nSel + selOff;
-                    if (j < S.capJobs)
+                    if (liveMask & (1u << r)) S.open[lo++] = nv[r];
+                    if (selMask & (1u << r))
                     {
-                        const uint32_t p = S.degree[node], depth = S.depth[node];
-                        const uint8_t flags = (uint8_t)((depth < S.maxDepth ? 1u : 0u) | (p < S.maxDegree ? 2u : 0u));    // Octree.cpp:600-601: fits that can never be used are skipped
-                        S.jobNode[j] = node; S.jobFlags[j] = flags;
-                        S.jobOf[node] = j;
-                        S.state[node] = kStEval;
-                        atomicSub(S.pendCnt + subOfKey(errKey(e)), 1u);
+                        const uint32_t j = job0 + so++;
+                        if (j < S.capJobs)
+                        {
+                            const uint32_t node = nv[r], p = S.degree[node], depth = S.depth[node];
+                            const uint8_t flags = (uint8_t)((depth < S.maxDepth ? 1u : 0u) | (p < S.maxDegree ? 2u : 0u));    // Octree.cpp:600-601: fits that can never be used are skipped
+                            S.jobNode[j] = node; S.jobFlags[j] = flags;
+                            S.jobOf[node] = j;
+                            S.state[node] = kStEval;
+                            atomicSub(S.pendCnt + subOfKey(errKey(ev[r])), 1u);
+                            if (flags & 1u) atomicAdd(&sh.degCnt[p], 8u);
+                            if (flags & 2u) atomicAdd(&sh.degCnt[p + 1], 1u);
+                        }
                     }
                 }
-                keepOpen += liveTotal; nSel += selTotal;
+                keepOpen += total & 0xFFFFu; nSel += total >> 16;
                 __syncthreads();
             }
             if (tid == 0) sh.nOpen = keepOpen;
             if (job0 + nSel > S.capJobs) { if (tid == 0) sh.done = 2u; nSel = 0; }
             __syncthreads();
-
-            // per-degree counts
-            for (uint32_t base = 0; base < nSel; base += kSchedThreads)
-            {
-                const uint32_t k = base + tid;
-                uint32_t p = 0; uint8_t flags = 0;
-                if (k < nSel) { const uint32_t j = job0 + k; p = S.degree[S.jobNode[j]]; flags = S.jobFlags[j]; }
-                for (int d = 1; d <= kMaxDegree; ++d)
-                {
-                    const uint32_t c = (k < nSel) ? (((flags & 1u) && p == (uint32_t)d ? 8u : 0u) + ((flags & 2u) && p + 1u == (uint32_t)d ? 1u : 0u)) : 0u;
-                    if (__syncthreads_or(c != 0u))
-                    {
-                        uint32_t total = 0;
-                        blockExclScanU(c, sh.warpU, total);
-                        cnt[d] += total;
-                    }
-                }
-            }
+            for (int d = 1; d <= kMaxDegree; ++d) cnt[d] = nSel ? sh.degCnt[d] : 0u;
             // layout: tasks in degree order, slots allocated in task order (contiguous per degree: a rank's shard of a degree
             // group is one contiguous pool range)
             uint32_t groupBegin[kMaxDegree + 2], groupPool[kMaxDegree + 2];
@@ -888,33 +932,49 @@ namespace hpsdf
             // positions of every job's fits inside its groups, in job order; job records for expandJobsKernel
             uint32_t cursor[kMaxDegree + 2];
             for (int d = 0; d <= kMaxDegree + 1; ++d) cursor[d] = groupBegin[d];
-            for (uint32_t base = 0; base < nSel; base += kSchedThreads)
+            for (uint32_t base = 0; base < nSel; base += kSchedThreads * 4u)
             {
-                const uint32_t k = base + tid;
-                uint32_t j = 0, node = 0, p = 0, hPos = 0, pPos = 0;
-                uint8_t flags = 0;
-                if (k < nSel) { j = job0 + k; node = S.jobNode[j]; p = S.degree[node]; flags = S.jobFlags[j]; }
+                uint32_t node[4], p[4], hPos[4], pPos[4];
+                uint8_t flags[4];
+                #pragma unroll
+                for (uint32_t r = 0; r < 4u; ++r)
+                {
+                    const uint32_t k = base + tid * 4u + r;
+                    node[r] = 0; p[r] = 0; flags[r] = 0; hPos[r] = 0; pPos[r] = 0;
+                    if (k < nSel) { const uint32_t j = job0 + k; node[r] = S.jobNode[j]; p[r] = S.degree[node[r]]; flags[r] = S.jobFlags[j]; }
+                }
                 for (int d = 1; d <= kMaxDegree; ++d)
                 {
                     if (!cnt[d]) continue;
-                    const bool h = k < nSel && (flags & 1u) && p == (uint32_t)d, q = k < nSel && (flags & 2u) && p + 1u == (uint32_t)d;
+                    uint32_t mine = 0;
+                    #pragma unroll
+                    for (uint32_t r = 0; r < 4u; ++r)
+                        mine += ((flags[r] & 1u) && p[r] == (uint32_t)d) ? 8u : (((flags[r] & 2u) && p[r] + 1u == (uint32_t)d) ? 1u : 0u);
                     uint32_t total = 0;
-                    const uint32_t off = blockExclScanU(h ? 8u : (q ? 1u : 0u), sh.warpU, total);
-                    if (h) hPos = cursor[d] + off;
-                    if (q) pPos = cursor[d] + off;
+                    uint32_t off = cursor[d] + blockExclScanU(mine, sh.warpU, total);
+                    #pragma unroll
+                    for (uint32_t r = 0; r < 4u; ++r)
+                    {
+                        if ((flags[r] & 1u) && p[r] == (uint32_t)d) { hPos[r] = off; off += 8u; }
+                        else if ((flags[r] & 2u) && p[r] + 1u == (uint32_t)d) { pPos[r] = off; off += 1u; }
+                    }
                     cursor[d] += total;
                 }
-                if (k < nSel)
+                #pragma unroll
+                for (uint32_t r = 0; r < 4u; ++r)
                 {
-                    const uint32_t depth = S.depth[node];
-                    S.jobHPos[j] = hPos; S.jobPPos[j] = pPos;
-                    S.jobHSlot[j] = (flags & 1u) ? groupPool[p] + (hPos - groupBegin[p]) * (uint32_t)coeffCount((int)p) : 0u;
-                    S.jobPSlot[j] = (flags & 2u) ? groupPool[p + 1] + (pPos - groupBegin[p + 1]) * (uint32_t)coeffCount((int)p + 1) : 0u;
-                    const float4 c = S.cell[node];
+                    const uint32_t k = base + tid * 4u + r;
+                    if (k >= nSel) continue;
+                    const uint32_t j = job0 + k, pp = p[r];
+                    const uint32_t depth = S.depth[node[r]];
+                    S.jobHPos[j] = hPos[r]; S.jobPPos[j] = pPos[r];
+                    S.jobHSlot[j] = (flags[r] & 1u) ? groupPool[pp] + (hPos[r] - groupBegin[pp]) * (uint32_t)coeffCount((int)pp) : 0u;
+                    S.jobPSlot[j] = (flags[r] & 2u) ? groupPool[pp + 1] + (pPos[r] - groupBegin[pp + 1]) * (uint32_t)coeffCount((int)pp + 1) : 0u;
+                    const float4 c = S.cell[node[r]];
                     JobDesc o;
                     o.cx = c.x; o.cy = c.y; o.cz = c.z; o.half = c.w;
-                    o.hPos = hPos; o.pPos = pPos; o.src = S.slot[node];
-                    o.depth = (uint8_t)depth; o.degree = (uint8_t)p; o.flags = flags; o.pad = 0;
+                    o.hPos = hPos[r]; o.pPos = pPos[r]; o.src = S.slot[node[r]];
+                    o.depth = (uint8_t)depth; o.degree = (uint8_t)pp; o.flags = flags[r]; o.pad = 0;
                     S.jobsOut[k] = o;
                 }
             }
@@ -942,6 +1002,8 @@ namespace hpsdf
             C.roundJob0 = job0; C.roundJobs = sh.done == 0u ? nSel : 0u;
             C.jobsEvaluated += sh.done == 0u ? nSel : 0u; C.fitsEvaluated += sh.done == 0u ? nTasks : 0u;
             C.round = round + 1;
+            const unsigned long long tEnd = globalTimerNs();
+            C.nsIngest += sh.tPhase[3] - sh.tPhase[0]; C.nsPasses += sh.tPhase[1] - sh.tPhase[3]; C.nsSelect += tEnd - sh.tPhase[1];
             C.levelKey = sh.levelKey; C.levelNode = sh.levelNode; C.aboveLevel = sh.aboveLevel;
             RoundHeader* H = S.hostHdr;
             H->done = sh.done; H->nJobs = sh.done == 0u ? nSel : 0u; H->nTasks = sh.done == 0u ? nTasks : 0u;

@@ -21,7 +21,7 @@ hpsdf_octree::~hpsdf_octree()
 
 namespace hpsdf
 {
-    static size_t paddedCoeffCount(const hpsdf_octree& t)
+    size_t paddedCoeffCount(const hpsdf_octree& t)
     {
         size_t pad = 0;
         for (const HostNode& n : t.nodes) if (n.child == kNoChild) pad += ((size_t)coeffCount(n.degree) + 1u) & ~(size_t)1u;
@@ -31,11 +31,11 @@ namespace hpsdf
     hpsdf_status allocTreeBlob(hpsdf_octree& t)
     {
         auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
-        const size_t nNodes = t.nodes.size();
-        t.nCoeffsPad = paddedCoeffCount(t);
+        const size_t nNodes = t.nNodes;
         const size_t bCoeffs = align(std::max<size_t>(t.nCoeffs, 1) * 8), bPad = align(std::max<size_t>(t.nCoeffsPad, 2) * 8);
-        const size_t bNodes = align(nNodes * sizeof(QNode)), bTop = align(4096 * 4), bView = align(sizeof(DeviceTreeView));
-        const size_t need = bCoeffs + bPad + bNodes + bTop + bView;
+        const size_t bNodes = align(nNodes * sizeof(QNode)), bTop = align(4096 * 4), bView = align(sizeof(DeviceTreeView)), bImage = align(nNodes * 56);
+        const size_t bLog = align(t.nLogDev * sizeof(hpsdf_apply_log_entry)), bErr = t.nLogDev ? align(nNodes * 8) : 0;
+        const size_t need = bCoeffs + bPad + bNodes + bTop + bView + bImage + bLog + bErr;
         if (!t.dBlob || t.dBlobBytes < need || t.dBlobBytes > 4 * need + ((size_t)1 << 20))
         {
             releaseBlob(*t.ctx, t.dBlob, t.dBlobBytes);
@@ -47,13 +47,18 @@ namespace hpsdf
         t.dCoeffsPad = (double*)p; p += bPad;
         t.dNodes = (QNode*)p; p += bNodes;
         t.dTop = (uint32_t*)p; p += bTop;
-        t.dView = (DeviceTreeView*)p;
+        t.dView = (DeviceTreeView*)p; p += bView;
+        t.dNodeImage = (unsigned char*)p; p += bImage;
+        t.dApplyLog = (hpsdf_apply_log_entry*)p; p += bLog;
+        t.dLeafErr = (double*)p;
+        t.imageValid = false; t.logOnDevice = false;
         return HPSDF_OK;
     }
 
     hpsdf_status finalizeQueryStructures(hpsdf_octree& t, cudaStream_t stream)
     {
         const size_t nNodes = t.nodes.size();
+        if (nNodes != t.nNodes) { setLastError("internal: host node array does not match the tree"); return HPSDF_ERR_CUDA; }
         if (nNodes >= 0xFFFFFFFFull) { setLastError("too many nodes for the 32-bit query layout"); return HPSDF_ERR_UNSUPPORTED; }
         // staging: [QNodes][top 4096][src|dst|count segments] in one pinned buffer, one H2D copy
         size_t nLeaves = 0;
@@ -166,7 +171,7 @@ namespace hpsdf
     // ToMemoryBlock (Octree.cpp:424-456)
     hpsdf_status toMemoryBlock(const hpsdf_octree& t, size_t* size, void** ptr)
     {
-        const size_t nC = t.nCoeffs, nN = t.nodes.size();
+        const size_t nC = t.nCoeffs, nN = t.nNodes;
         const size_t bytes = 8 + 8 * nC + 8 + 56 * nN + 80;
         uint8_t* p = (uint8_t*)malloc(bytes);                     // malloc-owned, the caller free()s it (Octree.cpp:445)
         if (!p) { setLastError("malloc failed"); return HPSDF_ERR_OOM; }
@@ -180,7 +185,14 @@ namespace hpsdf
         }
         uint8_t* q = p + 8 + 8 * nC;
         memcpy(q, &nn, 8); q += 8;
-        for (size_t i = 0; i < nN; ++i, q += 56)
+        if (t.nodes.empty() && t.imageValid)
+        {
+            // the build left the SDF::Node records on the device (finish_kernels.cuh: emitTreeKernel): one more copy
+            cudaError_t e = cudaMemcpy(q, t.dNodeImage, 56 * nN, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { free(p); return failCuda(e, "ToMemoryBlock copy"); }
+            q += 56 * nN;
+        }
+        else for (size_t i = 0; i < nN; ++i, q += 56)
         {
             const HostNode& n = t.nodes[i];
             memcpy(q, &n.child, 8); memcpy(q + 8, n.mn, 12); memcpy(q + 20, n.mx, 12);
@@ -242,7 +254,7 @@ namespace hpsdf
                 }
             }
         }
-        t.nCoeffs = nc;
+        t.nCoeffs = nc; t.nNodes = nn; t.nCoeffsPad = paddedCoeffCount(t);
         hpsdf_status st = allocTreeBlob(t);
         if (st != HPSDF_OK) return st;
         HPSDF_CUDA(cudaMemcpy(t.dCoeffs, p + 8, nc * 8, cudaMemcpyHostToDevice));
@@ -251,6 +263,24 @@ namespace hpsdf
         t.stats.n_nodes = nn; t.stats.n_leaves = leaves; t.stats.n_coeffs = nc;
         std::lock_guard<std::mutex> wsLock(*(std::mutex*)t.ctx->wsMutex);
         return finalizeQueryStructures(t, t.ctx->ws.stream);
+    }
+
+    hpsdf_status ensureHostNodes(hpsdf_octree& t)
+    {
+        if (!t.nodes.empty() || t.nNodes == 0) return HPSDF_OK;
+        if (!t.imageValid) { setLastError("internal: tree has neither host nodes nor a device image"); return HPSDF_ERR_CUDA; }
+        std::vector<uint8_t> img(56 * t.nNodes);
+        HPSDF_CUDA(cudaSetDevice(t.device));
+        HPSDF_CUDA(cudaMemcpy(img.data(), t.dNodeImage, img.size(), cudaMemcpyDeviceToHost));
+        t.nodes.resize(t.nNodes);
+        const uint8_t* q = img.data();
+        for (size_t i = 0; i < t.nNodes; ++i, q += 56)
+        {
+            HostNode& n = t.nodes[i];
+            memcpy(&n.child, q, 8); memcpy(n.mn, q + 8, 12); memcpy(n.mx, q + 20, 12);
+            memcpy(&n.cstart, q + 32, 8); n.degree = q[40]; n.depth = q[48];
+        }
+        return HPSDF_OK;
     }
 
     // Octree::Query for host arrays: chunks of points go H2D -> kernel -> D2H on three rotating streams so the copies of
