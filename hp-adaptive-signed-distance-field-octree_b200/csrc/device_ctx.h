@@ -66,6 +66,7 @@ namespace hpsdf
         PinnedBuf<FitRecord> hRecs;
         PinnedBuf<uint32_t>  hSegs;
         DeviceBuf<char>      cont;        // continuity: faces, COO, CSR, CG vectors, CUB temp
+        DeviceBuf<char>      meshTmp;     // hpsdf_mesh_create: uploaded arrays + temporaries of the device mesh builder
         PinnedBuf<FaceJobDev> hFaces;
         cudaStream_t         stream = nullptr;
         cudaEvent_t          ev0 = nullptr, ev1 = nullptr;

@@ -1,5 +1,6 @@
 // kernels.cu — the single device translation unit of libhpsdf: constant tables, all kernels, and their launchers.
 // Built for sm_100a only (B200): nvcc -gencode arch=compute_100a,code=sm_100a.
+#include <algorithm>
 #include <cuda_runtime.h>
 #include "hp_common.h"
 #include "device_ctx.h"
@@ -20,6 +21,7 @@ namespace hpsdf
 #include "points_kernel.cuh"
 #include "sched_kernels.cuh"
 #include "finish_kernels.cuh"
+#include "mesh_build.cuh"
 
 namespace hpsdf
 {
@@ -268,6 +270,130 @@ namespace hpsdf
                                       double* padded, cudaStream_t stream)
     {
         padCoefficientsKernel<<<(nNodes + 255) / 256, 256, 0, stream>>>(S.state, S.degree, nNodes, cstartOf, padOf, packed, padded);
+        return cudaGetLastError();
+    }
+
+    // ---- hpsdf_mesh_create on the device (mesh_build.cuh) ----------------------------------------------------------------------
+    size_t meshBuildTempBytes(uint32_t nTris, uint32_t nNodes)
+    {
+        auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t n = nTris, n3 = 3 * (size_t)nTris;
+        size_t sortEdge = 0, sortLevel = 0, scan = 0;
+        cub::DoubleBuffer<unsigned long long> kb((unsigned long long*)nullptr, (unsigned long long*)nullptr);
+        cub::DoubleBuffer<uint32_t> vb((uint32_t*)nullptr, (uint32_t*)nullptr);
+        cub::DeviceRadixSort::SortPairs(nullptr, sortEdge, kb, vb, (int)n3, 0, 64, (cudaStream_t)0);
+        cub::DeviceRadixSort::SortPairs(nullptr, sortLevel, kb, vb, (int)n, 0, 64, (cudaStream_t)0);
+        cub::DeviceScan::ExclusiveSum(nullptr, scan, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)nNodes, (cudaStream_t)0);
+        const size_t tmp = std::max(std::max(sortEdge, sortLevel), scan);
+        return al(n3 * 8) * 2 + al(n3 * 4) * 3 + al(n * 12) * 3 + al(n * 4) * 5 + al(n * 24) + al((size_t)nNodes * 4) * 7 + al(tmp) + 4096;
+    }
+
+    // Stage A: half-edges. flags (device, 2 words) must be zero; after the stream has drained, flags[0] & 1 = index out of range,
+    // & 2 = an edge without a twin.
+    struct MeshBuildTemp
+    {
+        unsigned long long *keys, *keysAlt;
+        uint32_t *vals, *valsAlt, *he;
+        float *tmn, *tmx, *cen;
+        uint32_t *order, *orderAlt, *segBegin, *segEnd, *segNode;
+        uint32_t *cbounds;
+        uint32_t *parent, *nodeDepth, *arrived, *nodeBegin, *nodeEnd, *wideFlag, *wideIdx;
+        void* cubTmp; size_t cubTmpBytes;
+        uint32_t* flags;
+    };
+
+    MeshBuildTemp carveMeshTemp(char* arena, uint32_t nTris, uint32_t nNodes)
+    {
+        auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t n = nTris, n3 = 3 * (size_t)nTris;
+        MeshBuildTemp T;
+        char* p = arena;
+        auto take = [&](size_t bytes) { char* at = p; p += al(bytes); return at; };
+        T.flags = (uint32_t*)take(256);
+        T.keys = (unsigned long long*)take(n3 * 8); T.keysAlt = (unsigned long long*)take(n3 * 8);
+        T.vals = (uint32_t*)take(n3 * 4); T.valsAlt = (uint32_t*)take(n3 * 4); T.he = (uint32_t*)take(n3 * 4);
+        T.tmn = (float*)take(n * 12); T.tmx = (float*)take(n * 12); T.cen = (float*)take(n * 12);
+        T.order = (uint32_t*)take(n * 4); T.orderAlt = (uint32_t*)take(n * 4); T.segBegin = (uint32_t*)take(n * 4); T.segEnd = (uint32_t*)take(n * 4);
+        T.segNode = (uint32_t*)take(n * 4);
+        T.cbounds = (uint32_t*)take(n * 24);
+        T.parent = (uint32_t*)take((size_t)nNodes * 4); T.nodeDepth = (uint32_t*)take((size_t)nNodes * 4); T.arrived = (uint32_t*)take((size_t)nNodes * 4);
+        T.nodeBegin = (uint32_t*)take((size_t)nNodes * 4); T.nodeEnd = (uint32_t*)take((size_t)nNodes * 4);
+        T.wideFlag = (uint32_t*)take((size_t)nNodes * 4); T.wideIdx = (uint32_t*)take((size_t)nNodes * 4);
+        T.cubTmp = p;
+        size_t sortEdge = 0, sortLevel = 0, scan = 0;
+        cub::DoubleBuffer<unsigned long long> kb((unsigned long long*)nullptr, (unsigned long long*)nullptr);
+        cub::DoubleBuffer<uint32_t> vb((uint32_t*)nullptr, (uint32_t*)nullptr);
+        cub::DeviceRadixSort::SortPairs(nullptr, sortEdge, kb, vb, (int)n3, 0, 64, (cudaStream_t)0);
+        cub::DeviceRadixSort::SortPairs(nullptr, sortLevel, kb, vb, (int)n, 0, 64, (cudaStream_t)0);
+        cub::DeviceScan::ExclusiveSum(nullptr, scan, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)nNodes, (cudaStream_t)0);
+        T.cubTmpBytes = std::max(std::max(sortEdge, sortLevel), scan);
+        return T;
+    }
+
+    static int bitsFor(uint64_t n) { int b = 1; while (b < 63 && (1ull << b) < n) ++b; return b; }
+
+    cudaError_t meshBuildHalfEdgesAndPseudo(const MeshBuildIn& M, const MeshBuildTemp& T, float* pseudo, cudaStream_t stream)
+    {
+        const uint32_t n3 = 3u * M.nTris;
+        const int vb = bitsFor(M.nVerts);
+        cudaError_t e = cudaMemsetAsync(T.flags, 0, 8, stream);
+        if (e != cudaSuccess) return e;
+        meshEdgeKeysKernel<<<(n3 + 255) / 256, 256, 0, stream>>>(M, vb, T.keys, T.vals, T.he, T.flags);
+        cub::DoubleBuffer<unsigned long long> kb(T.keys, T.keysAlt);
+        cub::DoubleBuffer<uint32_t> vbuf(T.vals, T.valsAlt);
+        size_t tb = T.cubTmpBytes;
+        e = cub::DeviceRadixSort::SortPairs(T.cubTmp, tb, kb, vbuf, (int)n3, 0, std::min(64, 2 * vb), stream);
+        if (e != cudaSuccess) return e;
+        meshPairKernel<<<(n3 + 255) / 256, 256, 0, stream>>>(M, vb, kb.Current(), vbuf.Current(), T.he);
+        meshCheckPairedKernel<<<(n3 + 255) / 256, 256, 0, stream>>>(T.he, n3, T.flags);
+        return cudaGetLastError();
+    }
+
+    // Stage B (after the flags were found clean): pseudonormals, the BVH levels, the refit. `levels` = depth of the median-split tree.
+    cudaError_t meshBuildBvh(const MeshBuildIn& M, const MeshBuildTemp& T, const BvhCountTable& counts, uint32_t levels, uint32_t nNodes,
+                             float* pseudo, BvhNode* nodes, const uint32_t** orderOut, cudaStream_t stream)
+    {
+        const uint32_t n = M.nTris;
+        meshPseudoKernel<<<(n + 127) / 128, 128, 0, stream>>>(M, T.he, pseudo);
+        meshTriBoundsKernel<<<(n + 255) / 256, 256, 0, stream>>>(M, T.tmn, T.tmx, T.cen, T.order, T.segBegin, T.segEnd, T.segNode);
+        fillU32Kernel<<<(unsigned)(((size_t)nNodes + 255) / 256), 256, 0, stream>>>(T.nodeDepth, nNodes, 0xFFFFFFFFu);
+        cudaError_t e = cudaMemsetAsync(T.arrived, 0, (size_t)nNodes * 4, stream);
+        if (e != cudaSuccess) return e;
+        cub::DoubleBuffer<unsigned long long> kb(T.keys, T.keysAlt);
+        cub::DoubleBuffer<uint32_t> ob(T.order, T.orderAlt);
+        const int endBit = 32 + bitsFor(n);
+        for (uint32_t level = 0; level <= levels; ++level)
+        {
+            meshSegInitKernel<<<(n + 255) / 256, 256, 0, stream>>>(T.segBegin, T.segEnd, n, T.cbounds);
+            meshSegBoundsKernel<<<(n + 255) / 256, 256, 0, stream>>>(ob.Current(), T.segBegin, T.segEnd, T.cen, n, T.cbounds);
+            meshLevelKeysKernel<<<(n + 255) / 256, 256, 0, stream>>>(ob.Current(), T.segBegin, T.segEnd, T.segNode, T.cen, T.cbounds, n, counts, kb.Current(),
+                                                                      nodes, T.parent, T.nodeDepth, level);
+            if (level == levels) break;                       // the last pass only writes the leaves that appeared at the deepest level
+            size_t tb = T.cubTmpBytes;
+            e = cub::DeviceRadixSort::SortPairs(T.cubTmp, tb, kb, ob, (int)n, 0, std::min(64, endBit), stream);
+            if (e != cudaSuccess) return e;
+            meshLevelSplitKernel<<<(n + 255) / 256, 256, 0, stream>>>(T.segBegin, T.segEnd, T.segNode, n, counts);
+        }
+        meshRefitKernel<<<(nNodes + 255) / 256, 256, 0, stream>>>(nodes, T.parent, ob.Current(), T.tmn, T.tmx, nNodes, T.arrived);
+        *orderOut = ob.Current();
+        return cudaGetLastError();
+    }
+
+    // Stage C (root bounds known -> inflation margin): oriented boxes, 4-wide collapse, triangle slots.
+    cudaError_t meshBuildBoxes(const MeshBuildIn& M, const MeshBuildTemp& T, const uint32_t* order, uint32_t nNodes, double inflate,
+                               const BvhNode* nodes, float* obb, float* wide, float4* triVerts, cudaStream_t stream)
+    {
+        meshNodeRangesKernel<<<(nNodes + 255) / 256, 256, 0, stream>>>(nodes, T.parent, T.nodeDepth, nNodes, M.nTris, T.nodeBegin, T.nodeEnd, T.wideFlag);
+        meshObbKernel<<<(unsigned)(((size_t)nNodes * 32 + 255) / 256), 256, 0, stream>>>(M, nodes, T.nodeBegin, T.nodeEnd, order, nNodes, inflate, obb);
+        if (nNodes == 1) meshWideSingleLeafKernel<<<1, 32, 0, stream>>>(nodes, wide);
+        else
+        {
+            size_t tb = T.cubTmpBytes;
+            const cudaError_t e = cub::DeviceScan::ExclusiveSum(T.cubTmp, tb, T.wideFlag, T.wideIdx, (int)nNodes, stream);
+            if (e != cudaSuccess) return e;
+            meshWideKernel<<<(nNodes + 255) / 256, 256, 0, stream>>>(nodes, obb, T.wideFlag, T.wideIdx, nNodes, inflate, wide);
+        }
+        meshSlotsKernel<<<(M.nTris + 255) / 256, 256, 0, stream>>>(M, order, triVerts);
         return cudaGetLastError();
     }
 
