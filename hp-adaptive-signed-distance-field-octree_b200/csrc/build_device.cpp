@@ -26,6 +26,7 @@ namespace hpsdf
     cudaError_t launchSchedRound(const SchedDev& S, const uint16_t* coarseOrder, cudaStream_t stream);                    // kernels.cu
     cudaError_t launchExpandJobsDev(const JobDesc* dJobs, uint32_t nJobs, const RoundLayout* dLayout, FitTask* dTasks, cudaStream_t stream);
     struct FinishHeader { volatile uint32_t seq; uint32_t nLeaves, nCoeffs, nCoeffsPad; SchedCounters counters; };     // finish_kernels.cuh
+    void        printMeshStats();                                                                                         // fit_kernels.cuh
     cudaError_t launchSchedInit(const SchedDev& S, const SchedTemplates& T, const SchedCounters& c0, const RoundLayout& lay, cudaStream_t stream);
     size_t      finishSortTempBytes(uint32_t capNodes);
     cudaError_t launchFinishOrder(const SchedDev& S, uint32_t nNodes, uint32_t* keys, uint32_t* vals, uint32_t* keysAlt, uint32_t* valsAlt,
@@ -498,6 +499,7 @@ namespace hpsdf
             t_.cutLogStart = c.lastPassLogStart; t_.cutQueueEmpty = c.nOpen == 0; t_.cutLogPending = nL != 0;
             t_.cutTotalBeforeLast = c.totalBeforeLast; t_.cutCheck = check;
             s.n_nodes = nN; s.n_leaves = nLeaves; s.n_coeffs = t_.nCoeffs; ws_.lastNodeCount = nN;
+            if (getenv("HPSDF_MESH_STATS")) printMeshStats();
             if (getenv("HPSDF_DEBUG_ROUNDS"))
                 fprintf(stderr, "device scheduler: rounds %llu, passes %u (exact head walks %u), applied P %u H %u, retired %u, nodes %u; kernel time ingest %.1f us, passes %.1f us, select %.1f us\n",
                         (unsigned long long)s.rounds, c.passes, c.windowPasses, c.appliedP, c.appliedH, c.retired, nN, c.nsIngest * 1e-3, c.nsPasses * 1e-3, c.nsSelect * 1e-3);

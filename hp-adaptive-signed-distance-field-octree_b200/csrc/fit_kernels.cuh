@@ -1,6 +1,7 @@
 // fit_kernels.cuh — host launchers of fitKernel<D, EXT> (the kernel itself: fit_kernel_body.cuh).
 #pragma once
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
 #include "hp_common.h"
@@ -41,6 +42,37 @@ namespace hpsdf
             const double f = sdfEval<1>(sProg, X, Y, Z);
             if (valid) samples[g] = f;
         }
+    }
+
+    // HPSDF_MESH_STATS=1: a 64-word device buffer collecting the node-step histogram of meshSampleKernel (printed by
+    // hpsdf_debug_mesh_stats); nullptr otherwise.
+    static unsigned long long* g_meshStats[16] = { nullptr };
+    static unsigned long long* meshStatsBuffer()
+    {
+        static const bool on = getenv("HPSDF_MESH_STATS") != nullptr;
+        if (!on) return nullptr;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!g_meshStats[dev & 15])
+        {
+            if (cudaMalloc((void**)&g_meshStats[dev & 15], 64 * 8) != cudaSuccess) return nullptr;
+            cudaMemset(g_meshStats[dev & 15], 0, 64 * 8);
+        }
+        return g_meshStats[dev & 15];
+    }
+    void printMeshStats()
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!g_meshStats[dev & 15]) return;
+        unsigned long long h[64];
+        cudaMemcpy(h, g_meshStats[dev & 15], sizeof(h), cudaMemcpyDeviceToHost);
+        cudaMemset(g_meshStats[dev & 15], 0, 64 * 8);
+        unsigned long long n = 0;
+        for (int b = 0; b < 40; ++b) n += h[b];
+        fprintf(stderr, "meshSampleKernel: %llu queries, mean %.1f node steps, max %llu; queries by steps:", n, n ? (double)h[40] / n : 0.0, h[41]);
+        for (int b = 0; b < 40; ++b) if (h[b]) fprintf(stderr, " <%llu: %llu", 1ull << b, h[b]);
+        fprintf(stderr, "\n");
     }
 
     template <int D, bool EXT>
@@ -84,7 +116,7 @@ namespace hpsdf
                     // B200 (870 k-triangle mesh, binary tree: 2 CTAs/24 lanes 113 ms, 3/24 101 ms, 4/24 95 ms, 4/12 88 ms, 4/4 95 ms;
                     // 4-wide tree: 8 or 12 lanes 62.8 ms, 16 63.9, 20 66.3, 24 70.5)
                     meshSampleKernel<<<(unsigned)std::min(want, sms * 4), 256, 0, stream>>>(dTasks + b, total, D, (const DeviceMeshView*)prog.instr[0].handle,
-                                                                                          map, tab, samples, counter, grab, 12);
+                                                                                          map, tab, samples, counter, grab, 12, meshStatsBuffer());
                 }
                 else
                 {

@@ -32,7 +32,8 @@ namespace hpsdf
     __global__ void __launch_bounds__(256, 4)
     meshSampleKernel(const FitTask* __restrict__ tasks, unsigned long long nSamples, int D, const DeviceMeshView* __restrict__ mesh,
                      const RootMap map, const FitTablesDev tab, double* __restrict__ samples, unsigned long long* __restrict__ counter,
-                     const unsigned grab, const int triThreshold)   // (triThreshold: see launchOne)
+                     const unsigned grab, const int triThreshold,   // (triThreshold: see launchOne)
+                     unsigned long long* __restrict__ stats)        // diagnostics (HPSDF_MESH_STATS): histogram of node steps per query, or nullptr
     {
         const float4* __restrict__ wide = (const float4*)mesh->wide;           // 17 float4 per 4-wide node: {child refs}, 4 x oriented box
         const float4* __restrict__ tv = (const float4*)mesh->triVerts;
@@ -49,6 +50,7 @@ namespace hpsdf
         uint32_t cur = kNoNode; float curD = 0.0f;       // wide node (or leaf reference, bit 31) to process and its bound
         uint32_t qLeaf[kMeshQueue]; float qD[kMeshQueue];        // circular: head qh, count qn; entry = leaf reference
         int qh = 0, qn = 0;
+        unsigned steps = 0;                                      // node steps of the lane's current query
         // warp-uniform work cursor
         unsigned long long cursor = 0, grabEnd = 0;
         bool exhausted = false;
@@ -69,6 +71,12 @@ namespace hpsdf
             {
                 samples[sid] = (double)finishHit(mesh, p, h);
                 sid = -1;
+                if (stats)
+                {
+                    atomicAdd(stats + (steps ? 32 - __clz(steps) : 0), 1ull);      // bucket b: steps in [2^(b-1), 2^b)
+                    atomicAdd(stats + 40, (unsigned long long)steps);
+                    atomicMax(stats + 41, (unsigned long long)steps);
+                }
             }
             unsigned idle = __ballot_sync(0xFFFFFFFFu, sid < 0);
             while (idle && !exhausted)
@@ -98,7 +106,7 @@ namespace hpsdf
                            (float)samplePos(roots[k], half, (double)cell.z, map.sizes[2], map.centre[2]));
                     h = MeshHit();
                     h.pt = p;
-                    sp = 0; cur = 0; curD = 0.0f; qh = 0; qn = 0;
+                    sp = 0; cur = 0; curD = 0.0f; qh = 0; qn = 0; steps = 0;
                 }
                 cursor += want < avail ? want : avail;
                 idle = __ballot_sync(0xFFFFFFFFu, sid < 0);
@@ -113,6 +121,7 @@ namespace hpsdf
             {
                 if (wantNode)
                 {
+                    ++steps;
                     if (curD > h.best * 1.000001f) pop();                        // went stale on the stack
                     else if (cur & 0x80000000u)
                     {
