@@ -9,6 +9,8 @@
 //   ConjugateGradient :1751-1756         persistent cooperative CG kernel, x0 = b = lambda * c.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "octree.h"
@@ -97,52 +99,82 @@ namespace hpsdf
         const uint32_t n = (uint32_t)t.nCoeffs;
         if (!n) return HPSDF_OK;
         if (t.nCoeffs >= 0xFFFFFFFFull) { setLastError("continuity: more than 2^32 unknowns"); return HPSDF_ERR_UNSUPPORTED; }
-        { const hpsdf_status hs = ensureHostNodes(t); if (hs != HPSDF_OK) return hs; }          // the face walk below runs on the host
+        BuildWorkspace& ws = t.ctx->ws;
+        auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
         const double tEnum0 = nowMs();
+        // A device-scheduled build leaves the node records on the device: the face pairs are enumerated there. A tree that came
+        // through the host (host scheduler, FromMemoryBlock) walks the reference's recursion on the host.
+        const bool onDevice = t.nodes.empty() && t.imageValid;
         std::vector<FaceJobDev> faces;
-        faces.reserve(4 * t.nodes.size());
-        FaceEnumerator en{ t.nodes, faces };
-        en.nodeProc(0);
-
-        // COO layout: [0, n) the lambda diagonal, then each face's entries
-        uint64_t cur = n;
-        for (FaceJobDev& f : faces)
+        uint64_t cur = n, nFaces = 0;
+        if (onDevice)
         {
-            f.cooOffset = cur;
-            const uint64_t nA = coeffCount(f.degA), nB = coeffCount(f.degB);
-            if (f.analytic) cur += matchCount(f.degA, f.degA, f.dim) + 2ull * matchCount(f.degA, f.degB, f.dim) + matchCount(f.degB, f.degB, f.dim);
-            else            cur += nA * nA + 2 * nA * nB + nB * nB;
+            if (!t.ctx->matchCount)
+            {
+                std::vector<uint32_t> mc(3 * 169, 0);
+                for (int dim = 0; dim < 3; ++dim)
+                    for (int a = 0; a <= kMaxDegree; ++a)
+                        for (int b = 0; b <= kMaxDegree; ++b) mc[dim * 169 + a * 13 + b] = matchCount(a, b, dim);
+                HPSDF_CUDA(cudaMalloc((void**)&t.ctx->matchCount, mc.size() * 4));
+                HPSDF_CUDA(cudaMemcpy(t.ctx->matchCount, mc.data(), mc.size() * 4, cudaMemcpyHostToDevice));
+            }
+            HPSDF_CUDA(ws.segs.reserve((faceEnumTempBytes((uint32_t)t.nNodes) + 3) / 4));
+            unsigned long long totals[2] = { 0, 0 };
+            HPSDF_CUDA(launchFaceCount(t.dNodeImage, (uint32_t)t.nNodes, t.ctx->matchCount, (char*)ws.segs.p, totals, stream));
+            HPSDF_CUDA(cudaStreamSynchronize(stream));
+            const unsigned long long sum = totals[0] + totals[1];
+            nFaces = sum >> 32; cur = n + (sum & 0xFFFFFFFFull);
+            t.stats.kernel_launches += 3;
+        }
+        else
+        {
+            { const hpsdf_status hs = ensureHostNodes(t); if (hs != HPSDF_OK) return hs; }
+            faces.reserve(4 * t.nodes.size());
+            FaceEnumerator en{ t.nodes, faces };
+            en.nodeProc(0);
+            // COO layout: [0, n) the lambda diagonal, then each face's entries
+            for (FaceJobDev& f : faces)
+            {
+                f.cooOffset = cur;
+                const uint64_t nA = coeffCount(f.degA), nB = coeffCount(f.degB);
+                if (f.analytic) cur += matchCount(f.degA, f.degA, f.dim) + 2ull * matchCount(f.degA, f.degB, f.dim) + matchCount(f.degB, f.degB, f.dim);
+                else            cur += nA * nA + 2 * nA * nB + nB * nB;
+            }
+            nFaces = faces.size();
         }
         if (cur >= 0x7FFFFFFFull) { setLastError("continuity: COO exceeds 2^31 entries"); return HPSDF_ERR_UNSUPPORTED; }
 
         t.stats.continuity_enum_ms = nowMs() - tEnum0;
         const double tAsm0 = nowMs();
         // one arena from the persistent build workspace (grow-only): no allocation in steady state
-        BuildWorkspace& ws = t.ctx->ws;
         const int grid = cgGridSize(n, t.ctx->smCount);
         const size_t tmpBytes = cooToCsrTempBytes(cur, n);
-        auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-        const size_t need = al(faces.size() * sizeof(FaceJobDev)) + 6 * al(cur * 8) + al(cur * 4) + al(((size_t)n + 1) * 4) + al((size_t)n * 8)
-                          + al((4 * (size_t)n + 3 * (size_t)grid + 2) * 8) + al(tmpBytes) + 512;
+        const size_t need = al(nFaces * sizeof(FaceJobDev)) + 6 * al(cur * 8) + al(cur * 4) + al(((size_t)n + 1) * 4) + al((size_t)n * 8)
+                          + al((6 * (size_t)n + 4 * (size_t)grid + 8) * 8) + al(tmpBytes) + 512;
         HPSDF_CUDA(ws.cont.reserve(need));
-        HPSDF_CUDA(ws.hFaces.reserve(faces.size() + 1));
-        memcpy(ws.hFaces.p, faces.data(), faces.size() * sizeof(FaceJobDev));
         char* ap = ws.cont.p;
         auto take = [&](size_t bytes) { char* r = ap; ap += al(bytes); return (void*)r; };
-        FaceJobDev* dFaces = (FaceJobDev*)take(faces.size() * sizeof(FaceJobDev));
+        FaceJobDev* dFaces = (FaceJobDev*)take(nFaces * sizeof(FaceJobDev));
         uint64_t* keys = (uint64_t*)take(cur * 8); double* vals = (double*)take(cur * 8);
         uint64_t* keysAlt = (uint64_t*)take(cur * 8); double* valsAlt = (double*)take(cur * 8);
         uint64_t* uniq = (uint64_t*)take(cur * 8);
         CsrDev csr;
         csr.val = (double*)take(cur * 8); csr.col = (uint32_t*)take(cur * 4); csr.rowPtr = (uint32_t*)take(((size_t)n + 1) * 4);
         double* b = (double*)take((size_t)n * 8);
-        double* cgScratch = (double*)take((4 * (size_t)n + 3 * (size_t)grid + 2) * 8);
+        double* cgScratch = (double*)take((6 * (size_t)n + 4 * (size_t)grid + 8) * 8);
         uint32_t* dNum = (uint32_t*)take(256);
         void* tmp = take(tmpBytes);
-        double result[2] = { 0.0, 0.0 };
-        cudaError_t e = cudaMemcpyAsync(dFaces, ws.hFaces.p, faces.size() * sizeof(FaceJobDev), cudaMemcpyHostToDevice, stream);
+        double result[6] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
+        cudaError_t e = cudaSuccess;
+        if (onDevice) e = launchFaceJobs(t.dNodeImage, (uint32_t)t.nNodes, t.ctx->matchCount, (const char*)ws.segs.p, n, dFaces, stream);
+        else
+        {
+            HPSDF_CUDA(ws.hFaces.reserve(faces.size() + 1));
+            memcpy(ws.hFaces.p, faces.data(), faces.size() * sizeof(FaceJobDev));
+            e = cudaMemcpyAsync(dFaces, ws.hFaces.p, faces.size() * sizeof(FaceJobDev), cudaMemcpyHostToDevice, stream);
+        }
         if (e == cudaSuccess) e = launchDiagEmit(keys, vals, n, t.cfg.continuity_strength, stream);
-        if (e == cudaSuccess) e = launchFaceEmit(dFaces, (uint32_t)faces.size(), *t.ctx, keys, vals, stream);
+        if (e == cudaSuccess) e = launchFaceEmit(dFaces, (uint32_t)nFaces, *t.ctx, keys, vals, stream);
         if (e == cudaSuccess) e = cooToCsr(keys, vals, keysAlt, valsAlt, uniq, dNum, tmp, tmpBytes, cur, n, csr, stream);
         t.stats.continuity_assembly_ms = nowMs() - tAsm0;
         const double tCg0 = nowMs();
@@ -154,6 +186,10 @@ namespace hpsdf
         if (e == cudaSuccess) e = launchCg(csr, b, t.dCoeffs, tol, maxIt, grid, cgScratch, result, stream);   // coeffStore <- x (:1756)
         t.stats.continuity_cg_ms = nowMs() - tCg0;
         t.stats.kernel_launches += 6 + 4;      // diag, faces, sort (~4 CUB kernels), reduce, rowptr, scale, cg
+        if (getenv("HPSDF_DEBUG_ROUNDS"))
+            fprintf(stderr, "cg: %d iterations, per iteration: update %.2f us, barrier %.2f us, product %.2f us, barrier + sums %.2f us\n", (int)result[0],
+                    result[2] * 1e-3 / std::max(result[0], 1.0), result[3] * 1e-3 / std::max(result[0], 1.0), result[4] * 1e-3 / std::max(result[0], 1.0),
+                    result[5] * 1e-3 / std::max(result[0], 1.0));
         t.stats.cg_iterations = (uint64_t)result[0];
         t.stats.cg_relative_residual = result[1];
         if (e != cudaSuccess) return failCuda(e, "continuityPostProcess");

@@ -11,15 +11,12 @@
 // conjugate-gradient kernel (sparse matrix-vector product, fused dot products, grid-wide syncs) runs Eigen's CG loop
 // with a diagonal preconditioner until |r|^2 < tol^2 |b|^2.
 #pragma once
-#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 #include "hp_common.h"
 #include "device_ctx.h"
 
 namespace hpsdf
 {
-    namespace cg = cooperative_groups;
-
     __constant__ double c_lp1[kMaxDegree + 1];    // LpX(a, +1) by the reference's recurrence (Octree.cpp:988-1004)
     __constant__ double c_lm1[kMaxDegree + 1];    // LpX(a, -1)
 
@@ -172,6 +169,116 @@ namespace hpsdf
         }
     }
 
+    // ---- face-pair enumeration on the device -------------------------------------------------------------------------------
+    // RunContinuityThreadPool enumerates every leaf-leaf shared face with the NodeProc / FaceProc recursion (Octree.cpp:
+    // 1549-1612, 1663-1714). The same set, one thread per node of the 56-byte SDF::Node image (finish_kernels.cuh): a leaf looks
+    // across each of its six faces for the node of its own depth (or the coarser leaf that contains that position);
+    //   + direction: neighbour is a leaf of the same or a coarser depth  -> face (me = low side, neighbour = high side)
+    //   - direction: neighbour is a strictly coarser leaf                -> face (neighbour = low side, me = high side)
+    // A finer neighbourhood is left to its own leaves, so every shared face is produced exactly once, in node order.
+    struct NodeRec { unsigned long long child; float mn[3], mx[3]; uint32_t cstart; uint32_t degree, depth; };
+    __device__ __forceinline__ NodeRec readNodeRec(const unsigned char* __restrict__ image, uint32_t i)
+    {
+        const uint2* r = reinterpret_cast<const uint2*>(image + 56 * (size_t)i);
+        NodeRec n;
+        const uint2 a = r[0], b = r[1], c = r[2], d = r[3], e = r[4], f = r[5], g = r[6];
+        n.child = ((unsigned long long)a.y << 32) | a.x;
+        n.mn[0] = __uint_as_float(b.x); n.mn[1] = __uint_as_float(b.y); n.mn[2] = __uint_as_float(c.x);
+        n.mx[0] = __uint_as_float(c.y); n.mx[1] = __uint_as_float(d.x); n.mx[2] = __uint_as_float(d.y);
+        n.cstart = e.x; n.degree = f.x & 0xFFu; n.depth = g.x & 0xFFu;
+        return n;
+    }
+
+    // entries an analytic block emits: (i, j) with equal tangential indices (table built on the host, continuity.cpp)
+    struct MatchTable { const uint32_t* count; };       // [dim][degR][degC], 13 x 13 per dim
+
+    __device__ __forceinline__ bool faceAcross(const unsigned char* __restrict__ image, uint32_t me, const NodeRec& M, int axis, int sign,
+                                               const MatchTable mt, FaceJobDev& f, uint32_t& entries)
+    {
+        const uint32_t d = M.depth;
+        uint32_t ic[3];
+        #pragma unroll
+        for (int a = 0; a < 3; ++a) ic[a] = (uint32_t)((M.mn[a] + 0.5f) * (float)(1u << d));         // cell index at depth d (dyadic: exact)
+        if (sign > 0) { if (ic[axis] + 1u >= (1u << d)) return false; ic[axis] += 1u; }
+        else { if (ic[axis] == 0u) return false; ic[axis] -= 1u; }
+        uint32_t cur = 0;
+        NodeRec N = readNodeRec(image, 0);
+        for (uint32_t l = 1; l <= d && N.child != kNoChild; ++l)
+        {
+            const uint32_t sh = d - l;
+            cur = (uint32_t)N.child + ((ic[0] >> sh) & 1u) + 2u * ((ic[1] >> sh) & 1u) + 4u * ((ic[2] >> sh) & 1u);
+            N = readNodeRec(image, cur);
+        }
+        if (N.child != kNoChild) return false;                       // finer leaves over there: they produce the face
+        if (sign < 0 && N.depth >= d) return false;                   // same depth: produced from the other side
+        const NodeRec& A = sign > 0 ? M : N;                           // low side (Octree.cpp:1593-1594)
+        const NodeRec& B = sign > 0 ? N : M;
+        f.cooOffset = 0;
+        f.cstartA = A.cstart; f.cstartB = B.cstart;
+        f.degA = (uint8_t)A.degree; f.degB = (uint8_t)B.degree; f.depthA = (uint8_t)A.depth; f.depthB = (uint8_t)B.depth;
+        f.dim = (uint8_t)axis; f.analytic = A.depth == B.depth; f.pad0 = f.pad1 = 0;       // Octree.cpp:1651
+        f.faceScale = 0.0; f.invDist = 0.0; f.invTr1 = 0.0; f.invTr2 = 0.0;
+        const uint32_t nA = (uint32_t)coeffCount((int)A.degree), nB = (uint32_t)coeffCount((int)B.degree);
+        if (f.analytic)
+        {
+            const uint32_t* mc = mt.count + axis * 169;
+            entries = mc[A.degree * 13 + A.degree] + 2u * mc[A.degree * 13 + B.degree] + mc[B.degree * 13 + B.degree];
+        }
+        else
+        {
+            const int t1 = (axis + 1) % 3, t2 = (axis + 2) % 3;
+            double fs[3];
+            #pragma unroll
+            for (int i = 0; i < 3; ++i)
+            {
+                const float lo = fmaxf(A.mn[i], B.mn[i]), hi = fminf(A.mx[i], B.mx[i]);              // shared face = A.aabb clamped to B.aabb (Octree.cpp:1265-1266)
+                fs[i] = (double)__fsub_rn(hi, lo) * 0.5;
+            }
+            f.faceScale = fs[t1] * fs[t2];
+            const uint32_t diff = A.depth > B.depth ? A.depth - B.depth : B.depth - A.depth;
+            f.invDist = 1.0 / (double)(1u << diff);                                                    // Octree.cpp:1275-1276
+            const NodeRec& fine = A.depth > B.depth ? A : B;
+            const NodeRec& coarse = A.depth > B.depth ? B : A;
+            const float cf1 = __fdiv_rn(__fadd_rn(fine.mn[t1], fine.mx[t1]), 2.0f), cc1 = __fdiv_rn(__fadd_rn(coarse.mn[t1], coarse.mx[t1]), 2.0f);
+            const float cf2 = __fdiv_rn(__fadd_rn(fine.mn[t2], fine.mx[t2]), 2.0f), cc2 = __fdiv_rn(__fadd_rn(coarse.mn[t2], coarse.mx[t2]), 2.0f);
+            f.invTr1 = (double)__fsub_rn(cf1, cc1) / ((double)__fsub_rn(fine.mx[t1], fine.mn[t1]) * 0.5);   // Octree.cpp:1280-1289
+            f.invTr2 = (double)__fsub_rn(cf2, cc2) / ((double)__fsub_rn(fine.mx[t2], fine.mn[t2]) * 0.5);
+            f.invTr1 *= f.invDist; f.invTr2 *= f.invDist;                                              // Octree.cpp:1290
+            entries = nA * nA + 2u * nA * nB + nB * nB;
+        }
+        return true;
+    }
+
+    // pass 1: per node (faces << 32 | COO entries); pass 2 (after an exclusive scan): the face jobs at their offsets
+    __global__ void __launch_bounds__(128) faceEnumKernel(const unsigned char* __restrict__ image, uint32_t nNodes, const MatchTable mt,
+                                                          const unsigned long long* __restrict__ offsets, uint32_t cooBase,
+                                                          unsigned long long* __restrict__ counts, FaceJobDev* __restrict__ faces)
+    {
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= nNodes) return;
+        const NodeRec M = readNodeRec(image, i);
+        unsigned long long mine = 0;
+        if (M.child == kNoChild)
+        {
+            unsigned long long off = offsets ? offsets[i] : 0ull;
+            for (int axis = 0; axis < 3; ++axis)
+                for (int sign = 1; sign >= -1; sign -= 2)
+                {
+                    FaceJobDev f;
+                    uint32_t entries = 0;
+                    if (!faceAcross(image, i, M, axis, sign, mt, f, entries)) continue;
+                    if (faces)
+                    {
+                        f.cooOffset = (unsigned long long)cooBase + (off & 0xFFFFFFFFull);
+                        faces[off >> 32] = f;
+                        off += (1ull << 32) | entries;
+                    }
+                    mine += (1ull << 32) | entries;
+                }
+        }
+        if (counts) counts[i] = mine;
+    }
+
     __global__ void diagEmitKernel(uint64_t* __restrict__ keys, double* __restrict__ vals, uint32_t n, double lambda)
     {
         const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -205,12 +312,15 @@ namespace hpsdf
         double   tol;
         const double* b;          // right-hand side (lambda * c)
         double* x;                // in: initial guess, out: solution
-        double* r; double* p; double* ap; double* invDiag;
-        double* partial;          // 3 * gridDim.x scratch for block partial sums
+        double* r; double* p; double* ap; double* invDiag; double* u; double* s;
+        double* partial;          // 4 * gridDim.x scratch for block partial sums
+        unsigned* barrier;        // arrival counter of the grid-wide barrier (zero at launch)
+        uint32_t eCap, slots;     // shared-memory staging of the matrix: entries per thread, rows per 8-lane group
+        uint32_t rowsStaged;      // 1 = the (start, length) of every owned row is staged too
         double* result;           // [0] iterations, [1] relative residual
     };
 
-    constexpr int kCgThreads = 256;
+    constexpr int kCgThreads = 1024;           // one CTA per SM: 148 arrivals per grid-wide barrier, and up to ~200 KB of shared memory for the matrix
 
     __device__ __forceinline__ double blockSum(double v, double* sRed)
     {
@@ -243,6 +353,42 @@ namespace hpsdf
         return r;
     }
 
+    // three sums at once: one exchange through shared memory instead of three
+    __device__ __forceinline__ void blockSum3(double& a, double& b, double& c, double* sRed3 /* 3 * warps */)
+    {
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, o); b += __shfl_xor_sync(0xFFFFFFFFu, b, o); c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+        }
+        constexpr int W = kCgThreads / 32;
+        if ((threadIdx.x & 31) == 0) { sRed3[threadIdx.x >> 5] = a; sRed3[W + (threadIdx.x >> 5)] = b; sRed3[2 * W + (threadIdx.x >> 5)] = c; }
+        __syncthreads();
+        double sa = 0.0, sb = 0.0, sc = 0.0;
+        #pragma unroll
+        for (int w = 0; w < W; ++w) { sa += sRed3[w]; sb += sRed3[W + w]; sc += sRed3[2 * W + w]; }
+        __syncthreads();
+        a = sa; b = sb; c = sc;
+    }
+
+    // every block sums the block partials of three quantities in the same fixed order (warps 0..2 take one each)
+    __device__ __forceinline__ void gridSum3(const double* p0, const double* p1, const double* p2, int nBlocks, double* sOut3, double& a, double& b, double& c)
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (warp < 3)
+        {
+            const double* p = warp == 0 ? p0 : (warp == 1 ? p1 : p2);
+            double s = 0.0;
+            for (int i = lane; i < nBlocks; i += 32) s += p[i];
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+            if (lane == 0) sOut3[warp] = s;
+        }
+        __syncthreads();
+        a = sOut3[0]; b = sOut3[1]; c = sOut3[2];
+        __syncthreads();
+    }
+
     // y[row] = sum_k val[k] * x[col[k]], 8 lanes per row. A row's columns come in contiguous runs (the coefficient ranges of
     // the leaf itself and of each face neighbour), so 8 lanes reading 8 consecutive entries also gather 8 mostly consecutive
     // x values: val / col are read as full 64 / 32-byte segments and the gathers coalesce into a few sectors. (One thread per
@@ -272,16 +418,135 @@ namespace hpsdf
         }
     }
 
-    // Eigen's conjugate_gradient loop (the shim in the CPU checker has the same structure): diagonal preconditioner.
+    // The matrix does not change during the solve and an 8-lane group owns the same rows in every iteration, so each CTA
+    // keeps ITS part of the CSR arrays in shared memory for the whole kernel (95 k rows x 20 entries x 12 B = 23 MB over 148
+    // SMs = 155 KB per SM): a matrix-vector product then reads nothing from L2 but the gathered vector entries, four
+    // independent gathers in flight per lane. Entries beyond the staged capacity are read from global memory (any size works).
+    struct CgStage
+    {
+        double*   val;        // [entry * blockDim + thread]
+        uint32_t* col;
+        uint32_t* rowStart;   // [slot * groupsPerBlock + group]: CSR start of the row the group owns in that slot
+        uint32_t* rowLen;
+        uint32_t  eCap;       // staged entries per thread
+        uint32_t  slots;      // rows per group (uniform trip count)
+    };
+
+    __device__ __forceinline__ void cgStageMatrix(const CgParams& P, const CgStage& S)
+    {
+        const uint32_t groupsPerGrid = (gridDim.x * kCgThreads) / kCgLanesPerRow, gpb = kCgThreads / kCgLanesPerRow;
+        const uint32_t group = (blockIdx.x * kCgThreads + threadIdx.x) / kCgLanesPerRow, gl = threadIdx.x / kCgLanesPerRow;
+        const uint32_t sub = threadIdx.x % kCgLanesPerRow;
+        uint32_t pos = 0;
+        for (uint32_t q = 0; q < S.slots; ++q)
+        {
+            const uint32_t row = group + q * groupsPerGrid;
+            uint32_t start = 0, len = 0;
+            if (row < P.n) { start = P.rowPtr[row]; len = P.rowPtr[row + 1] - start; }
+            if (sub == 0 && S.rowStart) { S.rowStart[q * gpb + gl] = start; S.rowLen[q * gpb + gl] = len; }
+            for (uint32_t k = sub; k < len; k += kCgLanesPerRow, ++pos)
+                if (pos < S.eCap) { S.val[pos * kCgThreads + threadIdx.x] = P.val[start + k]; S.col[pos * kCgThreads + threadIdx.x] = P.col[start + k]; }
+        }
+        __syncthreads();
+    }
+
+    __device__ __forceinline__ void spmvStaged(const CgParams& P, const CgStage& S, const double* __restrict__ x, double* __restrict__ y,
+                                               const double* __restrict__ dotWith, double& dotAcc)
+    {
+        const uint32_t groupsPerGrid = (gridDim.x * kCgThreads) / kCgLanesPerRow, gpb = kCgThreads / kCgLanesPerRow;
+        const uint32_t group = (blockIdx.x * kCgThreads + threadIdx.x) / kCgLanesPerRow, gl = threadIdx.x / kCgLanesPerRow;
+        const uint32_t sub = threadIdx.x % kCgLanesPerRow;
+        uint32_t pos = 0;
+        for (uint32_t q = 0; q < S.slots; ++q)
+        {
+            const uint32_t row = group + q * groupsPerGrid;
+            uint32_t start = 0, len = 0;
+            if (S.rowStart) { start = S.rowStart[q * gpb + gl]; len = S.rowLen[q * gpb + gl]; }
+            else if (row < P.n) { start = P.rowPtr[row]; len = P.rowPtr[row + 1] - start; }
+            const uint32_t c = len > sub ? (len - sub + kCgLanesPerRow - 1) / kCgLanesPerRow : 0u;
+            double acc = 0.0;
+            for (uint32_t j = 0; j < c; j += 6)
+            {
+                // up to six gathers in flight per lane (a scalar loop would serialise the L2 round trips: issue is in order)
+                double vv[6], xv[6];
+                #pragma unroll
+                for (uint32_t uu = 0; uu < 6; ++uu)
+                {
+                    const uint32_t jj = j + uu;
+                    vv[uu] = 0.0; xv[uu] = 0.0;
+                    if (jj < c)
+                    {
+                        uint32_t cc;
+                        if (pos + jj < S.eCap) { const uint32_t e = (pos + jj) * kCgThreads + threadIdx.x; vv[uu] = S.val[e]; cc = S.col[e]; }
+                        else { const uint32_t k = start + sub + jj * kCgLanesPerRow; vv[uu] = P.val[k]; cc = P.col[k]; }
+                        xv[uu] = x[cc];
+                    }
+                }
+                #pragma unroll
+                for (uint32_t uu = 0; uu < 6; ++uu) acc = fma(vv[uu], xv[uu], acc);
+            }
+            pos += c;
+            acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+            acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+            acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
+            if (sub == 0 && row < P.n) { y[row] = acc; dotAcc = fma(acc, dotWith[row], dotAcc); }
+        }
+    }
+
+    __device__ __forceinline__ unsigned long long cgTimerNs()
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        return t;
+    }
+
+    // Grid-wide barrier for a cooperatively launched (co-resident) grid: one arrival per block on a monotone counter, the
+    // arriving thread spins until `phase * gridDim.x` arrivals are in. Cheaper than cg::grid.sync(), same guarantees here.
+    __device__ __forceinline__ void gridBarrier(unsigned* counter, unsigned& phase)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            ++phase;
+            __threadfence();
+            atomicAdd(counter, 1u);
+            const unsigned target = phase * gridDim.x;
+            while (*((volatile unsigned*)counter) < target) { }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+
+    // Preconditioned conjugate gradients in the Chronopoulos-Gear form: both inner products of an iteration are taken after
+    // its matrix-vector product, so an iteration needs TWO grid-wide barriers (vector update | product + reductions) where
+    // the textbook loop (Eigen's conjugate_gradient, which the reference calls at Octree.cpp:1751-1755) needs three:
+    //     p = u + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s;  u = D^-1 r          | barrier
+    //     w = A u;  gamma' = (r, u);  delta = (w, u);  |r|^2                                    | barrier
+    //     beta = gamma' / gamma;  alpha = gamma' / (delta - beta gamma' / alpha)
+    // Same Krylov iterates in exact arithmetic; Eigen's stopping rule |r|^2 < tol^2 |b|^2 on the recursively updated residual,
+    // diagonal preconditioner, x0 = b = lambda c (Octree.cpp:1738-1755). Deterministic: fixed row -> lane assignment and
+    // fixed-shape reductions.
     __global__ void __launch_bounds__(kCgThreads) cgKernel(const CgParams P)
     {
-        cg::grid_group grid = cg::this_grid();
         __shared__ double sRed[kCgThreads / 32];
+        __shared__ double sRed3[3 * (kCgThreads / 32)];
+        __shared__ double sOut3[3];
         const int nb = gridDim.x;
         const uint32_t tid = blockIdx.x * kCgThreads + threadIdx.x, stride = gridDim.x * kCgThreads;
-        double* part0 = P.partial; double* part1 = P.partial + nb; double* part2 = P.partial + 2 * nb;
+        double* part0 = P.partial; double* part1 = P.partial + nb; double* part2 = P.partial + 2 * nb; double* part3 = P.partial + 3 * nb;
+        unsigned phase = 0;
+        double* u = P.u; double* w = P.ap; double* s = P.s;
+        unsigned long long tA = 0, tB1 = 0, tS = 0, tB2 = 0, t0 = 0, t1 = 0;      // diagnostics (block 0): ns in update | barrier | product | barrier + sums
+        const bool timing = blockIdx.x == 0 && threadIdx.x == 0;
+        extern __shared__ double cgSmem[];
+        CgStage S;
+        S.eCap = P.eCap; S.slots = P.slots;
+        S.val = cgSmem; S.col = reinterpret_cast<uint32_t*>(cgSmem + (size_t)P.eCap * kCgThreads);
+        S.rowStart = P.rowsStaged ? S.col + (size_t)P.eCap * kCgThreads : nullptr;
+        S.rowLen = P.rowsStaged ? S.rowStart + (size_t)P.slots * (kCgThreads / kCgLanesPerRow) : nullptr;
+        cgStageMatrix(P, S);
 
-        // diagonal, r = b - A x0, |b|^2, |r|^2
+        // diagonal; w = A x0 (x0 was written by the launch before: no barrier needed)
         for (uint32_t i = tid; i < P.n; i += stride)
         {
             double d = 1.0;
@@ -289,23 +554,30 @@ namespace hpsdf
             P.invDiag[i] = d;
         }
         double dummy = 0.0;
-        spmvRows(P, P.x, P.ap, P.x, dummy);
-        grid.sync();
-        double bb = 0.0, rr = 0.0, rz = 0.0;
+        spmvStaged(P, S, P.x, w, P.x, dummy);
+        gridBarrier(P.barrier, phase);
+        // r = b - A x0, u = D^-1 r
+        double bb = 0.0, rr = 0.0, ga = 0.0;
         for (uint32_t i = tid; i < P.n; i += stride)
         {
-            const double bi = P.b[i], ri = bi - P.ap[i];
+            const double bi = P.b[i], ri = bi - w[i];
             P.r[i] = ri;
-            const double zi = P.invDiag[i] * ri;
-            P.p[i] = zi;
-            bb = fma(bi, bi, bb); rr = fma(ri, ri, rr); rz = fma(ri, zi, rz);
+            const double ui = P.invDiag[i] * ri;
+            u[i] = ui;
+            P.p[i] = 0.0; s[i] = 0.0;
+            bb = fma(bi, bi, bb); rr = fma(ri, ri, rr); ga = fma(ri, ui, ga);
         }
-        bb = blockSum(bb, sRed); rr = blockSum(rr, sRed); rz = blockSum(rz, sRed);
-        if (threadIdx.x == 0) { part0[blockIdx.x] = bb; part1[blockIdx.x] = rr; part2[blockIdx.x] = rz; }
-        grid.sync();
+        bb = blockSum(bb, sRed); rr = blockSum(rr, sRed); ga = blockSum(ga, sRed);
+        gridBarrier(P.barrier, phase);                 // u complete
+        double de = 0.0;
+        spmvStaged(P, S, u, w, u, de);
+        de = blockSum(de, sRed);
+        if (threadIdx.x == 0) { part0[blockIdx.x] = bb; part1[blockIdx.x] = rr; part2[blockIdx.x] = ga; part3[blockIdx.x] = de; }
+        gridBarrier(P.barrier, phase);
         const double rhs2 = gridSum(part0, nb, sRed);
         double res2 = gridSum(part1, nb, sRed);
-        double absNew = gridSum(part2, nb, sRed);
+        double gamma = gridSum(part2, nb, sRed);
+        double delta = gridSum(part3, nb, sRed);
         const double threshold = fmax(P.tol * P.tol * rhs2, 2.2250738585072014e-308);
         uint32_t it = 0;
         if (rhs2 == 0.0)
@@ -315,36 +587,47 @@ namespace hpsdf
         }
         else if (res2 >= threshold)
         {
+            double alpha = gamma / delta, beta = 0.0;
             while (it < P.maxIt)
             {
-                grid.sync();                                   // p complete, partial buffers free
-                double pAp = 0.0;
-                spmvRows(P, P.p, P.ap, P.p, pAp);
-                pAp = blockSum(pAp, sRed);
-                if (threadIdx.x == 0) part0[blockIdx.x] = pAp;
-                grid.sync();
-                const double alpha = absNew / gridSum(part0, nb, sRed);
-                double rr2 = 0.0, rz2 = 0.0;
+                if (timing) t0 = cgTimerNs();
+                double rr2 = 0.0, ga2 = 0.0;
                 for (uint32_t i = tid; i < P.n; i += stride)
                 {
-                    P.x[i] = fma(alpha, P.p[i], P.x[i]);
-                    const double ri = fma(-alpha, P.ap[i], P.r[i]);
+                    const double pi = fma(beta, P.p[i], u[i]);
+                    const double si = fma(beta, s[i], w[i]);
+                    P.p[i] = pi; s[i] = si;
+                    P.x[i] = fma(alpha, pi, P.x[i]);
+                    const double ri = fma(-alpha, si, P.r[i]);
                     P.r[i] = ri;
-                    rr2 = fma(ri, ri, rr2); rz2 = fma(ri, P.invDiag[i] * ri, rz2);
+                    const double ui = P.invDiag[i] * ri;
+                    u[i] = ui;
+                    rr2 = fma(ri, ri, rr2); ga2 = fma(ri, ui, ga2);
                 }
-                rr2 = blockSum(rr2, sRed); rz2 = blockSum(rz2, sRed);
-                if (threadIdx.x == 0) { part1[blockIdx.x] = rr2; part2[blockIdx.x] = rz2; }
-                grid.sync();
-                res2 = gridSum(part1, nb, sRed);
-                if (res2 < threshold) break;
-                const double absOld = absNew;
-                absNew = gridSum(part2, nb, sRed);
-                const double beta = absNew / absOld;
-                for (uint32_t i = tid; i < P.n; i += stride) P.p[i] = fma(beta, P.p[i], P.invDiag[i] * P.r[i]);
+                if (timing) { t1 = cgTimerNs(); tA += t1 - t0; t0 = t1; }
+                gridBarrier(P.barrier, phase);             // u complete (and the partial buffers of the last iteration are consumed)
+                if (timing) { t1 = cgTimerNs(); tB1 += t1 - t0; t0 = t1; }
+                double de2 = 0.0;
+                spmvStaged(P, S, u, w, u, de2);
+                blockSum3(rr2, ga2, de2, sRed3);
+                if (threadIdx.x == 0) { part1[blockIdx.x] = rr2; part2[blockIdx.x] = ga2; part3[blockIdx.x] = de2; }
+                if (timing) { t1 = cgTimerNs(); tS += t1 - t0; t0 = t1; }
+                gridBarrier(P.barrier, phase);
+                double gammaNew;
+                gridSum3(part1, part2, part3, nb, sOut3, res2, gammaNew, delta);
+                if (timing) { t1 = cgTimerNs(); tB2 += t1 - t0; }
                 ++it;
+                if (res2 < threshold) break;
+                beta = gammaNew / gamma;
+                alpha = gammaNew / (delta - beta * gammaNew / alpha);
+                gamma = gammaNew;
             }
         }
-        if (tid == 0) { P.result[0] = (double)it; P.result[1] = rhs2 > 0.0 ? sqrt(res2 / rhs2) : 0.0; }
+        if (tid == 0)
+        {
+            P.result[0] = (double)it; P.result[1] = rhs2 > 0.0 ? sqrt(res2 / rhs2) : 0.0;
+            P.result[2] = (double)tA; P.result[3] = (double)tB1; P.result[4] = (double)tS; P.result[5] = (double)tB2;
+        }
     }
 
     __global__ void scaleKernel(const double* __restrict__ in, double* __restrict__ out, uint32_t n, double s)

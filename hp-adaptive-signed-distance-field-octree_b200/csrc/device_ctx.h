@@ -88,6 +88,7 @@ namespace hpsdf
         BuildWorkspace ws;
         void*          wsMutex = nullptr;     // std::mutex*, serialises builds on this device
         void*          blobCache = nullptr;   // released tree allocations kept for reuse (context.cpp)
+        uint32_t*      matchCount = nullptr;  // 3 x 13 x 13: entries of an analytic face block per (dim, degree, degree) (continuity.cpp)
     };
 
     // Tree storage comes from a small per-device cache: cudaFree + cudaMalloc per Create cost 0.3-3 ms (cudaFree synchronises
@@ -127,6 +128,11 @@ namespace hpsdf
     cudaError_t launchQueryGradient(const DeviceTreeView& view, const double* dXyz, size_t n, double* dOut, double* dGrad, cudaStream_t stream);
     // continuity (continuity_kernels.cuh)
     cudaError_t launchFaceEmit(const FaceJobDev* dFaces, uint32_t nFaces, const DeviceCtx& ctx, uint64_t* keys, double* vals, cudaStream_t stream);
+    size_t      faceEnumTempBytes(uint32_t nNodes);
+    cudaError_t launchFaceCount(const unsigned char* image, uint32_t nNodes, const uint32_t* matchCount, char* scratch, unsigned long long* hostTotals,
+                                cudaStream_t stream);
+    cudaError_t launchFaceJobs(const unsigned char* image, uint32_t nNodes, const uint32_t* matchCount, const char* scratch, uint32_t cooBase,
+                               FaceJobDev* faces, cudaStream_t stream);
     cudaError_t launchDiagEmit(uint64_t* keys, double* vals, uint32_t n, double lambda, cudaStream_t stream);
     size_t      cooToCsrTempBytes(size_t nCoo, uint32_t n);
     // sort COO by (row, col), sum duplicates, build CSR; every buffer comes from the caller (build workspace)

@@ -170,29 +170,79 @@ namespace hpsdf
         return e;
     }
 
+    // Face enumeration on the device (continuity_kernels.cuh): counts -> exclusive scan -> jobs. totals[0] = faces, totals[1] = COO entries
+    // (without the diagonal), valid after the stream has drained; scratch: 2 * nNodes u64 + CUB temp.
+    size_t faceEnumTempBytes(uint32_t nNodes)
+    {
+        size_t scan = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)nNodes, (cudaStream_t)0);
+        return 2 * (((size_t)nNodes * 8 + 255) & ~(size_t)255) + scan + 512;
+    }
+
+    cudaError_t launchFaceCount(const unsigned char* image, uint32_t nNodes, const uint32_t* matchCount, char* scratch, unsigned long long* hostTotals,
+                                cudaStream_t stream)
+    {
+        const size_t arr = ((size_t)nNodes * 8 + 255) & ~(size_t)255;
+        unsigned long long* counts = (unsigned long long*)scratch;
+        unsigned long long* offsets = (unsigned long long*)(scratch + arr);
+        void* tmp = scratch + 2 * arr;
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, counts, offsets, (int)nNodes, stream);
+        MatchTable mt{ matchCount };
+        faceEnumKernel<<<(nNodes + 127) / 128, 128, 0, stream>>>(image, nNodes, mt, nullptr, 0u, counts, nullptr);
+        cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tb, counts, offsets, (int)nNodes, stream);
+        if (e != cudaSuccess) return e;
+        // totals = offsets[last] + counts[last]
+        e = cudaMemcpyAsync(hostTotals, offsets + (nNodes - 1), 8, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hostTotals + 1, counts + (nNodes - 1), 8, cudaMemcpyDeviceToHost, stream);
+        return e;
+    }
+
+    cudaError_t launchFaceJobs(const unsigned char* image, uint32_t nNodes, const uint32_t* matchCount, const char* scratch, uint32_t cooBase,
+                               FaceJobDev* faces, cudaStream_t stream)
+    {
+        const size_t arr = ((size_t)nNodes * 8 + 255) & ~(size_t)255;
+        const unsigned long long* offsets = (const unsigned long long*)(scratch + arr);
+        MatchTable mt{ matchCount };
+        faceEnumKernel<<<(nNodes + 127) / 128, 128, 0, stream>>>(image, nNodes, mt, offsets, cooBase, nullptr, faces);
+        return cudaGetLastError();
+    }
+
     int cgGridSize(uint32_t n, int smCount)
     {
-        int perSm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, cgKernel, kCgThreads, 0) != cudaSuccess || perSm < 1) return 0;
-        // 8 lanes per row; at most 4 resident blocks per SM (grid syncs get dearer with more blocks)
+        // one CTA of 1024 threads per SM (8 lanes per row), fewer if the system is small
         int grid = (int)(((size_t)n * kCgLanesPerRow + kCgThreads - 1) / kCgThreads);
-        const int cap = smCount * (perSm < 4 ? perSm : 4);
-        if (grid > cap) grid = cap;
+        if (grid > smCount) grid = smCount;
         return grid < 1 ? 1 : grid;
     }
 
-    // scratch: 4 n + 3 grid + 2 doubles
+    // scratch: 6 n + 4 grid + 8 doubles (result[0..5], then the barrier counter); hostResult: 6 doubles (iterations, residual, ns by phase)
     cudaError_t launchCg(const CsrDev& csr, const double* b, double* x, double tol, uint32_t maxIt, int grid, double* scratch,
                          double* hostResult, cudaStream_t stream)
     {
         if (grid < 1) return cudaErrorLaunchOutOfResources;
+        const size_t n = csr.n;
         CgParams P;
         P.rowPtr = csr.rowPtr; P.col = csr.col; P.val = csr.val; P.n = csr.n; P.maxIt = maxIt; P.tol = tol; P.b = b; P.x = x;
-        P.r = scratch; P.p = scratch + csr.n; P.ap = scratch + 2 * (size_t)csr.n; P.invDiag = scratch + 3 * (size_t)csr.n;
-        P.partial = scratch + 4 * (size_t)csr.n; P.result = P.partial + 3 * (size_t)grid;
+        P.r = scratch; P.p = scratch + n; P.ap = scratch + 2 * n; P.invDiag = scratch + 3 * n; P.u = scratch + 4 * n; P.s = scratch + 5 * n;
+        P.partial = scratch + 6 * n; P.result = P.partial + 4 * (size_t)grid; P.barrier = (unsigned*)(P.result + 6);
+        // shared-memory staging of the matrix: rows per 8-lane group, and as many entries per thread as fit (the rest is read
+        // from global memory); 1.3x the mean leaves room for uneven rows
+        const size_t groups = (size_t)grid * kCgThreads / kCgLanesPerRow;
+        P.slots = (uint32_t)((n + groups - 1) / groups);
+        const size_t smemMax = 200 * 1024;
+        size_t rowBytes = (size_t)P.slots * (kCgThreads / kCgLanesPerRow) * 8;
+        P.rowsStaged = rowBytes <= 96 * 1024 ? 1u : 0u;
+        if (!P.rowsStaged) rowBytes = 0;
+        const size_t eWant = (size_t)((double)csr.nnz / ((double)grid * kCgThreads) * 1.3) + 4;
+        const size_t eFit = (smemMax - rowBytes) / ((size_t)kCgThreads * 12);
+        P.eCap = (uint32_t)std::min(eWant, eFit);
+        const size_t smem = (size_t)P.eCap * kCgThreads * 12 + rowBytes;
+        cudaError_t e = cudaFuncSetAttribute(cgKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemMax + 8192));
+        if (e == cudaSuccess) e = cudaMemsetAsync(P.barrier, 0, 8, stream);
         void* args[] = { (void*)&P };
-        cudaError_t e = cudaLaunchCooperativeKernel((void*)cgKernel, dim3(grid), dim3(kCgThreads), args, 0, stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(hostResult, P.result, 16, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaLaunchCooperativeKernel((void*)cgKernel, dim3(grid), dim3(kCgThreads), args, smem, stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hostResult, P.result, 48, cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         return e;
     }
