@@ -27,6 +27,8 @@ namespace hpsdf
     cudaError_t launchExpandJobsDev(const JobDesc* dJobs, uint32_t nJobs, const RoundLayout* dLayout, FitTask* dTasks, cudaStream_t stream);
     struct FinishHeader { volatile uint32_t seq; uint32_t nLeaves, nCoeffs, nCoeffsPad; SchedCounters counters; };     // finish_kernels.cuh
     void        printMeshStats();                                                                                         // fit_kernels.cuh
+    cudaError_t launchSchedIngest(const SchedDev& S, uint32_t nJobs, cudaStream_t stream);
+    cudaError_t launchSchedSelect(const SchedDev& S, uint32_t openEstimate, cudaStream_t stream);
     cudaError_t launchSchedInit(const SchedDev& S, const SchedTemplates& T, const SchedCounters& c0, const RoundLayout& lay, cudaStream_t stream);
     size_t      finishSortTempBytes(uint32_t capNodes);
     cudaError_t launchFinishOrder(const SchedDev& S, uint32_t nNodes, uint32_t* keys, uint32_t* vals, uint32_t* keysAlt, uint32_t* valsAlt,
@@ -191,7 +193,7 @@ namespace hpsdf
             const size_t sizes[] = {
                 n * 16, n * 4, n * 4, n * 8, n * 4, n * 4, n, n, n,                 // nodes: cell child slot err code jobOf depth degree state
                 n * 4, n * 4, n * 4, n * 4, n * 4, n * 72, n,                        // jobs: node hslot pslot hpos ppos err flags
-                n * 4, n * 4, 2 * n * 4,                                             // open, cached, scratch
+                n * 4, n * 4, 2 * n * 4, n * 4, (n / 8192 + 2) * 64,                // open, cached, scratch, second open list, chunk counters
                 (size_t)kSubBuckets * 4, (size_t)kSubBuckets * 8, (size_t)kSubBuckets * 4,
                 n * sizeof(JobDesc), sizeof(RoundLayout), n * sizeof(hpsdf_apply_log_entry), 4096 * sizeof(hpsdf_decision_log_entry),
                 sizeof(SchedCounters),
@@ -208,7 +210,8 @@ namespace hpsdf
             d.jobOf = (uint32_t*)take(); d.depth = (uint8_t*)take(); d.degree = (uint8_t*)take(); d.state = (uint8_t*)take();
             d.jobNode = (uint32_t*)take(); d.jobHSlot = (uint32_t*)take(); d.jobPSlot = (uint32_t*)take(); d.jobHPos = (uint32_t*)take();
             d.jobPPos = (uint32_t*)take(); d.jobErr = (double*)take(); d.jobFlags = (uint8_t*)take();
-            d.open = (uint32_t*)take(); d.cached = (uint32_t*)take(); d.scratch = (uint32_t*)take();
+            d.open = (uint32_t*)take(); d.cached = (uint32_t*)take(); d.scratch = (uint32_t*)take(); d.openAlt = (uint32_t*)take();
+            d.chunkCounts = (uint32_t*)take();
             d.allCnt = (uint32_t*)take(); d.allSum = (unsigned long long*)take(); d.pendCnt = (uint32_t*)take();
             d.jobsOut = (JobDesc*)take(); d.layout = (RoundLayout*)take(); d.log = (hpsdf_apply_log_entry*)take();
             d.decisions = (hpsdf_decision_log_entry*)take(); d.ctr = (SchedCounters*)take();
@@ -355,6 +358,8 @@ namespace hpsdf
             S.maxDegree = o_.max_degree; S.maxDepth = o_.max_depth; S.totalMode = o_.total_mode;
             S.minRoundJobs = o_.min_round_jobs ? o_.min_round_jobs : (progHasExt_ ? 1u : 512u);
             S.speculate = o_.speculate;
+            S.dealJobs = world_ > 1 ? 1u : 0u;
+            S.split = S.dealJobs ? 0u : 1u;
             S.hostHdr = w.devHdr;
             evUsed_ = 0;
             memset(&t_.stats, 0, sizeof(t_.stats));
@@ -386,17 +391,27 @@ namespace hpsdf
 
             // ---- rounds -----------------------------------------------------------------------------------------------------------
             uint32_t poolUsed = c0.poolUsed;
+            uint32_t roundJobs = 0, openEstimate = kCoarseCells;
             for (uint32_t round = 0;; ++round)
             {
                 S.recs = ws_.recs.p;
+                if (S.split && round > 0) { HPSDF_CUDA(launchSchedIngest(S, roundJobs, stream_)); t_.stats.kernel_launches++; }
                 HPSDF_CUDA(launchSchedRound(S, w.coarseOrder, stream_));
                 t_.stats.kernel_launches++;
+                if (S.split)
+                {
+                    // every H job of the round adds 8 entries to the open list before the selection compacts it
+                    HPSDF_CUDA(launchSchedSelect(S, openEstimate + 8u * (roundJobs + 4096u), stream_));
+                    t_.stats.kernel_launches += 2;
+                    std::swap(S.open, S.openAlt);                 // the compacted list of the next round
+                }
                 if ((st = waitHeader(w, round + 1)) != HPSDF_OK) return st;
                 RoundHeader h;
                 memcpy(&h, (const void*)w.hostHdr, sizeof(h));
                 if (getenv("HPSDF_DEBUG_ROUNDS"))
                     fprintf(stderr, "round %u: done %u, next jobs %u tasks %u, nodes %u open %u cached %u pool %u\n", round, h.done, h.nJobs, h.nTasks, h.nNodes, h.nOpen, h.nCached, h.poolUsed);
                 if (h.done) { doneCode = h.done; nNodesFinal_ = h.nNodes; break; }
+                roundJobs = h.nJobs; openEstimate = h.nOpen;
                 if (round > 100000) { setLastError("internal: build does not converge"); return HPSDF_ERR_CUDA; }
                 // next round: tasks in degree order, slots allocated in task order
                 uint32_t nTasks = 0;

@@ -247,6 +247,22 @@ namespace hpsdf
         return e;
     }
 
+    // split mode (single GPU): ingest and selection as multi-block kernels around the single-CTA pass kernel
+    cudaError_t launchSchedIngest(const SchedDev& S, uint32_t nJobs, cudaStream_t stream)
+    {
+        if (!nJobs) return cudaSuccess;
+        schedIngestKernel<<<(9u * nJobs + 255u) / 256u, 256, 0, stream>>>(S);
+        return cudaGetLastError();
+    }
+    cudaError_t launchSchedSelect(const SchedDev& S, uint32_t openEstimate, cudaStream_t stream)
+    {
+        uint32_t blocks = (openEstimate + kSelChunk - 1) / kSelChunk;
+        blocks = blocks < 1u ? 1u : (blocks > 148u ? 148u : blocks);
+        schedSelectCountKernel<<<blocks, kSchedThreads, 0, stream>>>(S);
+        schedSelectScatterKernel<<<blocks, kSchedThreads, 0, stream>>>(S);
+        return cudaGetLastError();
+    }
+
     // Uniform depth-4 start of a build (CreateRoot + UniformlyRefine, Octree.cpp:792-801, 112-191) from the per-device templates,
     // the 4096 coarse jobs, the counters and the layout of round 0: one launch instead of a dozen small copies.
     __global__ void schedInitKernel(const SchedDev S, const SchedTemplates T, const SchedCounters c0, const RoundLayout lay)

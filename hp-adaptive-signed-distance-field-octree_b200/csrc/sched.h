@@ -56,6 +56,10 @@ namespace hpsdf
         uint32_t levelNode;
         int32_t  aboveLevel;                 // open entries at or above the level that are not refined yet
         unsigned long long nsIngest, nsPasses, nsSelect;   // time inside the scheduler kernel by phase (diagnostics)
+        // selection parameters handed from the pass kernel to the multi-block selection kernels (split mode)
+        double   selLevel;
+        int32_t  selCutSub;
+        uint32_t selOpen, selJob0, selPool0; // open-list length before compaction, first job index and first pool slot of the new round
     };
 
     // What the host reads after every scheduler launch (mapped pinned memory).
@@ -101,6 +105,8 @@ namespace hpsdf
         uint8_t*  jobFlags;      // 1 = child fits evaluated, 2 = p-fit evaluated, 128 = applied
         // lists
         uint32_t* open;
+        uint32_t* openAlt;       // split mode: the compacted open list of the next round is written here (the host swaps the two per round)
+        uint32_t* chunkCounts;   // split mode: 16 counters per 8192-entry chunk of the open list
         uint32_t* cached;
         uint32_t* scratch;       // candidates of a window selection (capacity = nodes)
         // histograms
@@ -120,5 +126,7 @@ namespace hpsdf
         // configuration
         double   threshold, nearnessStrength;
         uint32_t nearnessType, maxDegree, maxDepth, totalMode, minRoundJobs, speculate;
+        uint32_t split;          // 1 = ingest and selection run as multi-block kernels around the single-CTA pass kernel
+        uint32_t dealJobs;       // 1 = deal the jobs of a round out along a stride permutation (multi-GPU shards get the same mix)
     };
 }

@@ -697,7 +697,7 @@ namespace hpsdf
         else
         {
             const uint32_t j0 = C.roundJob0, nj = C.roundJobs;
-            for (uint32_t item = tid; item < 9u * nj; item += kSchedThreads)          // one thread per (job, fit): 9 independent record reads per job
+            for (uint32_t item = tid; item < (S.split ? 0u : 9u * nj); item += kSchedThreads)          // one thread per (job, fit): 9 independent record reads per job (split mode: schedIngestKernel did it)
             {
                 const uint32_t k = item / 9u, c = item - 9u * k;
                 const uint32_t j = j0 + k, node = S.jobNode[j];
@@ -858,132 +858,150 @@ namespace hpsdf
                 }
                 if (!found) cutSub = 0;                             // fewer pending leaves than minRoundJobs: all of them
             }
-            // pass A over the open list: compaction (dead entries out) + selection. Offsets come from one block-wide scan of
-            // packed per-thread counts (warp shuffles + one exchange through shared memory), so list order is preserved.
-            uint32_t keepOpen = 0;
-            for (uint32_t base = 0; base < sh.nOpen; base += kSchedThreads * IT)
+            uint32_t lay2Begin[kMaxDegree + 2], lay2Pool[kMaxDegree + 2];
+            for (int d = 0; d <= kMaxDegree + 1; ++d) { lay2Begin[d] = 0; lay2Pool[d] = sh.poolUsed; }
+            if (S.split)
             {
-                uint32_t nv[IT];
-                double ev[IT];
-                uint32_t liveMask = 0, selMask = 0, nl = 0, ns = 0;
-                #pragma unroll
-                for (uint32_t r = 0; r < IT; ++r)
-                {
-                    const uint32_t i = base + tid * IT + r;
-                    nv[r] = i < sh.nOpen ? S.open[i] : kNone;
-                }
-                #pragma unroll
-                for (uint32_t r = 0; r < IT; ++r)
-                {
-                    ev[r] = 0.0;
-                    if (nv[r] == kNone) continue;
-                    const uint8_t st = S.state[nv[r]];
-                    if (st == kStPending || st == kStEval || st == kStCached) { liveMask |= 1u << r; ++nl; }
-                    if (st == kStPending)
-                    {
-                        ev[r] = S.err[nv[r]];
-                        if (ev[r] >= selLevel || subOfKey(errKey(ev[r])) >= cutSub) { selMask |= 1u << r; ++ns; }
-                    }
-                }
-                uint32_t total = 0;
-                const uint32_t excl = blockExclScanU(nl | (ns << 16), sh.warpU, total);
-                uint32_t lo = keepOpen + (excl & 0xFFFFu), so = nSel + (excl >> 16);
-                #pragma unroll
-                for (uint32_t r = 0; r < IT; ++r)
-                {
-                    if (liveMask & (1u << r)) S.open[lo++] = nv[r];
-                    if (selMask & (1u << r))
-                    {
-                        const uint32_t j = job0 + so++;
-                        if (j < S.capJobs)
-                        {
-                            const uint32_t node = nv[r], p = S.degree[node], depth = S.depth[node];
-                            const uint8_t flags = (uint8_t)((depth < S.maxDepth ? 1u : 0u) | (p < S.maxDegree ? 2u : 0u));    // Octree.cpp:600-601: fits that can never be used are skipped
-                            S.jobNode[j] = node; S.jobFlags[j] = flags;
-                            S.jobOf[node] = j;
-                            S.state[node] = kStEval;
-                            atomicSub(S.pendCnt + subOfKey(errKey(ev[r])), 1u);
-                            if (flags & 1u) atomicAdd(&sh.degCnt[p], 8u);
-                            if (flags & 2u) atomicAdd(&sh.degCnt[p + 1], 1u);
-                        }
-                    }
-                }
-                keepOpen += total & 0xFFFFu; nSel += total >> 16;
+                // the multi-block selection kernels take it from here (schedSelectCountKernel / schedSelectScatterKernel)
+                if (tid == 0) { C.selLevel = selLevel; C.selCutSub = cutSub; C.selOpen = sh.nOpen; C.selJob0 = job0; C.selPool0 = sh.poolUsed; }
                 __syncthreads();
             }
-            if (tid == 0) sh.nOpen = keepOpen;
-            if (job0 + nSel > S.capJobs) { if (tid == 0) sh.done = 2u; nSel = 0; }
-            __syncthreads();
-            for (int d = 1; d <= kMaxDegree; ++d) cnt[d] = nSel ? sh.degCnt[d] : 0u;
-            // layout: tasks in degree order, slots allocated in task order (contiguous per degree: a rank's shard of a degree
-            // group is one contiguous pool range)
-            uint32_t groupBegin[kMaxDegree + 2], groupPool[kMaxDegree + 2];
-            uint32_t nTasks = 0;
-            unsigned long long poolNeed = sh.poolUsed;
-            groupBegin[0] = 0; groupPool[0] = sh.poolUsed;
-            for (int d = 1; d <= kMaxDegree; ++d)
+            else
             {
-                groupBegin[d] = nTasks; groupPool[d] = (uint32_t)poolNeed;
-                nTasks += cnt[d]; poolNeed += (unsigned long long)cnt[d] * (unsigned long long)coeffCount(d);
-            }
-            groupBegin[kMaxDegree + 1] = nTasks; groupPool[kMaxDegree + 1] = (uint32_t)poolNeed;
-            if (poolNeed >= 0xFFFFFFF0ull) { if (tid == 0) sh.done = 2u; nSel = 0; }
-            __syncthreads();
-            // positions of every job's fits inside its groups, in job order; job records for expandJobsKernel
-            uint32_t cursor[kMaxDegree + 2];
-            for (int d = 0; d <= kMaxDegree + 1; ++d) cursor[d] = groupBegin[d];
-            for (uint32_t base = 0; base < nSel; base += kSchedThreads * 4u)
-            {
-                uint32_t node[4], p[4], hPos[4], pPos[4];
-                uint8_t flags[4];
-                #pragma unroll
-                for (uint32_t r = 0; r < 4u; ++r)
+                // pass A over the open list: compaction (dead entries out) + selection. Offsets come from one block-wide scan of
+                // packed per-thread counts (warp shuffles + one exchange through shared memory), so list order is preserved.
+                uint32_t keepOpen = 0;
+                for (uint32_t base = 0; base < sh.nOpen; base += kSchedThreads * IT)
                 {
-                    const uint32_t k = base + tid * 4u + r;
-                    node[r] = 0; p[r] = 0; flags[r] = 0; hPos[r] = 0; pPos[r] = 0;
-                    if (k < nSel) { const uint32_t j = job0 + k; node[r] = S.jobNode[j]; p[r] = S.degree[node[r]]; flags[r] = S.jobFlags[j]; }
+                    uint32_t nv[IT];
+                    double ev[IT];
+                    uint32_t liveMask = 0, selMask = 0, nl = 0, ns = 0;
+                    #pragma unroll
+                    for (uint32_t r = 0; r < IT; ++r)
+                    {
+                        const uint32_t i = base + tid * IT + r;
+                        nv[r] = i < sh.nOpen ? S.open[i] : kNone;
+                    }
+                    #pragma unroll
+                    for (uint32_t r = 0; r < IT; ++r)
+                    {
+                        ev[r] = 0.0;
+                        if (nv[r] == kNone) continue;
+                        const uint8_t st = S.state[nv[r]];
+                        if (st == kStPending || st == kStEval || st == kStCached) { liveMask |= 1u << r; ++nl; }
+                        if (st == kStPending)
+                        {
+                            ev[r] = S.err[nv[r]];
+                            if (ev[r] >= selLevel || subOfKey(errKey(ev[r])) >= cutSub) { selMask |= 1u << r; ++ns; }
+                        }
+                    }
+                    uint32_t total = 0;
+                    const uint32_t excl = blockExclScanU(nl | (ns << 16), sh.warpU, total);
+                    uint32_t lo = keepOpen + (excl & 0xFFFFu), so = nSel + (excl >> 16);
+                    #pragma unroll
+                    for (uint32_t r = 0; r < IT; ++r)
+                    {
+                        if (liveMask & (1u << r)) S.open[lo++] = nv[r];
+                        if (selMask & (1u << r))
+                        {
+                            const uint32_t j = job0 + so++;
+                            if (j < S.capJobs)
+                            {
+                                const uint32_t node = nv[r], p = S.degree[node], depth = S.depth[node];
+                                const uint8_t flags = (uint8_t)((depth < S.maxDepth ? 1u : 0u) | (p < S.maxDegree ? 2u : 0u));    // Octree.cpp:600-601: fits that can never be used are skipped
+                                S.jobNode[j] = node; S.jobFlags[j] = flags;
+                                S.jobOf[node] = j;
+                                S.state[node] = kStEval;
+                                atomicSub(S.pendCnt + subOfKey(errKey(ev[r])), 1u);
+                                if (flags & 1u) atomicAdd(&sh.degCnt[p], 8u);
+                                if (flags & 2u) atomicAdd(&sh.degCnt[p + 1], 1u);
+                            }
+                        }
+                    }
+                    keepOpen += total & 0xFFFFu; nSel += total >> 16;
+                    __syncthreads();
                 }
+                if (tid == 0) sh.nOpen = keepOpen;
+                if (job0 + nSel > S.capJobs) { if (tid == 0) sh.done = 2u; nSel = 0; }
+                __syncthreads();
+                for (int d = 1; d <= kMaxDegree; ++d) cnt[d] = nSel ? sh.degCnt[d] : 0u;
+                // layout: tasks in degree order, slots allocated in task order (contiguous per degree: a rank's shard of a degree
+                // group is one contiguous pool range)
+                uint32_t groupBegin[kMaxDegree + 2], groupPool[kMaxDegree + 2];
+                uint32_t nTasks = 0;
+                unsigned long long poolNeed = sh.poolUsed;
+                groupBegin[0] = 0; groupPool[0] = sh.poolUsed;
                 for (int d = 1; d <= kMaxDegree; ++d)
                 {
-                    if (!cnt[d]) continue;
-                    uint32_t mine = 0;
-                    #pragma unroll
-                    for (uint32_t r = 0; r < 4u; ++r)
-                        mine += ((flags[r] & 1u) && p[r] == (uint32_t)d) ? 8u : (((flags[r] & 2u) && p[r] + 1u == (uint32_t)d) ? 1u : 0u);
-                    uint32_t total = 0;
-                    uint32_t off = cursor[d] + blockExclScanU(mine, sh.warpU, total);
+                    groupBegin[d] = nTasks; groupPool[d] = (uint32_t)poolNeed;
+                    nTasks += cnt[d]; poolNeed += (unsigned long long)cnt[d] * (unsigned long long)coeffCount(d);
+                }
+                groupBegin[kMaxDegree + 1] = nTasks; groupPool[kMaxDegree + 1] = (uint32_t)poolNeed;
+                if (poolNeed >= 0xFFFFFFF0ull) { if (tid == 0) sh.done = 2u; nSel = 0; }
+                for (int d = 0; d <= kMaxDegree + 1; ++d) { lay2Begin[d] = groupBegin[d]; lay2Pool[d] = groupPool[d]; }
+                __syncthreads();
+                // positions of every job's fits inside its groups, in job order; job records for expandJobsKernel
+                uint32_t cursor[kMaxDegree + 2];
+                for (int d = 0; d <= kMaxDegree + 1; ++d) cursor[d] = groupBegin[d];
+                // Several GPUs evaluate contiguous shards of each degree group, and list order is spatially coherent (far and near cells
+                // of a mesh cluster; their fits differ 10x in cost): task positions are handed out along a fixed stride permutation of the
+                // round's jobs, so every shard gets the same mix. (Only pool slots and record positions depend on it.)
+                uint32_t dealStride = 1u;
+                if (S.dealJobs && nSel > 2u)
+                    for (const uint32_t cand : { 7919u, 7907u, 7901u, 7883u }) if (nSel % cand != 0u) { dealStride = cand; break; }
+                for (uint32_t base = 0; base < nSel; base += kSchedThreads * 4u)
+                {
+                    uint32_t node[4], p[4], hPos[4], pPos[4];
+                    uint8_t flags[4];
                     #pragma unroll
                     for (uint32_t r = 0; r < 4u; ++r)
                     {
-                        if ((flags[r] & 1u) && p[r] == (uint32_t)d) { hPos[r] = off; off += 8u; }
-                        else if ((flags[r] & 2u) && p[r] + 1u == (uint32_t)d) { pPos[r] = off; off += 1u; }
+                        const uint32_t k = base + tid * 4u + r;
+                        node[r] = 0; p[r] = 0; flags[r] = 0; hPos[r] = 0; pPos[r] = 0;
+                        if (k < nSel) { const uint32_t j = job0 + (uint32_t)(((unsigned long long)k * dealStride) % nSel); node[r] = S.jobNode[j]; p[r] = S.degree[node[r]]; flags[r] = S.jobFlags[j]; }
                     }
-                    cursor[d] += total;
-                }
-                #pragma unroll
-                for (uint32_t r = 0; r < 4u; ++r)
-                {
-                    const uint32_t k = base + tid * 4u + r;
-                    if (k >= nSel) continue;
-                    const uint32_t j = job0 + k, pp = p[r];
-                    const uint32_t depth = S.depth[node[r]];
-                    S.jobHPos[j] = hPos[r]; S.jobPPos[j] = pPos[r];
-                    S.jobHSlot[j] = (flags[r] & 1u) ? groupPool[pp] + (hPos[r] - groupBegin[pp]) * (uint32_t)coeffCount((int)pp) : 0u;
-                    S.jobPSlot[j] = (flags[r] & 2u) ? groupPool[pp + 1] + (pPos[r] - groupBegin[pp + 1]) * (uint32_t)coeffCount((int)pp + 1) : 0u;
-                    const float4 c = S.cell[node[r]];
-                    JobDesc o;
-                    o.cx = c.x; o.cy = c.y; o.cz = c.z; o.half = c.w;
-                    o.hPos = hPos[r]; o.pPos = pPos[r]; o.src = S.slot[node[r]];
-                    o.depth = (uint8_t)depth; o.degree = (uint8_t)pp; o.flags = flags[r]; o.pad = 0;
-                    S.jobsOut[k] = o;
+                    for (int d = 1; d <= kMaxDegree; ++d)
+                    {
+                        if (!cnt[d]) continue;
+                        uint32_t mine = 0;
+                        #pragma unroll
+                        for (uint32_t r = 0; r < 4u; ++r)
+                            mine += ((flags[r] & 1u) && p[r] == (uint32_t)d) ? 8u : (((flags[r] & 2u) && p[r] + 1u == (uint32_t)d) ? 1u : 0u);
+                        uint32_t total = 0;
+                        uint32_t off = cursor[d] + blockExclScanU(mine, sh.warpU, total);
+                        #pragma unroll
+                        for (uint32_t r = 0; r < 4u; ++r)
+                        {
+                            if ((flags[r] & 1u) && p[r] == (uint32_t)d) { hPos[r] = off; off += 8u; }
+                            else if ((flags[r] & 2u) && p[r] + 1u == (uint32_t)d) { pPos[r] = off; off += 1u; }
+                        }
+                        cursor[d] += total;
+                    }
+                    #pragma unroll
+                    for (uint32_t r = 0; r < 4u; ++r)
+                    {
+                        const uint32_t k = base + tid * 4u + r;
+                        if (k >= nSel) continue;
+                        const uint32_t j = job0 + (uint32_t)(((unsigned long long)k * dealStride) % nSel), pp = p[r];
+                        const uint32_t depth = S.depth[node[r]];
+                        S.jobHPos[j] = hPos[r]; S.jobPPos[j] = pPos[r];
+                        S.jobHSlot[j] = (flags[r] & 1u) ? groupPool[pp] + (hPos[r] - groupBegin[pp]) * (uint32_t)coeffCount((int)pp) : 0u;
+                        S.jobPSlot[j] = (flags[r] & 2u) ? groupPool[pp + 1] + (pPos[r] - groupBegin[pp + 1]) * (uint32_t)coeffCount((int)pp + 1) : 0u;
+                        const float4 c = S.cell[node[r]];
+                        JobDesc o;
+                        o.cx = c.x; o.cy = c.y; o.cz = c.z; o.half = c.w;
+                        o.hPos = hPos[r]; o.pPos = pPos[r]; o.src = S.slot[node[r]];
+                        o.depth = (uint8_t)depth; o.degree = (uint8_t)pp; o.flags = flags[r]; o.pad = 0;
+                        S.jobsOut[k] = o;
+                    }
                 }
             }
-            if (tid == 0)
+            if (tid == 0 && !S.split)
             {
                 RoundLayout lay;
-                for (int d = 0; d <= kMaxDegree + 1; ++d) { lay.groupBegin[d] = groupBegin[d]; lay.groupPool[d] = groupPool[d]; }
+                for (int d = 0; d <= kMaxDegree + 1; ++d) { lay.groupBegin[d] = lay2Begin[d]; lay.groupPool[d] = lay2Pool[d]; }
                 *S.layout = lay;
-                if (sh.done == 0u) { sh.poolUsed = (uint32_t)poolNeed; sh.nJobs = job0 + nSel; }
+                if (sh.done == 0u) { sh.poolUsed = lay2Pool[kMaxDegree + 1]; sh.nJobs = job0 + nSel; }
                 if (nSel == 0u && sh.done == 0u) sh.done = 4u;               // nothing to evaluate and not terminated: internal error
             }
             __syncthreads();
@@ -1005,13 +1023,222 @@ namespace hpsdf
             const unsigned long long tEnd = globalTimerNs();
             C.nsIngest += sh.tPhase[3] - sh.tPhase[0]; C.nsPasses += sh.tPhase[1] - sh.tPhase[3]; C.nsSelect += tEnd - sh.tPhase[1];
             C.levelKey = sh.levelKey; C.levelNode = sh.levelNode; C.aboveLevel = sh.aboveLevel;
-            RoundHeader* H = S.hostHdr;
-            H->done = sh.done; H->nJobs = sh.done == 0u ? nSel : 0u; H->nTasks = sh.done == 0u ? nTasks : 0u;
-            for (int d = 0; d <= kMaxDegree + 1; ++d) H->cnt[d] = sh.done == 0u ? cnt[d] : 0u;
-            H->nNodes = sh.nNodes; H->nOpen = sh.nOpen; H->nCached = sh.nCached; H->poolUsed = sh.poolUsed;
-            __threadfence_system();
-            H->seq = round + 1;
-            __threadfence_system();
+            if (!(S.split && sh.done == 0u))               // split mode: the selection kernel publishes the header of a round that goes on
+            {
+                RoundHeader* H = S.hostHdr;
+                H->done = sh.done; H->nJobs = sh.done == 0u ? nSel : 0u; H->nTasks = sh.done == 0u ? nTasks : 0u;
+                for (int d = 0; d <= kMaxDegree + 1; ++d) H->cnt[d] = sh.done == 0u ? cnt[d] : 0u;
+                H->nNodes = sh.nNodes; H->nOpen = sh.nOpen; H->nCached = sh.nCached; H->poolUsed = sh.poolUsed;
+                __threadfence_system();
+                H->seq = round + 1;
+                __threadfence_system();
+            }
+        }
+    }
+
+    // ---- split mode: ingest and selection as multi-block kernels around the single-CTA pass kernel -------------------------------
+    // (single GPU; several GPUs deal the jobs out along a stride permutation, which the single-CTA selection above does)
+    __global__ void __launch_bounds__(256) schedIngestKernel(const SchedDev S)
+    {
+        const SchedCounters& C = *S.ctr;
+        const uint32_t j0 = C.roundJob0, nj = C.roundJobs, nCached = C.nCached;
+        const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+        if (item >= 9u * nj) return;
+        const uint32_t k = item / 9u, c = item - 9u * k;
+        const uint32_t j = j0 + k, node = S.jobNode[j];
+        const uint32_t depth = S.depth[node];
+        const uint8_t flags = S.jobFlags[j];
+        if (c < 8u)
+        {
+            if (flags & 1u)
+            {
+                const FitRecord r = S.recs[S.jobHPos[j] + c];
+                S.jobErr[9 * (size_t)j + c] = r.rawErr * nearnessWeightDev(S, r.c0, depth + 1);
+            }
+        }
+        else
+        {
+            if (flags & 2u)
+            {
+                const FitRecord r = S.recs[S.jobPPos[j]];
+                S.jobErr[9 * (size_t)j + 8] = r.rawErr * nearnessWeightDev(S, r.c0, depth);
+            }
+            S.state[node] = kStCached;
+            S.cached[nCached + k] = j;
+        }
+    }
+
+    constexpr uint32_t kSelItems = 8, kSelChunk = kSchedThreads * kSelItems;
+
+    // what one thread sees of its 8 consecutive open-list entries
+    struct SelView
+    {
+        uint32_t node[kSelItems];
+        double   err[kSelItems];
+        uint32_t liveMask, selMask, nLive, nSel;
+    };
+    __device__ __forceinline__ void selLoad(const SchedDev& S, const SchedCounters& C, uint32_t chunk, SelView& V)
+    {
+        const uint32_t base = chunk * kSelChunk + threadIdx.x * kSelItems;
+        V.liveMask = V.selMask = V.nLive = V.nSel = 0;
+        #pragma unroll
+        for (uint32_t r = 0; r < kSelItems; ++r) V.node[r] = base + r < C.selOpen ? S.open[base + r] : kNone;
+        #pragma unroll
+        for (uint32_t r = 0; r < kSelItems; ++r)
+        {
+            V.err[r] = 0.0;
+            if (V.node[r] == kNone) continue;
+            const uint8_t st = S.state[V.node[r]];
+            if (st == kStPending || st == kStEval || st == kStCached) { V.liveMask |= 1u << r; ++V.nLive; }
+            if (st == kStPending)
+            {
+                V.err[r] = S.err[V.node[r]];
+                if (V.err[r] >= C.selLevel || subOfKey(errKey(V.err[r])) >= C.selCutSub) { V.selMask |= 1u << r; ++V.nSel; }
+            }
+        }
+    }
+
+    // pass 1: per chunk of 8192 entries: live entries, selected entries, fits per degree -> chunkCounts[chunk][16]
+    __global__ void __launch_bounds__(kSchedThreads, 1) schedSelectCountKernel(const SchedDev S)
+    {
+        __shared__ uint32_t sCnt[16];
+        const SchedCounters& C = *S.ctr;
+        if (C.done != 0u) return;
+        const uint32_t nChunks = (C.selOpen + kSelChunk - 1) / kSelChunk;
+        for (uint32_t chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x)
+        {
+            if (threadIdx.x < 16) sCnt[threadIdx.x] = 0;
+            __syncthreads();
+            SelView V;
+            selLoad(S, C, chunk, V);
+            #pragma unroll
+            for (uint32_t r = 0; r < kSelItems; ++r)
+                if (V.selMask & (1u << r))
+                {
+                    const uint32_t node = V.node[r], p = S.degree[node], depth = S.depth[node];
+                    if (depth < S.maxDepth) atomicAdd(&sCnt[2 + p], 8u);
+                    if (p < S.maxDegree) atomicAdd(&sCnt[2 + p + 1], 1u);
+                }
+            uint32_t packed = V.nLive | (V.nSel << 16);
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
+            if ((threadIdx.x & 31) == 0) { atomicAdd(&sCnt[0], packed & 0xFFFFu); atomicAdd(&sCnt[1], packed >> 16); }
+            __syncthreads();
+            if (threadIdx.x < 16) S.chunkCounts[chunk * 16 + threadIdx.x] = sCnt[threadIdx.x];
+            __syncthreads();
+        }
+    }
+
+    // pass 2: offsets from the chunk counts; compacted open list -> openAlt; the selected leaves become jobs with deterministic task
+    // positions (list order); block 0 publishes the round: layout, counters, header
+    __global__ void __launch_bounds__(kSchedThreads, 1) schedSelectScatterKernel(const SchedDev S)
+    {
+        __shared__ uint32_t sBase[16], sTotal[16], sWarp[32];
+        SchedCounters& C = *S.ctr;
+        if (C.done != 0u) return;
+        const uint32_t tid = threadIdx.x;
+        const uint32_t nChunks = (C.selOpen + kSelChunk - 1) / kSelChunk;
+        const uint32_t job0 = C.selJob0, poolUsed0 = C.selPool0, round = C.round;           // (the pass kernel already advanced `round`)
+        for (uint32_t chunk = blockIdx.x; chunk < (nChunks ? nChunks : 1u); chunk += gridDim.x)
+        {
+            // totals over all chunks and the sums over the chunks before this one, 16 counters each
+            if (tid < 16) { sBase[tid] = 0; sTotal[tid] = 0; }
+            __syncthreads();
+            for (uint32_t e = tid; e < nChunks * 16u; e += kSchedThreads)
+            {
+                const uint32_t v = S.chunkCounts[e];
+                if (v) { atomicAdd(&sTotal[e & 15u], v); if ((e >> 4) < chunk) atomicAdd(&sBase[e & 15u], v); }
+            }
+            __syncthreads();
+            const uint32_t nSel = sTotal[1];
+            uint32_t groupBegin[kMaxDegree + 2], groupPool[kMaxDegree + 2];
+            uint32_t nTasks = 0;
+            unsigned long long poolNeed = poolUsed0;
+            groupBegin[0] = 0; groupPool[0] = poolUsed0;
+            for (int d = 1; d <= kMaxDegree; ++d)
+            {
+                groupBegin[d] = nTasks; groupPool[d] = (uint32_t)poolNeed;
+                nTasks += sTotal[2 + d]; poolNeed += (unsigned long long)sTotal[2 + d] * (unsigned long long)coeffCount(d);
+            }
+            groupBegin[kMaxDegree + 1] = nTasks; groupPool[kMaxDegree + 1] = (uint32_t)poolNeed;
+            const bool overflow = job0 + nSel > S.capJobs || poolNeed >= 0xFFFFFFF0ull;
+            const uint32_t doneCode = overflow ? 2u : (nSel == 0u ? 4u : 0u);
+            if (chunk == 0 && tid == 0)
+            {
+                // publish the round (the pass kernel left the header alone)
+                RoundLayout lay;
+                for (int d = 0; d <= kMaxDegree + 1; ++d) { lay.groupBegin[d] = groupBegin[d]; lay.groupPool[d] = groupPool[d]; }
+                *S.layout = lay;
+                RoundHeader* H = S.hostHdr;
+                H->done = doneCode; H->nJobs = doneCode ? 0u : nSel; H->nTasks = doneCode ? 0u : nTasks;
+                for (int d = 0; d <= kMaxDegree + 1; ++d) H->cnt[d] = (doneCode || d < 1 || d > kMaxDegree) ? 0u : sTotal[2 + d];
+                H->nNodes = C.nNodes; H->nOpen = sTotal[0]; H->nCached = C.nCached; H->poolUsed = doneCode ? poolUsed0 : (uint32_t)poolNeed;
+                __threadfence_system();
+                H->seq = round;
+                __threadfence_system();
+            }
+            if (doneCode) { if (chunk == 0 && tid == 0) C.done = doneCode; return; }
+            SelView V;
+            selLoad(S, C, chunk, V);
+            // offsets inside the chunk (list order)
+            uint32_t total = 0;
+            const uint32_t excl = blockExclScanU(V.nLive | (V.nSel << 16), sWarp, total);
+            uint32_t lo = sBase[0] + (excl & 0xFFFFu), so = sBase[1] + (excl >> 16);
+            uint32_t p[kSelItems], hPos[kSelItems], pPos[kSelItems];
+            uint8_t flags[kSelItems];
+            #pragma unroll
+            for (uint32_t r = 0; r < kSelItems; ++r)
+            {
+                p[r] = 0; flags[r] = 0; hPos[r] = 0; pPos[r] = 0;
+                if (V.selMask & (1u << r))
+                {
+                    const uint32_t node = V.node[r];
+                    p[r] = S.degree[node];
+                    flags[r] = (uint8_t)((S.depth[node] < S.maxDepth ? 1u : 0u) | (p[r] < S.maxDegree ? 2u : 0u));    // Octree.cpp:600-601
+                }
+            }
+            for (int d = 1; d <= kMaxDegree; ++d)
+            {
+                if (!S.chunkCounts[chunk * 16 + 2 + d]) continue;                       // no fit of this degree in this chunk
+                uint32_t mine = 0;
+                #pragma unroll
+                for (uint32_t r = 0; r < kSelItems; ++r)
+                    mine += ((flags[r] & 1u) && p[r] == (uint32_t)d) ? 8u : (((flags[r] & 2u) && p[r] + 1u == (uint32_t)d) ? 1u : 0u);
+                uint32_t t2 = 0;
+                uint32_t off = groupBegin[d] + sBase[2 + d] + blockExclScanU(mine, sWarp, t2);
+                #pragma unroll
+                for (uint32_t r = 0; r < kSelItems; ++r)
+                {
+                    if ((flags[r] & 1u) && p[r] == (uint32_t)d) { hPos[r] = off; off += 8u; }
+                    else if ((flags[r] & 2u) && p[r] + 1u == (uint32_t)d) { pPos[r] = off; off += 1u; }
+                }
+            }
+            #pragma unroll
+            for (uint32_t r = 0; r < kSelItems; ++r)
+            {
+                if (V.liveMask & (1u << r)) S.openAlt[lo++] = V.node[r];
+                if (!(V.selMask & (1u << r))) continue;
+                const uint32_t k = so++, j = job0 + k, node = V.node[r], pp = p[r];
+                S.jobNode[j] = node; S.jobFlags[j] = flags[r];
+                S.jobOf[node] = j;
+                S.state[node] = kStEval;
+                atomicSub(S.pendCnt + subOfKey(errKey(V.err[r])), 1u);
+                S.jobHPos[j] = hPos[r]; S.jobPPos[j] = pPos[r];
+                S.jobHSlot[j] = (flags[r] & 1u) ? groupPool[pp] + (hPos[r] - groupBegin[pp]) * (uint32_t)coeffCount((int)pp) : 0u;
+                S.jobPSlot[j] = (flags[r] & 2u) ? groupPool[pp + 1] + (pPos[r] - groupBegin[pp + 1]) * (uint32_t)coeffCount((int)pp + 1) : 0u;
+                const float4 c = S.cell[node];
+                JobDesc o;
+                o.cx = c.x; o.cy = c.y; o.cz = c.z; o.half = c.w;
+                o.hPos = hPos[r]; o.pPos = pPos[r]; o.src = S.slot[node];
+                o.depth = S.depth[node]; o.degree = (uint8_t)pp; o.flags = flags[r]; o.pad = 0;
+                S.jobsOut[k] = o;
+            }
+            if (chunk == 0 && tid == 0)
+            {
+                C.nOpen = sTotal[0]; C.nJobs = job0 + nSel; C.poolUsed = (uint32_t)poolNeed;
+                C.roundJob0 = job0; C.roundJobs = nSel; C.jobsEvaluated += nSel; C.fitsEvaluated += nTasks;
+            }
+            __syncthreads();
         }
     }
 }
