@@ -57,7 +57,7 @@ namespace hpsdf
         if (grid > tiles) grid = tiles;
         int dev = 0;
         cudaGetDevice(&dev);
-        queryKernel<<<(unsigned)grid, kQueryThreads, 0, stream>>>(view, dXyz, n, dOut, g_bidxDev[dev & 15]);
+        queryKernel<<<(unsigned)grid, kQueryThreads, 0, stream>>>(view, dXyz, n, dOut, g_bidxDev[dev & 15], ((uintptr_t)dXyz & 15u) == 0 ? 1 : 0);
         return cudaGetLastError();
     }
 

@@ -18,7 +18,7 @@ namespace hpsdf
 
     __global__ void __launch_bounds__(kQueryThreads, kQueryBlocksPerSm)
     queryKernel(const DeviceTreeView view, const double* __restrict__ xyz, size_t n, double* __restrict__ out,
-                const uint32_t* __restrict__ bidx)
+                const uint32_t* __restrict__ bidx, const int aligned /* xyz starts on a 16-byte boundary */)
     {
         __shared__ uint32_t sTop[4096];
         __shared__ __align__(16) double sPts[kQueryThreads / 32][96];          // per warp: 32 points x 3 doubles
@@ -38,7 +38,7 @@ namespace hpsdf
             const size_t base = g * 32;
             const size_t cnt = n - base < 32 ? n - base : 32;
             const double* src = xyz + 3 * base;                                 // 32 * 24 B = 768 B: 16-byte aligned
-            if (cnt == 32)
+            if (cnt == 32 && aligned)
             {
                 reinterpret_cast<double2*>(sp)[lane] = __ldcs(reinterpret_cast<const double2*>(src) + lane);
                 if (lane < 16) reinterpret_cast<double2*>(sp)[32 + lane] = __ldcs(reinterpret_cast<const double2*>(src) + 32 + lane);

@@ -205,7 +205,8 @@ HPSDF_API hpsdf_status hpsdf_create(const hpsdf_config* cfg, const hpsdf_build_o
 /* Octree::Query (Octree.cpp:662-702) for n points, xyz = n x 3 f64 (AoS), out = n f64, HOST pointers.
  * Points outside the root give DBL_MAX (Octree.cpp:668-671). Thread-safe on a finished tree. */
 HPSDF_API hpsdf_status hpsdf_query(const hpsdf_octree* tree, const double* xyz, size_t n, double* out);
-/* Same with DEVICE pointers, asynchronous on `stream` (cudaStream_t; NULL = legacy default stream). */
+/* Same with DEVICE pointers, asynchronous on `stream` (cudaStream_t; NULL = legacy default stream). The tree's device must be the
+ * current device. d_xyz needs 8-byte alignment only (a 16-byte aligned array takes the vectorised load path). */
 HPSDF_API hpsdf_status hpsdf_query_device(const hpsdf_octree* tree, const double* d_xyz, size_t n, double* d_out, void* stream);
 /* Octree::QueryWithGradient (Octree.cpp:749-789, 904-985): value + unit central-difference gradient. */
 HPSDF_API hpsdf_status hpsdf_query_with_gradient(const hpsdf_octree* tree, const double* xyz, size_t n, double* out, double* unit_grad);

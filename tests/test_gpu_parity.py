@@ -329,6 +329,14 @@ def test_large_batch_properties(hp, oracle, built):
     sub = pts[torch.from_numpy(idx).cuda()].cpu().numpy()
     assert np.abs(o.query(sub, 8) - out[torch.from_numpy(idx).cuda()].cpu().numpy()).max() <= QUERY_TOL
     assert float(out.abs().max()) < 2.0                                 # all inside the root: no DBL_MAX
+    # a point array that starts 8 bytes off a 16-byte boundary (a slice of a larger tensor) takes the scalar load path: same bits
+    flat = torch.empty(3 * 100003 + 1, device="cuda", dtype=torch.float64)
+    flat[1:] = pts[:100003].reshape(-1)
+    odd = torch.empty(100003, device="cuda", dtype=torch.float64)
+    assert (flat.data_ptr() + 8) % 16 == 8
+    t.QueryDevice(flat.data_ptr() + 8, 100003, odd.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(odd, out[:100003])
 
 
 def compare_with_oracle_tree(hp, t, o, cfg_kwargs, n_pts=100000, seed=5):
