@@ -287,7 +287,23 @@ namespace hpsdf
             HPSDF_CUDA(cudaEventRecord(w.ev[evUsed_], stream_));
             int groups = 0;
             for (int d = 1; d <= kMaxDegree; ++d) groups += cnt[d] != 0;
-            const bool fan = !progHasExt_ && groups > 1;
+            // The launches of a round (one per degree present) are independent: they fan out over four auxiliary streams and join
+            // again. Mesh / octree programs sample into a scratch buffer: their groups run concurrently when every group gets its own
+            // slice of it (a mesh query is a chain of ~50-300 dependent L2 round trips, so a launch lasts at least 0.1-0.4 ms however
+            // few samples it has: back to back, the groups of a small round — all of them, on 8 GPUs — just queue those latencies up).
+            size_t slice[kMaxDegree + 2] = { 0 }, sliceOff[kMaxDegree + 2] = { 0 }, sliceTotal = 0;
+            if (progHasExt_ && groups > 1)
+                for (int d = 1; d <= kMaxDegree; ++d)
+                {
+                    size_t b = 0, e = cnt[d];
+                    if (shard) hpsdf_shard_range(cnt[d], rank_, world_, &b, &e);
+                    slice[d] = (e - b) * (size_t)fitRule(d) * fitRule(d) * fitRule(d);
+                    sliceOff[d] = sliceTotal;
+                    sliceTotal += (slice[d] + 31) & ~(size_t)31;
+                }
+            const bool sliced = progHasExt_ && groups > 1 && sliceTotal <= ((size_t)1 << 28) && !getenv("HPSDF_SAMPLE_CAP");
+            if (sliced) HPSDF_CUDA(reserveSampleScratch(*t_.ctx, sliceTotal, stream_));
+            const bool fan = groups > 1 && (!progHasExt_ || sliced);
             if (fan) HPSDF_CUDA(cudaEventRecord(ws_.evFork, stream_));
             int g = 0;
             bool used[4] = { false, false, false, false };
@@ -307,7 +323,8 @@ namespace hpsdf
                         if (!used[g & 3]) { HPSDF_CUDA(cudaStreamWaitEvent(s, ws_.evFork, 0)); used[g & 3] = true; }
                         ++g;
                     }
-                    const hpsdf_status ls = launchFit(o_.jit, d, ws_.tasks.p + groupBegin[d] + b, (int)(e - b), ws_.pool.p, ws_.recs.p, prog_, t_.map, *t_.ctx, s);
+                    const hpsdf_status ls = launchFit(o_.jit, d, ws_.tasks.p + groupBegin[d] + b, (int)(e - b), ws_.pool.p, ws_.recs.p, prog_, t_.map, *t_.ctx, s,
+                                                      sliced ? sliceOff[d] : 0, sliced ? slice[d] : 0, sliced ? d : 0);
                     if (ls != HPSDF_OK) return ls;
                     t_.stats.kernel_launches++;
                 }

@@ -111,10 +111,13 @@ namespace hpsdf
     void        uploadConstants();
     constexpr size_t kSampleScratchDoubles = (size_t)1 << 26;      // 512 MB of samples per chunk at most
     cudaError_t launchFitKernel(int degree, const FitTask* dTasks, int n, double* pool, FitRecord* recs,
-                                const SdfProgramDev& prog, const RootMap& map, DeviceCtx& ctx, cudaStream_t stream);
+                                const SdfProgramDev& prog, const RootMap& map, DeviceCtx& ctx, cudaStream_t stream,
+                                size_t sliceOffset = 0, size_t sliceDoubles = 0, int counterIdx = 0);
+    cudaError_t reserveSampleScratch(DeviceCtx& ctx, size_t doubles, cudaStream_t stream);
     // jit.cpp: the fit launch the scheduler calls (interpreted kernels, or NVRTC-specialised ones; see hpsdf_build_opts.jit)
     hpsdf_status launchFit(uint32_t jitMode, int degree, const FitTask* dTasks, int n, double* pool, FitRecord* recs,
-                           const SdfProgramDev& prog, const RootMap& map, DeviceCtx& ctx, cudaStream_t stream);
+                           const SdfProgramDev& prog, const RootMap& map, DeviceCtx& ctx, cudaStream_t stream,
+                           size_t sliceOffset = 0, size_t sliceDoubles = 0, int counterIdx = 0);
     bool        jitCompileCheck(const SdfProgramDev& prog, int degree, std::string* source, size_t* cubinBytes, std::string& why);
     void        setJitDefault(bool on);
     bool        jitDefault();

@@ -152,30 +152,43 @@ namespace hpsdf
         }
     }
 
+    // Sample scratch of mesh / octree programs: grow-only, sized by the caller BEFORE a round whose degree groups run
+    // concurrently (a reallocation inside the round would pull the buffer from under the launches in flight).
+    cudaError_t reserveSampleScratch(DeviceCtx& ctx, size_t doubles, cudaStream_t stream)
+    {
+        if (ctx.ws.samples.cap < doubles)
+        {
+            cudaError_t e = cudaStreamSynchronize(stream);
+            if (e == cudaSuccess) e = ctx.ws.samples.reserve(doubles);
+            if (e != cudaSuccess) return e;
+        }
+        if (!ctx.ws.sampleCounter.p) return ctx.ws.sampleCounter.reserve(32);
+        return cudaSuccess;
+    }
+
     // Launch the fits of one degree. dTasks: n tasks, all with task.degree == degree. Programs with mesh / octree
-    // primitives need the device context's sample scratch (ctx.ws.samples, reserved here).
+    // primitives need the device context's sample scratch: the whole buffer in chunks (sliceDoubles == 0), or — when the
+    // degree groups of a round run on different streams — the caller's slice [sliceOffset, sliceOffset + sliceDoubles) of a
+    // buffer it reserved with reserveSampleScratch, and its own work counter.
     cudaError_t launchFitKernel(int degree, const FitTask* dTasks, int n, double* pool, FitRecord* recs,
-                                const SdfProgramDev& prog, const RootMap& map, DeviceCtx& ctx, cudaStream_t stream)
+                                const SdfProgramDev& prog, const RootMap& map, DeviceCtx& ctx, cudaStream_t stream,
+                                size_t sliceOffset, size_t sliceDoubles, int counterIdx)
     {
         if (!programHasExt(prog)) return launchFitKernelT<false>(degree, dTasks, n, pool, recs, prog, map, ctx.fitTab, nullptr, 0, nullptr, ctx.smCount, stream);
         const size_t n3 = (size_t)fitRule(degree) * fitRule(degree) * fitRule(degree);
+        if (sliceDoubles)
+        {
+            if (sliceDoubles < (size_t)std::max(n, 1) * n3 || sliceOffset + sliceDoubles > ctx.ws.samples.cap || !ctx.ws.sampleCounter.p) return cudaErrorInvalidValue;
+            return launchFitKernelT<true>(degree, dTasks, n, pool, recs, prog, map, ctx.fitTab, ctx.ws.samples.p + sliceOffset, sliceDoubles,
+                                          ctx.ws.sampleCounter.p + counterIdx, ctx.smCount, stream);
+        }
         // chunk size limit; HPSDF_SAMPLE_CAP (doubles, read per call) lets the tests force the multi-chunk path on small inputs
         size_t limit = kSampleScratchDoubles;
         if (const char* env = getenv("HPSDF_SAMPLE_CAP")) limit = (size_t)strtoull(env, nullptr, 10);
         limit = std::max(limit, n3);
         const size_t want = std::min<size_t>((size_t)std::max(n, 1) * n3, limit);
-        if (ctx.ws.samples.cap < want)
-        {
-            // grow-only scratch; queued work that reads the old buffer must finish before it is freed
-            cudaError_t e = cudaStreamSynchronize(stream);
-            if (e == cudaSuccess) e = ctx.ws.samples.reserve(want);
-            if (e != cudaSuccess) return e;
-        }
-        if (!ctx.ws.sampleCounter.p)
-        {
-            const cudaError_t e = ctx.ws.sampleCounter.reserve(2);
-            if (e != cudaSuccess) return e;
-        }
+        const cudaError_t e = reserveSampleScratch(ctx, want, stream);
+        if (e != cudaSuccess) return e;
         return launchFitKernelT<true>(degree, dTasks, n, pool, recs, prog, map, ctx.fitTab, ctx.ws.samples.p, std::min(ctx.ws.samples.cap, limit),
                                       ctx.ws.sampleCounter.p, ctx.smCount, stream);
     }
