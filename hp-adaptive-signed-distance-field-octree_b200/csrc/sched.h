@@ -59,6 +59,7 @@ namespace hpsdf
         // selection parameters handed from the pass kernel to the multi-block selection kernels (split mode)
         double   selLevel;
         int32_t  selCutSub;
+        uint32_t selCutTau;                  // share of the cut sub-bucket taken by the top-up, in 1/65536
         uint32_t selOpen, selJob0, selPool0; // open-list length before compaction, first job index and first pool slot of the new round
     };
 

@@ -165,6 +165,17 @@ namespace hpsdf
         return sh.levelKey != kNoLevel && (key > sh.levelKey || (key == sh.levelKey && node <= sh.levelNode));
     }
 
+    // Does a pending leaf join the next round? At or above the selection level: always. Top-up (min_round_jobs): sub-buckets above the
+    // cut one whole, the cut sub-bucket by a hash of the node index with the share `cutTau` / 65536 — about as many leaves as the round
+    // still wants, chosen independently per leaf (no ordering needed; a top-up job is speculation, any choice is valid).
+    __device__ __forceinline__ bool selectsLeaf(double err, uint32_t node, double selLevel, int cutSub, uint32_t cutTau)
+    {
+        if (err >= selLevel) return true;
+        const int sub = subOfKey(errKey(err));
+        if (sub > cutSub) return true;
+        return sub == cutSub && ((node * 2654435761u) >> 16) < cutTau;
+    }
+
     // ---- histogram updates (integer atomics only) -------------------------------------------------------------------------
     __device__ __forceinline__ void histAdd(const SchedDev& S, SchedShared& sh, double e, bool pending)
     {
@@ -841,6 +852,7 @@ namespace hpsdf
             // top-up: the sub-bucket in which the count of pending leaves reaches minRoundJobs; it is taken whole (its errors
             // lie within 6 % of each other: the greedy loop is about to reach all of them)
             int cutSub = 0x7FFFFFFF;
+            uint32_t cutTau = 65536u;                               // share of the cut sub-bucket that is taken, in 1/65536 (by a hash of the node index)
             if (S.minRoundJobs > 1u)
             {
                 uint32_t above = 0;
@@ -853,7 +865,17 @@ namespace hpsdf
                     const uint32_t excl = blockExclScanU(pc, sh.warpU, total);
                     const bool reach = pc > 0u && above + excl + pc >= S.minRoundJobs;
                     const uint32_t first = blockMinU(reach ? (uint32_t)tid : (uint32_t)kSchedThreads, sh.warpU);
-                    if (first < (uint32_t)kSchedThreads) { cutSub = hi - (int)first; found = true; }
+                    if (first < (uint32_t)kSchedThreads)
+                    {
+                        if ((uint32_t)tid == first)
+                        {
+                            const uint32_t need = S.minRoundJobs - (above + excl);           // leaves wanted from this sub-bucket, of pc
+                            sh.tmpU[0] = (uint32_t)min(65536ull, ((unsigned long long)need * 65536ull + pc - 1u) / pc);
+                        }
+                        __syncthreads();
+                        cutSub = hi - (int)first; cutTau = sh.tmpU[0]; found = true;
+                        __syncthreads();
+                    }
                     else above += total;
                 }
                 if (!found) cutSub = 0;                             // fewer pending leaves than minRoundJobs: all of them
@@ -863,7 +885,7 @@ namespace hpsdf
             if (S.split)
             {
                 // the multi-block selection kernels take it from here (schedSelectCountKernel / schedSelectScatterKernel)
-                if (tid == 0) { C.selLevel = selLevel; C.selCutSub = cutSub; C.selOpen = sh.nOpen; C.selJob0 = job0; C.selPool0 = sh.poolUsed; }
+                if (tid == 0) { C.selLevel = selLevel; C.selCutSub = cutSub; C.selCutTau = cutTau; C.selOpen = sh.nOpen; C.selJob0 = job0; C.selPool0 = sh.poolUsed; }
                 __syncthreads();
             }
             else
@@ -892,7 +914,7 @@ namespace hpsdf
                         if (st == kStPending)
                         {
                             ev[r] = S.err[nv[r]];
-                            if (ev[r] >= selLevel || subOfKey(errKey(ev[r])) >= cutSub) { selMask |= 1u << r; ++ns; }
+                            if (selectsLeaf(ev[r], nv[r], selLevel, cutSub, cutTau)) { selMask |= 1u << r; ++ns; }
                         }
                     }
                     uint32_t total = 0;
@@ -1093,7 +1115,7 @@ namespace hpsdf
             if (st == kStPending)
             {
                 V.err[r] = S.err[V.node[r]];
-                if (V.err[r] >= C.selLevel || subOfKey(errKey(V.err[r])) >= C.selCutSub) { V.selMask |= 1u << r; ++V.nSel; }
+                if (selectsLeaf(V.err[r], V.node[r], C.selLevel, C.selCutSub, C.selCutTau)) { V.selMask |= 1u << r; ++V.nSel; }
             }
         }
     }

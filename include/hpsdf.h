@@ -125,7 +125,7 @@ typedef struct hpsdf_build_opts
                                      cached in memory), 2 = interpreted kernels. Mesh / octree programs are always interpreted. */
     uint32_t min_round_jobs;      /* a batched round evaluates at least this many refinement jobs when that many leaves are waiting
                                      (the next-largest errors beyond the guaranteed level); 0 = 512 for closed-form programs,
-                                     1 for mesh / octree programs, whose fits are too expensive to speculate on */
+                                     128 for mesh / octree programs (device scheduler; the host replay uses 1 for those) */
     uint32_t scheduler;           /* 0 = the greedy loop (queue, h-vs-p decision, error bookkeeping, node allocation, job selection) runs
                                      on the device, one 128-byte header per round comes back; 1 = the loop is replayed on the host from
                                      16-byte fit records (round-1 implementation; also used when strict_order = 1) */

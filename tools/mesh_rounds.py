@@ -15,7 +15,7 @@ cfg = hp.Config(target_error_threshold=thr, continuity_enforce=0, root_min=lo, r
 tree = hp.Octree()
 for i in range(3):
     t0 = time.perf_counter()
-    tree.Create(cfg, hp.SdfProgram([("mesh", [], m)]), hp.BuildOpts(max_degree=maxdeg))
+    tree.Create(cfg, hp.SdfProgram([("mesh", [], m)]), hp.BuildOpts(max_degree=maxdeg, min_round_jobs=int(os.environ.get('MRJ', '0'))))
     s = tree.stats()
     print("Create %.2f ms" % (1e3 * (time.perf_counter() - t0)), {k: (round(s[k], 3) if isinstance(s[k], float) else s[k]) for k in
           ("rounds", "fits_evaluated", "sdf_evals", "fit_kernel_ms", "device_wait_ms", "total_ms", "n_nodes")}, flush=True)
