@@ -4,8 +4,6 @@ import numpy as np, torch, torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-if rank != 0:
-    os.environ.pop("HPSDF_DEBUG_ROUNDS", None)
 torch.cuda.set_device(local)
 hp = importlib.import_module("hp-adaptive-signed-distance-field-octree_b200")
 from meshgen import bumpy_torus, mesh_root
@@ -26,7 +24,7 @@ for i in range(3):
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     tree.Create(cfg, hp.SdfProgram([("mesh", [], m)]), opts)
-    if rank == 0:
+    if True:
         s = tree.stats()
-        print("Create %.2f ms" % (1e3 * (time.perf_counter() - t0)), {k: (round(s[k], 3) if isinstance(s[k], float) else s[k]) for k in ("rounds", "fit_kernel_ms", "device_wait_ms", "total_ms")}, flush=True)
+        print("rank", rank, "Create %.2f ms" % (1e3 * (time.perf_counter() - t0)), {k: (round(s[k], 3) if isinstance(s[k], float) else s[k]) for k in ("rounds", "fit_kernel_ms", "device_wait_ms", "total_ms")}, flush=True)
 comm.close(); dist.destroy_process_group()
