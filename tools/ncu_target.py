@@ -14,6 +14,20 @@ if what == "fitjit":
 elif what == "fit":
     for p in (2, 3):
         print(p, hp.bench_frontier(cfg, prog, 5, p, repeats=1))
+elif what == "mesh":
+    from meshgen import bumpy_torus, mesh_root
+    v, t = bumpy_torus(1000, 435)
+    lo, hi = mesh_root(v)
+    m = hp.Mesh(v, t)
+    mcfg = hp.Config(target_error_threshold=1e-6, continuity_enforce=1, continuity_strength=8.0, root_min=lo, root_max=hi)
+    tree = hp.Octree()
+    tree.Create(mcfg, hp.SdfProgram([("mesh", [], m)]))
+    print(tree.stats())
+elif what == "sched":
+    t = hp.Octree()
+    for _ in range(2):
+        t.Create(cfg, prog, hp.BuildOpts(jit=1))
+    print(t.stats())
 elif what == "query":
     import torch
     t = hp.Octree(); t.Create(cfg, prog)

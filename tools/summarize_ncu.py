@@ -21,6 +21,7 @@ KEYS = [
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
     "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
