@@ -298,13 +298,16 @@ def bench_c3(cx, args, clk_holder):
         cx.barrier()
         out["multi_gpu_parity"] = ok
 
-    # e2e: host arrays -> mesh set-up -> Create -> MemoryBlock on the host, every step
+    # e2e: host arrays (pinned, as the contract asks) -> mesh set-up -> Create -> MemoryBlock on the host, every step
+    pv = torch.from_numpy(np.ascontiguousarray(verts, np.float32)).pin_memory()
+    pt = torch.from_numpy(np.ascontiguousarray(tris, np.uint32).view(np.int32)).pin_memory()
+    verts_p, tris_p = pv.numpy(), pt.numpy().view(np.uint32)
     n_e2e = max(2, min(args.steps, 5))
     cx.barrier()
     times, blk_bytes = [], 0
     for i in range(n_e2e + 1):
         t0 = time.perf_counter()
-        m2 = hp.Mesh(verts, tris, device=cx.local)
+        m2 = hp.Mesh(verts_p, tris_p, device=cx.local)
         t2 = hp.Octree()
         t2.Create(cfg, hp.SdfProgram([("mesh", [], m2)]), opts)
         blk = t2.ToMemoryBlock()
@@ -509,7 +512,9 @@ def bench_c4(cx, with_cpu):
            "ms_per_step": ms, "fits_per_s": fits / (ms * 1e-3), "nodes_fitted_per_step": fits, "fits_evaluated": st["fits_evaluated"],
            "mesh_sdf_evals": st["sdf_evals"], "mesh_sdf_evals_per_s": st["sdf_evals"] / (ms * 1e-3),
            "fit_and_sample_kernel_ms": st["fit_kernel_ms"], "rounds": st["rounds"], "n_nodes": st["n_nodes"], "n_coeffs": st["n_coeffs"],
-           "mesh_setup_s": setup_s, "e2e_ms": 1e3 * setup_s + ms, "scaling": "strong"}
+           "mesh_setup_s": setup_s, "e2e_ms": 1e3 * setup_s + ms, "scaling": "strong",
+           "step_breakdown_ms": {k: agg[k] for k in ("fit_kernel_ms", "continuity_ms", "continuity_cg_ms", "continuity_assembly_ms",
+                                                      "continuity_enum_ms", "device_wait_ms", "pack_ms", "finalize_ms") if k in agg}}
     if with_cpu:
         try:
             res["cpu_baseline"] = cpu_fit_sample(hp, tree, verts, tris, box, C4, budget_s=12.0)

@@ -559,7 +559,10 @@ namespace hpsdf
             SchedWorkspace& w = *(SchedWorkspace*)ws_.sched;
             hpsdf_status st = ensureTemplates(w);
             if (st != HPSDF_OK) return st;
-            uint32_t cap = std::max<uint32_t>(w.cap, std::max<uint32_t>(1u << 18, (uint32_t)std::min<size_t>(4 * ws_.lastNodeCount, (size_t)1 << 26)));
+            // the capacity only ever grows (an overflow restarts the build with four times as much and the larger arena is
+            // kept), so a repeated Create never reallocates: re-sizing it from the previous node count cost C4 330 ms of
+            // cudaFree + cudaMalloc in its second build
+            uint32_t cap = std::max<uint32_t>(w.cap, 1u << 18);
             for (;;)
             {
                 if ((st = ensureCapacity(w, cap)) != HPSDF_OK) return st;
