@@ -372,6 +372,7 @@ namespace hpsdf
             SchedDev& S = w.dev;
             const hpsdf_config& cfg = t_.cfg;
             S.threshold = cfg.target_error_threshold; S.nearnessStrength = cfg.nearness_strength; S.nearnessType = cfg.nearness_type;
+            S.nearnessMode = o_.nearness_mode; S.nearnessSeed = o_.nearness_seed;
             S.maxDegree = o_.max_degree; S.maxDepth = o_.max_depth; S.totalMode = o_.total_mode;
             S.minRoundJobs = o_.min_round_jobs ? o_.min_round_jobs : (progHasExt_ ? 128u : 512u);     // measured: 870 k-triangle config 9 -> 6 rounds at +0.5 % fits; 512 evaluates 60 % more
             S.speculate = o_.speculate;
@@ -411,7 +412,7 @@ namespace hpsdf
             uint32_t roundJobs = 0, openEstimate = kCoarseCells;
             for (uint32_t round = 0;; ++round)
             {
-                S.recs = ws_.recs.p;
+                S.recs = ws_.recs.p; S.pool = ws_.pool.p;
                 if (S.split && round > 0) { HPSDF_CUDA(launchSchedIngest(S, roundJobs, stream_)); t_.stats.kernel_launches++; }
                 HPSDF_CUDA(launchSchedRound(S, w.coarseOrder, stream_));
                 t_.stats.kernel_launches++;
@@ -599,12 +600,16 @@ namespace hpsdf
     {
         static const char* env = getenv("HPSDF_SCHEDULER");
         const bool host = opts.scheduler == 1u || opts.strict_order || (opts.scheduler == 0u && env && env[0] == 'h');
+        if (opts.nearness_mode > HPSDF_NEARNESS_MC_COUNTER) { setLastError("unknown nearness_mode"); return HPSDF_ERR_INVALID_ARG; }
+        const bool mc = opts.nearness_mode == HPSDF_NEARNESS_MC_COUNTER && t.cfg.nearness_type != HPSDF_NEARNESS_NONE;
         if (!host)
         {
             bool fallBack = false;
             const hpsdf_status st = buildOctreeDevice(t, opts, prog, fallBack);
             if (st != HPSDF_OK || !fallBack) return st;
         }
+        // the host replay sees 16-byte fit records, not coefficients: it cannot sample the approximant
+        if (mc) { setLastError("nearness_mode = HPSDF_NEARNESS_MC_COUNTER needs the device scheduler (scheduler = 0, strict_order = 0)"); return HPSDF_ERR_UNSUPPORTED; }
         return buildOctreeHost(t, opts, prog);
     }
 }

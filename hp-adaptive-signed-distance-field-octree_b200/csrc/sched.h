@@ -122,11 +122,13 @@ namespace hpsdf
         SchedCounters* ctr;
         RoundHeader*   hostHdr;  // device pointer of the mapped header
         const FitRecord* recs;   // records of the round in flight
+        const double*    pool;   // coefficient pool (read by the mc_counter nearness estimate only)
         // capacities
         uint32_t capNodes, capJobs, capLog, capDecisions;
         // configuration
         double   threshold, nearnessStrength;
-        uint32_t nearnessType, maxDegree, maxDepth, totalMode, minRoundJobs, speculate;
+        unsigned long long nearnessSeed;
+        uint32_t nearnessType, nearnessMode, maxDegree, maxDepth, totalMode, minRoundJobs, speculate;
         uint32_t split;          // 1 = ingest and selection run as multi-block kernels around the single-CTA pass kernel
         uint32_t dealJobs;       // 1 = deal the jobs of a round out along a stride permutation (multi-GPU shards get the same mix)
     };

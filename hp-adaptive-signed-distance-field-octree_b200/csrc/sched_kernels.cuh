@@ -194,14 +194,72 @@ namespace hpsdf
         atomicAdd(S.allSum + sub, 0ull - errUnits(key));
     }
 
-    // Nearness weight from the exact cell mean c000 * NL[0][depth]^3 (Octree.cpp:1209-1247 in the limit of many samples; the
-    // expressions of build.cpp / the CPU checker, evaluated with CUDA's exp / pow: <= 2 ulp from the host libm, i.e. below the
-    // 1e-15 relative difference the GPU fit itself has against the CPU one)
-    __device__ __forceinline__ double nearnessWeightDev(const SchedDev& S, double c0, uint32_t depth)
+    // ---- nearness weight (CalculatePolyWeighting / CalculateExpWeighting, Octree.cpp:1209-1247) ------------------------------------
+    // The reference averages FApprox over 100 std::rand() points of the cell. Two deterministic statements of that estimate:
+    //   HPSDF_NEARNESS_EXACT_MEAN: its limit, the exact cell mean c000 * NL[0][depth]^3;
+    //   HPSDF_NEARNESS_MC_COUNTER: the estimator itself on Philox4x32-10 points (key = seed, counter = cell coordinates, depth, degree,
+    //                              sample index) — the rule stated in include/hpsdf.h; the CPU checker runs the same rule through
+    //                              the reference's own FApprox. FApprox (Octree.cpp:859-901) is mirrored operation by operation,
+    //                              so the estimate differs from the checker's only through the 1e-15 relative difference of the
+    //                              coefficients.
+    // exp / pow are CUDA's: <= 2 ulp from the host libm, the same order as that difference.
+    __device__ __noinline__ double nearnessMeanMc(const SchedDev& S, const double* __restrict__ c, uint32_t degree, float4 cell, uint32_t depth)
+    {
+        const float ctr[3] = { cell.x, cell.y, cell.z };
+        const float ext = __fadd_rn(cell.w, cell.w);                                  // max - min of a dyadic cell: exact
+        float mn[3];
+        uint32_t ic[3];
+        #pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+            mn[a] = __fsub_rn(ctr[a], cell.w);
+            ic[a] = (uint32_t)__fmul_rn(__fadd_rn(mn[a], 0.5f), (float)(1u << depth));
+        }
+        const double scale = (double)(2u << depth);                                    // Octree.cpp:862
+        const uint32_t nC = (uint32_t)coeffCount((int)degree);
+        double sum = 0.0;
+        for (uint32_t smp = 0; smp < 100u; ++smp)                                      // nSamples, Octree.cpp:1216, 1236
+        {
+            const Philox4 r = philox4x32_10(ic[0], ic[1], ic[2], depth | (degree << 8) | (smp << 16), (uint32_t)S.nearnessSeed, (uint32_t)(S.nearnessSeed >> 32));
+            const uint32_t w[3] = { r.x, r.y, r.z };
+            double lut[3][kMaxDegree + 1];
+            #pragma unroll
+            for (int a = 0; a < 3; ++a)
+            {
+                const float uf = __fmul_rn((float)(w[a] >> 8), 0x1p-24f);
+                const float x = __fadd_rn(mn[a], __fmul_rn(ext, uf));                 // AlignedBox::sample(): min + (max - min) * u, f32
+                const double u = __dmul_rn(__dsub_rn((double)x, (double)ctr[a]), scale);
+                lut[a][0] = c_nl[0][depth];
+                double m2 = 0.0, m1 = 1.0;
+                for (uint32_t j = 1; j <= degree; ++j)
+                {
+                    const double l = __dsub_rn(__dmul_rn(__dmul_rn(c_rec[j][0], u), m1), __dmul_rn(c_rec[j][1], m2));      // Octree.cpp:879
+                    m2 = m1; m1 = l;
+                    lut[a][j] = __dmul_rn(l, c_nl[j][depth]);
+                }
+            }
+            double f = 0.0;
+            uint32_t idx = 0;
+            for (uint32_t p = 0; p <= degree; ++p)                                     // BasisIndexValues order: shell p, then i, then j
+                for (uint32_t i = 0; i <= p; ++i)
+                    for (uint32_t j = 0; j <= p - i && idx < nC; ++j, ++idx)
+                        f = __dadd_rn(f, __dmul_rn(c[idx], __dmul_rn(__dmul_rn(lut[0][i], lut[1][j]), lut[2][p - i - j])));      // Octree.cpp:891-897
+            sum = __dadd_rn(sum, f);
+        }
+        return fabs(__ddiv_rn(sum, 100.0));
+    }
+
+    // coeffs / degree / cell: the fitted basis and its cell (only read in the mc_counter mode); c0 = coeffs[0] from the fit record
+    __device__ __forceinline__ double nearnessWeightDev(const SchedDev& S, double c0, uint32_t depth, const double* __restrict__ coeffs, uint32_t degree, float4 cell)
     {
         if (S.nearnessType == HPSDF_NEARNESS_NONE) return 1.0;
-        const double nl = c_nl[0][depth];
-        const double m = fabs(__dmul_rn(c0, __dmul_rn(__dmul_rn(nl, nl), nl)));
+        double m;
+        if (S.nearnessMode == HPSDF_NEARNESS_MC_COUNTER) m = nearnessMeanMc(S, coeffs, degree, cell, depth);
+        else
+        {
+            const double nl = c_nl[0][depth];
+            m = fabs(__dmul_rn(c0, __dmul_rn(__dmul_rn(nl, nl), nl)));
+        }
         const double d = sqrt(3.0);
         if (S.nearnessType == HPSDF_NEARNESS_POLYNOMIAL)
         {
@@ -210,6 +268,23 @@ namespace hpsdf
             return (kk < 1.0) ? kk : 1.0;                        // std::min<double>(1.0, .)
         }
         return exp(__ddiv_rn(__dmul_rn(__dmul_rn(-1.0, S.nearnessStrength), m), d));
+    }
+
+    // the weighted error of fit c (0..7 children, 8 = the p-fit) of job j
+    __device__ __forceinline__ double ingestFitError(const SchedDev& S, uint32_t j, uint32_t c, uint32_t node, uint32_t depth, uint8_t flags)
+    {
+        const float4 cell = S.cell[node];
+        if (c < 8u)
+        {
+            const FitRecord r = S.recs[S.jobHPos[j] + c];
+            const uint32_t deg = S.degree[node];
+            const float q = cell.w * 0.5f;                                              // CornerAABB (Octree.cpp:1096-1112), as expandJobsDevKernel
+            const float4 child = make_float4(cell.x + ((c & 1u) ? q : -q), cell.y + ((c & 2u) ? q : -q), cell.z + ((c & 4u) ? q : -q), q);
+            return r.rawErr * nearnessWeightDev(S, r.c0, depth + 1, S.pool + S.jobHSlot[j] + (size_t)c * (size_t)coeffCount((int)deg), deg, child);
+        }
+        const FitRecord r = S.recs[S.jobPPos[j]];
+        const uint32_t deg = (flags & 4u) ? (uint32_t)kCoarseDegree : (uint32_t)S.degree[node] + 1u;
+        return r.rawErr * nearnessWeightDev(S, r.c0, depth, S.pool + S.jobPSlot[j], deg, cell);
     }
 
     // The h-vs-p decision of one cached job (Octree.cpp:600-601, 825, 854 with BASIS_MAX_DEGREE-1 -> maxDegree,
@@ -632,7 +707,7 @@ namespace hpsdf
         {
             const uint32_t node = S.jobNode[j];
             const FitRecord r = S.recs[S.jobPPos[j]];
-            const double e = r.rawErr * nearnessWeightDev(S, r.c0, S.depth[node]);
+            const double e = r.rawErr * nearnessWeightDev(S, r.c0, S.depth[node], S.pool + S.jobPSlot[j], (uint32_t)kCoarseDegree, S.cell[node]);
             sErr[j] = e;
             bad |= !(e < kInitialErr);
             S.jobFlags[j] |= 128u;
@@ -716,19 +791,11 @@ namespace hpsdf
                 const uint8_t flags = S.jobFlags[j];
                 if (c < 8u)
                 {
-                    if (flags & 1u)
-                    {
-                        const FitRecord r = S.recs[S.jobHPos[j] + c];
-                        S.jobErr[9 * (size_t)j + c] = r.rawErr * nearnessWeightDev(S, r.c0, depth + 1);
-                    }
+                    if (flags & 1u) S.jobErr[9 * (size_t)j + c] = ingestFitError(S, j, c, node, depth, flags);
                 }
                 else
                 {
-                    if (flags & 2u)
-                    {
-                        const FitRecord r = S.recs[S.jobPPos[j]];
-                        S.jobErr[9 * (size_t)j + 8] = r.rawErr * nearnessWeightDev(S, r.c0, depth);
-                    }
+                    if (flags & 2u) S.jobErr[9 * (size_t)j + 8] = ingestFitError(S, j, 8u, node, depth, flags);
                     S.state[node] = kStCached;
                     S.cached[sh.nCached + k] = j;
                 }
@@ -1072,19 +1139,11 @@ namespace hpsdf
         const uint8_t flags = S.jobFlags[j];
         if (c < 8u)
         {
-            if (flags & 1u)
-            {
-                const FitRecord r = S.recs[S.jobHPos[j] + c];
-                S.jobErr[9 * (size_t)j + c] = r.rawErr * nearnessWeightDev(S, r.c0, depth + 1);
-            }
+            if (flags & 1u) S.jobErr[9 * (size_t)j + c] = ingestFitError(S, j, c, node, depth, flags);
         }
         else
         {
-            if (flags & 2u)
-            {
-                const FitRecord r = S.recs[S.jobPPos[j]];
-                S.jobErr[9 * (size_t)j + 8] = r.rawErr * nearnessWeightDev(S, r.c0, depth);
-            }
+            if (flags & 2u) S.jobErr[9 * (size_t)j + 8] = ingestFitError(S, j, 8u, node, depth, flags);
             S.state[node] = kStCached;
             S.cached[nCached + k] = j;
         }

@@ -99,6 +99,11 @@ enum
 {
     HPSDF_NEARNESS_EXACT_MEAN = 0,   /* mean of the approximant over the cell = c000 * 2^(3*depth/2): the deterministic
                                         limit of the reference's 100-sample std::rand() estimate (Octree.cpp:1209-1247) */
+    HPSDF_NEARNESS_MC_COUNTER = 1,   /* the reference's estimator itself (mean of FApprox at 100 points of the cell) with the points
+                                        from a counter-based generator instead of std::rand(): Philox4x32-10, key = nearness_seed,
+                                        counter = (ix, iy, iz, depth | degree << 8 | sample << 16), u = (word >> 8) * 2^-24, point =
+                                        min + (max - min) * u in f32 as AlignedBox::sample(). Reproducible for a given seed and
+                                        independent of the schedule; for A/B runs against the literal reference. Device scheduler only. */
     HPSDF_TOTAL_REFERENCE     = 0,   /* totalCoeffError bookkeeping exactly as Octree.cpp:212,257,272,276 (sentinel 8^4*100) */
     HPSDF_TOTAL_EXACT_SUM     = 1    /* sum of leaf errors recomputed without the sentinel bias */
 };
@@ -110,7 +115,7 @@ typedef struct hpsdf_build_opts
     uint32_t struct_size;         /* = sizeof(hpsdf_build_opts) */
     uint32_t max_degree;          /* highest reachable basis degree; reference: BASIS_MAX_DEGREE-1 = 11 (Consts.h:7, Octree.cpp:600) */
     uint32_t max_depth;           /* reference: TREE_MAX_DEPTH = 10 (Consts.h:8) */
-    uint32_t nearness_mode;       /* HPSDF_NEARNESS_EXACT_MEAN */
+    uint32_t nearness_mode;       /* HPSDF_NEARNESS_EXACT_MEAN | HPSDF_NEARNESS_MC_COUNTER */
     uint32_t total_mode;          /* HPSDF_TOTAL_REFERENCE | HPSDF_TOTAL_EXACT_SUM */
     uint32_t cg_max_iterations;   /* 0 = 2n, Eigen's default */
     double   cg_tolerance;        /* relative residual; 0 = the reference's (double)1e-6f (Octree.cpp:1754) */
@@ -129,6 +134,8 @@ typedef struct hpsdf_build_opts
     uint32_t scheduler;           /* 0 = the greedy loop (queue, h-vs-p decision, error bookkeeping, node allocation, job selection) runs
                                      on the device, one 128-byte header per round comes back; 1 = the loop is replayed on the host from
                                      16-byte fit records (round-1 implementation; also used when strict_order = 1) */
+    uint32_t reserved0;
+    uint64_t nearness_seed;       /* HPSDF_NEARNESS_MC_COUNTER: key of the sample-point generator */
 } hpsdf_build_opts;
 
 HPSDF_API void hpsdf_build_opts_default(hpsdf_build_opts* opts);

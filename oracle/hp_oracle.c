@@ -323,14 +323,66 @@ static double fit_polynomial(const Tree* t, double* coeffs, uint32_t degreeIn, c
     return err;
 }
 
-/* Exact-mean limit of CalculatePolyWeighting / CalculateExpWeighting (Octree.cpp:1209-1247): the cell mean of the
- * approximant is coeffs[0] * NL[0][depth]^3 (orthonormal basis), replacing the 100 std::rand() samples. */
-static double nearness_weight(const hpsdf_config* cfg, double c0, uint32_t depth)
+/* ---- nearness weight (CalculatePolyWeighting / CalculateExpWeighting, Octree.cpp:1209-1247) ----------------------------
+ * The reference averages FApprox over 100 points from aabb_.sample(), i.e. std::rand(): not reproducible. Two
+ * deterministic statements of it:
+ *   exact mean (default): the cell mean of the approximant is coeffs[0] * NL[0][depth]^3 (orthonormal basis) — the limit
+ *                         of the estimate for many samples;
+ *   mc_counter(seed):     the reference's estimator itself, 100 samples, with the sample points drawn from a counter-based
+ *                         generator instead of std::rand(): Philox4x32-10, key = seed, counter = (ix, iy, iz,
+ *                         depth | degree << 8 | sample << 16) with (ix, iy, iz) the integer coordinates of the cell at its
+ *                         depth; unit coordinate u = (word >> 8) * 2^-24 in f32 and the point min + (max - min) * u in f32
+ *                         like Eigen's AlignedBox::sample(), cast to f64 for FApprox (Octree.cpp:1222, 1242). A weight
+ *                         then depends only on (seed, cell, degree, coefficients), never on the schedule. */
+static int      g_nearnessMc = 0;
+static uint64_t g_nearnessSeed = 0;
+void hporacle_set_nearness_mc(int on, uint64_t seed) { g_nearnessMc = on; g_nearnessSeed = seed; }
+
+static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
+{
+    for (int r = 0; r < 10; ++r)
+    {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        c[0] = n0; c[1] = (uint32_t)p1; c[2] = n2; c[3] = (uint32_t)p0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+static double f_approx(const double* coeffs, uint32_t degree, const Box* aabb, const double pt[3], uint32_t depth);
+
+static double nearness_mean(const double* coeffs, uint32_t degree, const Box* aabb, uint32_t depth)
+{
+    if (!g_nearnessMc)
+    {
+        const double nl = NL[0][depth];
+        return fabs(coeffs[0] * (nl * nl * nl));
+    }
+    uint32_t cell[3];
+    for (int a = 0; a < 3; ++a) cell[a] = (uint32_t)((aabb->mn[a] + 0.5f) * (float)(1u << depth));      /* dyadic cells of [-0.5, 0.5]^3: exact */
+    double sum = 0.0;
+    for (uint32_t s = 0; s < 100; ++s)                                                                  /* nSamples, Octree.cpp:1216, 1236 */
+    {
+        uint32_t c[4] = { cell[0], cell[1], cell[2], depth | (degree << 8) | (s << 16) };
+        philox4x32_10(c, (uint32_t)g_nearnessSeed, (uint32_t)(g_nearnessSeed >> 32));
+        double pt[3];
+        for (int a = 0; a < 3; ++a)
+        {
+            const float u = (float)(c[a] >> 8) * 0x1p-24f;
+            const float ext = aabb->mx[a] - aabb->mn[a];
+            const float x = aabb->mn[a] + ext * u;
+            pt[a] = (double)x;
+        }
+        sum += f_approx(coeffs, degree, aabb, pt, depth);
+    }
+    sum /= 100;
+    return fabs(sum);
+}
+
+static double nearness_weight(const hpsdf_config* cfg, const double* coeffs, uint32_t degree, const Box* aabb, uint32_t depth)
 {
     if (cfg->nearness_type == HPSDF_NEARNESS_NONE) return 1.0;
-    const double nl = NL[0][depth];
-    double m = c0 * (nl * nl * nl);
-    m = fabs(m);
+    const double m = nearness_mean(coeffs, degree, aabb, depth);
     const double d = sqrt(3.0);
     if (cfg->nearness_type == HPSDF_NEARNESS_POLYNOMIAL)
     {
@@ -389,13 +441,13 @@ static void greedy_build(Tree* t, uint32_t maxDegree, uint32_t maxDepth, uint32_
         if (doH)
         {
             double maxNew = 0.0;
-            for (uint32_t i = 0; i < 8; ++i) { hErr[i] = rawH[i] * nearness_weight(&t->cfg, hC[i][0], depth + 1); maxNew = (maxNew < hErr[i]) ? hErr[i] : maxNew; }
+            for (uint32_t i = 0; i < 8; ++i) { hErr[i] = rawH[i] * nearness_weight(&t->cfg, hC[i], p, &childBox[i], depth + 1); maxNew = (maxNew < hErr[i]) ? hErr[i] : maxNew; }
             hImp = (1.0 / (7.0 * COUNT[p])) * (err - 8.0 * maxNew);                                                    /* Octree.cpp:825 */
             t->fits += 8;
         }
         if (doP)
         {
-            pErr = rawP * nearness_weight(&t->cfg, pC[0], depth);
+            pErr = rawP * nearness_weight(&t->cfg, pC, isCoarse ? 2u : p + 1u, &node.aabb, depth);
             pImp = isCoarse ? pErr : (1.0 / (COUNT[p + 1] - COUNT[p])) * (err - 8.0 * pErr);                           /* Octree.cpp:842, 854 */
             t->fits += 1;
         }

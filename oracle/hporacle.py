@@ -58,6 +58,7 @@ def lib():
     L.hporacle_mesh_create.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
     L.hporacle_mesh_destroy.argtypes = [C.c_void_p]
     L.hporacle_mesh_sdf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+    L.hporacle_set_nearness_mc.argtypes = [C.c_int, C.c_uint64]
     _lib = L
     return L
 
@@ -69,8 +70,13 @@ class OracleTree:
         self.h, self._keep = handle, keep
 
     @classmethod
-    def build(cls, cfg, prog, max_degree=11, max_depth=10, total_mode=0, cg_tol=0.0, threads=1):
-        h = lib().hporacle_build(C.byref(cfg), prog, len(prog), max_degree, max_depth, total_mode, cg_tol, threads, None)
+    def build(cls, cfg, prog, max_degree=11, max_depth=10, total_mode=0, cg_tol=0.0, threads=1, mc_seed=None):
+        """mc_seed: None = exact-mean nearness; an integer = the 100-sample estimator on Philox points (mc_counter)."""
+        lib().hporacle_set_nearness_mc(0 if mc_seed is None else 1, 0 if mc_seed is None else mc_seed)
+        try:
+            h = lib().hporacle_build(C.byref(cfg), prog, len(prog), max_degree, max_depth, total_mode, cg_tol, threads, None)
+        finally:
+            lib().hporacle_set_nearness_mc(0, 0)
         return cls(h, keep=(prog,))
 
     @classmethod

@@ -116,9 +116,15 @@ class RefTree:
         self.h, self.L, self._keep = handle, L, keep
 
     @classmethod
-    def build(cls, cfg, prog, mode=1, max_degree=11, max_depth=10, total_mode=0, cg_tol=0.0, threads=1, fast=False):
+    def build(cls, cfg, prog, mode=1, max_degree=11, max_depth=10, total_mode=0, cg_tol=0.0, threads=1, fast=False, mc_seed=None):
+        """mc_seed (mode 1): None = exact-mean nearness; an integer = 100 FApprox samples on Philox points (mc_counter)."""
         L = lib(fast)
-        h = L.hpref_build(C.byref(cfg), prog, len(prog), mode, max_degree, max_depth, total_mode, cg_tol, threads)
+        L.hpref_set_nearness_mc.argtypes = [C.c_int, C.c_uint64]
+        L.hpref_set_nearness_mc(0 if mc_seed is None else 1, 0 if mc_seed is None else mc_seed)
+        try:
+            h = L.hpref_build(C.byref(cfg), prog, len(prog), mode, max_degree, max_depth, total_mode, cg_tol, threads)
+        finally:
+            L.hpref_set_nearness_mc(0, 0)
         return cls(h, L, keep=(prog,))
 
     @classmethod

@@ -126,13 +126,55 @@ namespace
         return cfg;
     }
 
-    // Deterministic limit of CalculatePolyWeighting / CalculateExpWeighting (Octree.cpp:1209-1247): the mean of the
-    // approximant over its cell is coeffs[0] * NL[0][depth]^3 by orthonormality, instead of 100 std::rand() samples.
-    double nearnessWeight(const SDF::Config& cfg, const double c0, const u32 depth)
+    // Deterministic statements of CalculatePolyWeighting / CalculateExpWeighting (Octree.cpp:1209-1247):
+    //   default:          the mean of the approximant over its cell is coeffs[0] * NL[0][depth]^3 by orthonormality
+    //                     (the limit of the 100-sample estimate);
+    //   mc_counter(seed): the reference's own estimator — 100 calls of the reference's FApprox — with the sample points
+    //                     from Philox4x32-10 (key = seed, counter = cell coordinates, depth, degree, sample index) instead
+    //                     of aabb_.sample() / std::rand(). Same rule as oracle/hp_oracle.c: nearness_mean.
+    int      g_nearnessMc = 0;
+    uint64_t g_nearnessSeed = 0;
+
+    void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
+    {
+        for (int r = 0; r < 10; ++r)
+        {
+            const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+            c[0] = n0; c[1] = (uint32_t)p1; c[2] = n2; c[3] = (uint32_t)p0;
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+    }
+
+    double nearnessWeight(const SDF::Octree& o, const SDF::Config& cfg, const SDF::Node::Basis& basis, const Eigen::AlignedBox3f& aabb, const u32 depth)
     {
         if (cfg.nearnessWeighting.type == SDF::Config::NearnessWeighting::None) return 1.0;
-        const double nl = SDF::NormalisedLengths[0][depth];
-        double fIntegral = c0 * (nl * nl * nl);
+        double fIntegral = 0.0;
+        if (!g_nearnessMc)
+        {
+            const double nl = SDF::NormalisedLengths[0][depth];
+            fIntegral = basis.coeffs[0] * (nl * nl * nl);
+        }
+        else
+        {
+            uint32_t cell[3];
+            for (int a = 0; a < 3; ++a) cell[a] = (uint32_t)((aabb.min()(a) + 0.5f) * (float)(1u << depth));
+            for (u32 s = 0; s < 100; ++s)
+            {
+                uint32_t c[4] = { cell[0], cell[1], cell[2], depth | ((u32)basis.degree << 8) | (s << 16) };
+                philox4x32_10(c, (uint32_t)g_nearnessSeed, (uint32_t)(g_nearnessSeed >> 32));
+                Eigen::Vector3d pt;
+                for (int a = 0; a < 3; ++a)
+                {
+                    const float u = (float)(c[a] >> 8) * 0x1p-24f;
+                    const float ext = aabb.max()(a) - aabb.min()(a);
+                    const float x = aabb.min()(a) + ext * u;
+                    pt(a) = (double)x;
+                }
+                fIntegral += o.FApprox(basis, aabb, pt, depth);                  // the reference's own evaluator (Octree.cpp:859-901)
+            }
+            fIntegral /= 100;
+        }
         fIntegral = std::abs<f64>(fIntegral);
         const double d = sqrt(3.0);
         if (cfg.nearnessWeighting.type == SDF::Config::NearnessWeighting::Polynomial)
@@ -215,7 +257,7 @@ namespace
                 f64 maxNewErr = 0.0;
                 for (u32 i = 0; i < 8; ++i)
                 {
-                    hErrs[i]  = rawH[i] * nearnessWeight(userCfg, hBases[i].coeffs[0], depth + 1);
+                    hErrs[i]  = rawH[i] * nearnessWeight(o, userCfg, hBases[i], o.CornerAABB(node.aabb, i), depth + 1);
                     maxNewErr = std::max<f64>(maxNewErr, hErrs[i]);                                                            // Octree.cpp:821
                 }
                 hImp = (1.0 / (7.0 * LegendreCoeffientCount[p])) * (err - 8.0 * maxNewErr);                                   // Octree.cpp:825
@@ -223,7 +265,7 @@ namespace
             }
             if (doP)
             {
-                pErr = rawP * nearnessWeight(userCfg, pBasis.coeffs[0], depth);
+                pErr = rawP * nearnessWeight(o, userCfg, pBasis, node.aabb, depth);
                 pImp = isCoarse ? pErr                                                                                         // Octree.cpp:842
                                 : (1.0 / (LegendreCoeffientCount[p + 1] - LegendreCoeffientCount[p])) * (err - 8.0 * pErr);   // Octree.cpp:854
                 t->fits += 1;
@@ -316,6 +358,8 @@ extern "C"
         Eigen::shim_cg_tolerance_override() = 0.0;
         return t;
     }
+
+    void hpref_set_nearness_mc(int on_, uint64_t seed_) { g_nearnessMc = on_; g_nearnessSeed = seed_; }
 
     void* hpref_from_block(const void* ptr_, size_t size_)
     {

@@ -206,6 +206,34 @@ def test_build_option_switches_match_oracle(hp, oracle):
         assert max(rel_inf(ca[i], cb[mb[k]]) for k, i in ma.items() if k in mb and k not in div) <= COEFF_TOL
 
 
+@pytest.mark.parametrize("name", ["sphere_exp_1e8", "sphere_poly_1e8", "custom_domain"])
+def test_mc_counter_nearness_matches_oracle(hp, oracle, name):
+    """nearness_mode = HPSDF_NEARNESS_MC_COUNTER: the reference's 100-sample nearness estimator (Octree.cpp:1209-1247) on
+    Philox points. The oracle side of this mode is bit-identical to the reference's own FApprox run on the same points
+    (tests/test_oracle_vs_ref.py::test_mc_counter_nearness_bit_identical); the device evaluates the same estimator in the
+    scheduler's ingest step. Same bar as the exact-mean mode: identical topology, coefficients 1e-10, Query 1e-9."""
+    from oracle import hpref
+    kw = CASES[name]["cfg"]
+    if kw["nearness"] == 0:
+        pytest.skip("nearness weighting is off in this case")
+    ocfg, oprog = oracle_cfg(hpref, name)
+    cfg, prog = product_cfg(hp, name)
+    o = oracle.OracleTree.build(ocfg, oprog, threads=8, mc_seed=2017)
+    t = hp.Octree()
+    t.Create(cfg, prog, hp.BuildOpts(nearness_mode=hp.NEARNESS_MC_COUNTER, nearness_seed=2017))
+    worst, ndiv = compare_with_oracle_tree(hp, t, o, kw)
+    exact = hp.Octree()
+    exact.Create(cfg, prog)
+    other = hp.Octree()
+    other.Create(cfg, prog, hp.BuildOpts(nearness_mode=hp.NEARNESS_MC_COUNTER, nearness_seed=2018))
+    sizes = [x.stats()["n_coeffs"] for x in (t, exact, other)]
+    print(name, "nodes", t.stats()["n_nodes"], "coeffs (seed 2017, exact mean, seed 2018)", sizes, "worst", worst, "divergent (logged)", ndiv)
+    # the host replay only sees fit records: the mode is refused there, loudly
+    with pytest.raises(hp.HpsdfError) as e:
+        hp.Octree().Create(cfg, prog, hp.BuildOpts(nearness_mode=hp.NEARNESS_MC_COUNTER, nearness_seed=1, scheduler=1))
+    assert e.value.status == hp.ERR_UNSUPPORTED
+
+
 @pytest.mark.parametrize("name", ["csg_small", "sphere_poly_1e8"])
 def test_scheduling_knobs_do_not_change_the_tree(hp, built, name):
     """Round size (min_round_jobs), speculation and strict ordering only change WHEN a job is evaluated and node numbering:

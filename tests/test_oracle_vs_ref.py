@@ -42,6 +42,28 @@ def test_build_bit_identical(ref, oracle, name):
     assert np.array_equal(oracle.OracleTree.from_block(r.block()).query(pts[:2000]), r.query(pts[:2000]))
 
 
+@pytest.mark.parametrize("name", ["sphere_exp_1e8", "sphere_poly_1e8"])
+def test_mc_counter_nearness_bit_identical(ref, oracle, name):
+    """mc_counter(seed): the reference's 100-sample nearness estimator (Octree.cpp:1209-1247) through the reference's own
+    FApprox on Philox points == the restatement, bit for bit; it is a different tree than the exact-mean one, and another
+    seed gives another estimate."""
+    cfg, prog = oracle_cfg(ref, name)
+    r = ref.RefTree.build(cfg, prog, mode=1, threads=8, mc_seed=2017)
+    o = oracle.OracleTree.build(cfg, prog, threads=8, mc_seed=2017)
+    assert np.array_equal(r.apply_log(), o.apply_log())
+    br, bo = ref.parse_block(r.block()), ref.parse_block(o.block())
+    assert np.array_equal(br["coeffs"], bo["coeffs"])
+    for f in ("child", "mn", "mx", "deg", "depth"):
+        assert np.array_equal(br["nodes"][f], bo["nodes"][f]), f
+    exact = oracle.OracleTree.build(cfg, prog, threads=8)
+    other = oracle.OracleTree.build(cfg, prog, threads=8, mc_seed=2018)
+    la, le, lo = o.apply_log(), exact.apply_log(), other.apply_log()
+    assert la.shape != le.shape or not np.array_equal(la, le)
+    assert la.shape != lo.shape or not np.array_equal(la, lo)
+    # the estimate is close to the mean it estimates: the trees have similar sizes
+    assert abs(len(la) - len(le)) <= 0.2 * len(le)
+
+
 def test_max_degree_and_exact_total_switches(ref, oracle):
     cfg, prog = oracle_cfg(ref, "sphere_poly_1e8")
     for kw in (dict(max_degree=3), dict(total_mode=1), dict(max_degree=2, max_depth=6)):
