@@ -88,6 +88,7 @@ namespace hpsdf
             FinishHeader* hostFin = nullptr; FinishHeader* devFin = nullptr;
             uint32_t  finSeq = 0;
             std::vector<cudaEvent_t> ev;         // pairs around the fit launches of a round
+            std::vector<cudaEvent_t> dbgEv;      // HPSDF_DEBUG_ROUNDS=2: one more per round, after the exchange
             // pinned staging for the final read-back
             PinnedBuf<char> hBack;
         };
@@ -360,6 +361,13 @@ namespace hpsdf
                 const hpsdf_status cs = commBroadcastSegments(o_.comm, segs, stream_);
                 if (cs != HPSDF_OK) return cs;
             }
+            static const char* dbg = getenv("HPSDF_DEBUG_ROUNDS");
+            if (dbg && dbg[0] == '2')
+            {
+                const size_t k = evUsed_ / 2 - 1;
+                while (w.dbgEv.size() <= k) { cudaEvent_t e; HPSDF_CUDA(cudaEventCreate(&e)); w.dbgEv.push_back(e); }
+                HPSDF_CUDA(cudaEventRecord(w.dbgEv[k], stream_));
+            }
             t_.stats.algorithmic_flops += flops;
             t_.stats.sdf_evals += evals;
             t_.stats.fits_evaluated += nTasks;
@@ -512,7 +520,24 @@ namespace hpsdf
             t_.stats.kernel_launches++;
             HPSDF_CUDA(cudaStreamSynchronize(stream_));
             t_.stats.finalize_ms = nowMs() - tFin0;
+            {
+                static const char* dbg = getenv("HPSDF_DEBUG_ROUNDS");
+                if (dbg && dbg[0] == '2' && w.dbgEv.size() >= evUsed_ / 2)
+                {
+                    // per round: fit launches, exchange, and the gap to the next round's launches (scheduler kernels + host turn-around)
+                    cudaStreamSynchronize(stream_);
+                    for (size_t k = 0; k + 1 < evUsed_; k += 2)
+                    {
+                        float fit = 0, comm = 0, gap = 0;
+                        cudaEventElapsedTime(&fit, w.ev[k], w.ev[k + 1]);
+                        cudaEventElapsedTime(&comm, w.ev[k + 1], w.dbgEv[k / 2]);
+                        if (k + 2 < evUsed_) cudaEventElapsedTime(&gap, w.dbgEv[k / 2], w.ev[k + 2]);
+                        fprintf(stderr, "rank %d round %zu: fits %.3f ms, exchange %.3f ms, scheduler + turn-around %.3f ms\n", rank_, k / 2, fit, comm, gap);
+                    }
+                }
+            }
             const bool dbgRounds = getenv("HPSDF_DEBUG_ROUNDS") != nullptr;
+            if (dbgRounds) printFitTimeline(rank_);
             if (dbgRounds) fprintf(stderr, "fit launches per round (ms):");
             for (size_t k = 0; k + 1 < evUsed_; k += 2)
             {

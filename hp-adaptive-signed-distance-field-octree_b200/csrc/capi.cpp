@@ -7,6 +7,7 @@
 #include <vector>
 #include "octree.h"
 
+namespace hpsdf { void printMeshStats(); }      // fit_kernels.cuh (HPSDF_MESH_STATS)
 using namespace hpsdf;
 
 namespace
@@ -358,6 +359,7 @@ extern "C"
         std::vector<FitRecord> recs(n);
         if (e == cudaSuccess) e = cudaMemcpy(recs.data(), dR, n * sizeof(FitRecord), cudaMemcpyDeviceToHost);
         if (e == cudaSuccess && elapsed_ms) e = cudaEventElapsedTime(elapsed_ms, e0, e1);
+        if (getenv("HPSDF_MESH_STATS")) printMeshStats();
         if (e == cudaSuccess) for (size_t i = 0; i < n; ++i) raw_err_out[i] = recs[i].rawErr;
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);

@@ -114,6 +114,7 @@ namespace hpsdf
                                 const SdfProgramDev& prog, const RootMap& map, DeviceCtx& ctx, cudaStream_t stream,
                                 size_t sliceOffset = 0, size_t sliceDoubles = 0, int counterIdx = 0);
     cudaError_t reserveSampleScratch(DeviceCtx& ctx, size_t doubles, cudaStream_t stream);
+    void        printFitTimeline(int rank);      // HPSDF_DEBUG_ROUNDS=3
     // jit.cpp: the fit launch the scheduler calls (interpreted kernels, or NVRTC-specialised ones; see hpsdf_build_opts.jit)
     hpsdf_status launchFit(uint32_t jitMode, int degree, const FitTask* dTasks, int n, double* pool, FitRecord* recs,
                            const SdfProgramDev& prog, const RootMap& map, DeviceCtx& ctx, cudaStream_t stream,

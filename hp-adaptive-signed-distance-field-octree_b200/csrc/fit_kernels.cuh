@@ -75,6 +75,30 @@ namespace hpsdf
         fprintf(stderr, "\n");
     }
 
+    // HPSDF_DEBUG_ROUNDS=3: events around the sample and fit kernels of every degree group (diagnostics only)
+    struct FitTimelineEntry { cudaEvent_t a, b, c; int degree; unsigned long long samples; size_t fits; };
+    static std::vector<FitTimelineEntry> g_fitTimeline;
+    static bool fitTimelineOn()
+    {
+        static const char* dbg = getenv("HPSDF_DEBUG_ROUNDS");
+        return dbg && dbg[0] == '3';
+    }
+    void printFitTimeline(int rank)
+    {
+        if (!fitTimelineOn()) return;
+        cudaDeviceSynchronize();
+        for (size_t i = 0; i < g_fitTimeline.size(); ++i)
+        {
+            FitTimelineEntry& e = g_fitTimeline[i];
+            float s = 0, f = 0, fromFirst = 0;
+            cudaEventElapsedTime(&s, e.a, e.b); cudaEventElapsedTime(&f, e.b, e.c);
+            cudaEventElapsedTime(&fromFirst, g_fitTimeline[0].a, e.a);
+            fprintf(stderr, "rank %d t=%8.3f ms: degree %d, %zu fits, %llu samples: sample kernel %.3f ms, fit kernel %.3f ms\n", rank, fromFirst, e.degree, e.fits, e.samples, s, f);
+            cudaEventDestroy(e.a); cudaEventDestroy(e.b); cudaEventDestroy(e.c);
+        }
+        g_fitTimeline.clear();
+    }
+
     template <int D, bool EXT>
     static cudaError_t launchOne(const FitTask* dTasks, int n, double* pool, FitRecord* recs, const SdfProgramDev& prog,
                                  const RootMap& map, const FitTablesDev& tab, double* samples, size_t sampleCap, unsigned long long* counter,
@@ -105,6 +129,13 @@ namespace hpsdf
                 const size_t m = std::min(chunk, (size_t)n - b);
                 const unsigned long long total = (unsigned long long)m * n3;
                 const unsigned long long sms = (unsigned long long)(smCount > 0 ? smCount : 148);
+                FitTimelineEntry tl{};
+                if (fitTimelineOn())
+                {
+                    cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); cudaEventCreate(&tl.c);
+                    tl.degree = D; tl.samples = total; tl.fits = m;
+                    cudaEventRecord(tl.a, stream);
+                }
                 if (prog.n == 1 && prog.instr[0].op == HPSDF_PRIM_MESH)
                 {
                     // the whole program is one mesh: the warp-scheduled traversal kernel (mesh_sample_kernel.cuh)
@@ -116,14 +147,16 @@ namespace hpsdf
                     // B200 (870 k-triangle mesh, binary tree: 2 CTAs/24 lanes 113 ms, 3/24 101 ms, 4/24 95 ms, 4/12 88 ms, 4/4 95 ms;
                     // 4-wide tree: 8 or 12 lanes 62.8 ms, 16 63.9, 20 66.3, 24 70.5)
                     meshSampleKernel<<<(unsigned)std::min(want, sms * 4), 256, 0, stream>>>(dTasks + b, total, D, (const DeviceMeshView*)prog.instr[0].handle,
-                                                                                          map, tab, samples, counter, grab, 12, meshStatsBuffer());
+                                                                                          map, tab, samples, counter, grab, 12, getenv("HPSDF_MESH_NO_HANDOVER") ? 0 : 1, meshStatsBuffer());
                 }
                 else
                 {
                     const unsigned long long want = (total + 255) / 256;
                     sampleKernel<<<(unsigned)std::min(want, sms * 64), 256, 0, stream>>>(dTasks + b, total, D, prog, map, tab, samples);
                 }
+                if (tl.a) cudaEventRecord(tl.b, stream);
                 fitKernel<D, true><<<(unsigned)((m + fitGroup(D) - 1) / fitGroup(D)), fitThreads(D), smem, stream>>>(dTasks + b, pool, recs, prog, map, tab, samples, (int)m);
+                if (tl.a) { cudaEventRecord(tl.c, stream); g_fitTimeline.push_back(tl); }
             }
             return cudaGetLastError();
         }

@@ -1,6 +1,7 @@
 // kernels.cu — the single device translation unit of libhpsdf: constant tables, all kernels, and their launchers.
 // Built for sm_100a only (B200): nvcc -gencode arch=compute_100a,code=sm_100a.
 #include <algorithm>
+#include <vector>
 #include <cuda_runtime.h>
 #include "hp_common.h"
 #include "device_ctx.h"
