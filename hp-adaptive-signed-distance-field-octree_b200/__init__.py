@@ -25,6 +25,7 @@ OK, ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_BAD_BLOCK, ERR_UNSUPPORTED, ER
 NEARNESS_NONE, NEARNESS_POLYNOMIAL, NEARNESS_EXPONENTIAL = 0, 1, 2
 TOTAL_REFERENCE, TOTAL_EXACT_SUM = 0, 1
 NEARNESS_EXACT_MEAN, NEARNESS_MC_COUNTER = 0, 1      # hpsdf_build_opts.nearness_mode
+CG_GUESS_COEFFS, CG_GUESS_REFERENCE = 0, 1           # hpsdf_build_opts.cg_guess
 PRIM = dict(sphere=1, box=2, torus=3, capsule=4, plane=5, mesh=16, octree=17)
 OP = dict(union=64, intersect=65, subtract=66, negate=67)
 # LegendreCoeffientCount incl. the reference's f64 truncation at degree 6 (Utility.h:87-106 yields 83, not 84)
@@ -65,7 +66,7 @@ class BuildOpts(C.Structure):
                 ("nearness_mode", C.c_uint32), ("total_mode", C.c_uint32), ("cg_max_iterations", C.c_uint32),
                 ("cg_tolerance", C.c_double), ("device", C.c_int32), ("speculate", C.c_uint32),
                 ("strict_order", C.c_uint32), ("comm", C.c_void_p), ("stream", C.c_void_p),
-                ("jit", C.c_uint32), ("min_round_jobs", C.c_uint32), ("scheduler", C.c_uint32), ("reserved0", C.c_uint32),
+                ("jit", C.c_uint32), ("min_round_jobs", C.c_uint32), ("scheduler", C.c_uint32), ("cg_guess", C.c_uint32),
                 ("nearness_seed", C.c_uint64)]
 
     def __init__(self, **kw):

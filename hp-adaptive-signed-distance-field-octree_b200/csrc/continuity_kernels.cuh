@@ -524,7 +524,7 @@ namespace hpsdf
     //     w = A u;  gamma' = (r, u);  delta = (w, u);  |r|^2                                    | barrier
     //     beta = gamma' / gamma;  alpha = gamma' / (delta - beta gamma' / alpha)
     // Same Krylov iterates in exact arithmetic; Eigen's stopping rule |r|^2 < tol^2 |b|^2 on the recursively updated residual,
-    // diagonal preconditioner, x0 = b = lambda c (Octree.cpp:1738-1755). Deterministic: fixed row -> lane assignment and
+    // diagonal preconditioner, x0 = what the caller left in x (c, or the reference's lambda c: Octree.cpp:1738-1755). Deterministic: fixed row -> lane assignment and
     // fixed-shape reductions.
     __global__ void __launch_bounds__(kCgThreads) cgKernel(const CgParams P)
     {

@@ -105,7 +105,9 @@ enum
                                         min + (max - min) * u in f32 as AlignedBox::sample(). Reproducible for a given seed and
                                         independent of the schedule; for A/B runs against the literal reference. Device scheduler only. */
     HPSDF_TOTAL_REFERENCE     = 0,   /* totalCoeffError bookkeeping exactly as Octree.cpp:212,257,272,276 (sentinel 8^4*100) */
-    HPSDF_TOTAL_EXACT_SUM     = 1    /* sum of leaf errors recomputed without the sentinel bias */
+    HPSDF_TOTAL_EXACT_SUM     = 1,   /* sum of leaf errors recomputed without the sentinel bias */
+    HPSDF_CG_GUESS_COEFFS     = 0,
+    HPSDF_CG_GUESS_REFERENCE  = 1
 };
 
 typedef struct hpsdf_comm hpsdf_comm;   /* one rank of a multi-GPU job, see hpsdf_comm_init */
@@ -134,7 +136,10 @@ typedef struct hpsdf_build_opts
     uint32_t scheduler;           /* 0 = the greedy loop (queue, h-vs-p decision, error bookkeeping, node allocation, job selection) runs
                                      on the device, one 128-byte header per round comes back; 1 = the loop is replayed on the host from
                                      16-byte fit records (round-1 implementation; also used when strict_order = 1) */
-    uint32_t reserved0;
+    uint32_t cg_guess;            /* initial guess of the continuity solve (M + lambda I) x = lambda c: 0 = the unconstrained coefficients c
+                                     (the solution is c plus a small correction: 38 iterations instead of 71 on the README config, same
+                                     stopping rule), 1 = the reference's own guess lambda c (solveWithGuess(oldCoeffs, oldCoeffs),
+                                     Octree.cpp:1741, 1755) */
     uint64_t nearness_seed;       /* HPSDF_NEARNESS_MC_COUNTER: key of the sample-point generator */
 } hpsdf_build_opts;
 

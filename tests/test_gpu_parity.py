@@ -181,8 +181,15 @@ def test_continuity_matches_reference_golden(hp, built, name):
     b6 = hp.parse_block(t6.ToMemoryBlockBytes())
     gap = np.abs(b6["coeffs"] - blk["coeffs"]).max()
     assert gap <= 1e-6 * np.abs(blk["coeffs"]).max() * 10
+    # the reference starts CG from lambda * c (Octree.cpp:1755); the default here starts from c: same converged solution,
+    # same stopping rule, fewer iterations
+    tr = built(name, cg_tolerance=1e-13, cg_guess=hp.CG_GUESS_REFERENCE)
+    br = hp.parse_block(tr.ToMemoryBlockBytes())
+    assert np.abs(br["coeffs"] - blk["coeffs"]).max() <= 1e-12 * np.abs(blk["coeffs"]).max()
+    t6r = built(name, cg_guess=hp.CG_GUESS_REFERENCE)
+    assert t6.stats()["cg_iterations"] < t6r.stats()["cg_iterations"]
     print(name, "worst", worst, "cg its", st["cg_iterations"], "res", st["cg_relative_residual"], "ms", st["continuity_ms"],
-          "tol-1e-6 gap", gap, "its", t6.stats()["cg_iterations"])
+          "tol-1e-6 gap", gap, "its", t6.stats()["cg_iterations"], "its with the reference's guess", t6r.stats()["cg_iterations"])
 
 
 def test_build_option_switches_match_oracle(hp, oracle):
