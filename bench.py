@@ -42,6 +42,7 @@ PKG = "hp-adaptive-signed-distance-field-octree_b200"
 WORKLOAD = "c3_dragon_standin"
 METRIC = "octree_build_nodes_fitted_per_s"
 QUERY_POINTS = 1 << 24            # 16.7 M points = 512 MB in + 128 MB out: larger than the 126 MB L2
+NCU_QUERY_TRAFFIC_BYTES = 405746176 + 119461632
 MESH_UV = (1000, 435)             # bumpy torus with 870 000 triangles: the stand-in of configs[2]'s dragon.obj (absent from the reference tree)
 MESH_C4_UV = (1000, 800)          # 1.6 M triangles: the stand-in of configs[3]'s Ramesses.obj
 C3 = dict(threshold=1e-6, continuity=True, cstrength=8.0, max_degree=11)
@@ -409,7 +410,11 @@ def bench_query(cx, tree, box, fp64_peak, label):
             "ms": q_ms, "scaling": "weak",
             "e2e": {"value": cx.world * n_qe / qe_s, "unit": "points/s", "h2d_bytes_per_step": n_qe * 24, "d2h_bytes_per_step": n_qe * 8},
             "roofline": {"kernel": "queryKernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                         "algorithmic_bytes_per_launch": n_q * 32, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": n_q * 32,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch shape (2^24 points,
+                         # C2 tree): profiles/r2_query_kernel.md. Not re-measured in this run.
+                         "traffic": NCU_QUERY_TRAFFIC_BYTES if n_q == (1 << 24) else None,
+                         "traffic_source": "profiles/r2_query_kernel.md (405.7 MB read + 119.5 MB written per 2^24-point launch)", "peak_source": peak_src,
                          "fp64": {"algorithmic_flops_per_point": q_flops, "achieved": q_flops * n_q / (q_ms * 1e-3) / 1e12,
                                   "peak": fp64_peak, "unit": "TFLOP/s", "frac": q_flops * n_q / (q_ms * 1e-3) / 1e12 / fp64_peak}}}
 

@@ -272,6 +272,7 @@ namespace hpsdf
         if (i < T.nNodes)
         {
             S.cell[i] = T.cell[i]; S.child[i] = T.child[i]; S.code[i] = T.code[i]; S.depth[i] = T.depth[i]; S.degree[i] = T.degree[i]; S.state[i] = T.state[i];
+            S.err[i] = 0.0;                       // internal template nodes never get one; the array is copied out whole (leaf errors of the cut-tie log)
         }
         if (i < T.nJobs)
         {

@@ -819,7 +819,9 @@ namespace hpsdf
             {
                 // sequential-greedy state (Octree.cpp:216): terminated?
                 const double value = S.totalMode == HPSDF_TOTAL_EXACT_SUM ? sh.exactSum : sh.total;
-                if (!(value >= S.threshold) || sh.nOpen == 0u) { if (tid == 0) sh.done = 1u; __syncthreads(); break; }
+                // (every thread takes this decision from the same shared values; the barrier before the write keeps a thread that is
+                // still reading sh.done above from seeing it — it would leave the loop through the other exit, one barrier out of step)
+                if (!(value >= S.threshold) || sh.nOpen == 0u) { __syncthreads(); if (tid == 0) sh.done = 1u; __syncthreads(); break; }
                 uint32_t cntAbove = 0;
                 const double L = histLevel(S, sh, value, cntAbove);
                 if (cntAbove > 0u)
@@ -867,7 +869,9 @@ namespace hpsdf
                 applyJobs(S, sh, bulk, nBulk);
             }
             if (sh.done != 0u) break;
-            if (sh.aboveLevel <= 0)
+            const int aboveNow = sh.aboveLevel;
+            __syncthreads();                                                   // everybody has read it before thread 0 resets it
+            if (aboveNow <= 0)
             {
                 if (tid == 0) { sh.levelKey = kNoLevel; sh.levelNode = kNone; sh.aboveLevel = 0; }     // everything at or above the level is refined: sequential state again
                 __syncthreads();
@@ -889,7 +893,8 @@ namespace hpsdf
             constexpr uint32_t IT = 8;                              // list entries per thread and chunk: one block-wide scan per 8192 entries
             // compact the cached list (drop applied jobs)
             uint32_t keep = 0;
-            for (uint32_t base = 0; base < sh.nCached; base += kSchedThreads * IT)
+            const uint32_t nCachedNow = sh.nCached;                 // (read once: thread 0 overwrites it right after the loop)
+            for (uint32_t base = 0; base < nCachedNow; base += kSchedThreads * IT)
             {
                 uint32_t jv[IT];
                 uint32_t liveMask = 0, nl = 0;
@@ -897,7 +902,7 @@ namespace hpsdf
                 for (uint32_t r = 0; r < IT; ++r)
                 {
                     const uint32_t i = base + tid * IT + r;
-                    jv[r] = i < sh.nCached ? S.cached[i] : kNone;
+                    jv[r] = i < nCachedNow ? S.cached[i] : kNone;
                 }
                 #pragma unroll
                 for (uint32_t r = 0; r < IT; ++r)
@@ -909,6 +914,7 @@ namespace hpsdf
                 keep += total;
                 __syncthreads();
             }
+            __syncthreads();
             if (tid == 0) sh.nCached = keep;
             if (tid < kMaxDegree + 2) sh.degCnt[tid] = 0;
             __syncthreads();
@@ -960,7 +966,8 @@ namespace hpsdf
                 // pass A over the open list: compaction (dead entries out) + selection. Offsets come from one block-wide scan of
                 // packed per-thread counts (warp shuffles + one exchange through shared memory), so list order is preserved.
                 uint32_t keepOpen = 0;
-                for (uint32_t base = 0; base < sh.nOpen; base += kSchedThreads * IT)
+                const uint32_t nOpenNow = sh.nOpen;                 // (read once: thread 0 overwrites it right after the loop)
+                for (uint32_t base = 0; base < nOpenNow; base += kSchedThreads * IT)
                 {
                     uint32_t nv[IT];
                     double ev[IT];
@@ -969,7 +976,7 @@ namespace hpsdf
                     for (uint32_t r = 0; r < IT; ++r)
                     {
                         const uint32_t i = base + tid * IT + r;
-                        nv[r] = i < sh.nOpen ? S.open[i] : kNone;
+                        nv[r] = i < nOpenNow ? S.open[i] : kNone;
                     }
                     #pragma unroll
                     for (uint32_t r = 0; r < IT; ++r)
