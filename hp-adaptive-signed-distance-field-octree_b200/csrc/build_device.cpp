@@ -386,7 +386,9 @@ namespace hpsdf
             S.speculate = o_.speculate;
             S.dealJobs = world_ > 1 ? 1u : 0u;
             S.split = S.dealJobs ? 0u : 1u;
+            if (const char* dl = getenv("HPSDF_SCHED_DEAL")) S.dealJobs = dl[0] != '0' ? 1u : S.dealJobs;               // diagnostics: the multi-GPU job order on one GPU
             if (const char* sp = getenv("HPSDF_SCHED_SPLIT")) S.split = sp[0] != '0' && !S.dealJobs ? 1u : 0u;      // diagnostics: the single-CTA ingest / selection on one GPU
+            if (S.dealJobs) S.split = 0u;
             S.hostHdr = w.devHdr;
             evUsed_ = 0;
             memset(&t_.stats, 0, sizeof(t_.stats));
