@@ -174,7 +174,7 @@ namespace hpsdf
             e = cudaMemcpyAsync(dFaces, ws.hFaces.p, faces.size() * sizeof(FaceJobDev), cudaMemcpyHostToDevice, stream);
         }
         if (e == cudaSuccess) e = launchDiagEmit(keys, vals, n, t.cfg.continuity_strength, stream);
-        if (e == cudaSuccess) e = launchFaceEmit(dFaces, (uint32_t)nFaces, *t.ctx, keys, vals, stream);
+        if (e == cudaSuccess) e = launchFaceEmit(dFaces, (uint32_t)nFaces, *t.ctx, keys, vals, n, stream);
         if (e == cudaSuccess) e = cooToCsr(keys, vals, keysAlt, valsAlt, uniq, dNum, tmp, tmpBytes, cur, n, csr, stream);
         t.stats.continuity_assembly_ms = nowMs() - tAsm0;
         const double tCg0 = nowMs();

@@ -4,7 +4,7 @@
 // (EvaluateSharedFaceIntegralAnalytically :1459-1546 for equal depths, ...Numerically :1250-1456 otherwise), lambda is
 // added on the diagonal, and (M + lambda I) x = lambda c is solved with Eigen's ConjugateGradient (:1751-1755).
 //
-// Here: (1) one CTA per face emits that face's entries as (row << 32 | col, value) pairs at a precomputed offset —
+// Here: (1) one CTA per face emits that face's entries as (row << bits | col, value) pairs (bits = ceil(log2 n): the radix sort then needs 2 bits / 8 passes) at a precomputed offset —
 // positions inside a face come from an ordered block-wide compaction, so the COO order (and hence the order in which
 // duplicates are summed) is deterministic; (2) a radix sort + segmented reduction (CUB: plumbing) turns COO into CSR
 // with duplicates summed, which is what setFromTriplets does (:1732-1735); (3) a hand-written persistent cooperative
@@ -49,7 +49,7 @@ namespace hpsdf
     __global__ void __launch_bounds__(kFaceThreads)
     faceEmitKernel(const FaceJobDev* __restrict__ faces, uint32_t nFaces, const uint32_t* __restrict__ bidx,
                    const double* __restrict__ glRoots, const double* __restrict__ glWeights,
-                   uint64_t* __restrict__ keys, double* __restrict__ vals)
+                   uint64_t* __restrict__ keys, double* __restrict__ vals, const int keyShift)   // key = row << keyShift | col
     {
         __shared__ uint32_t sWarp[kFaceThreads / 32];
         __shared__ double sL[2][3][kMaxDegree + 1][kMaxDegree + 1];     // [side A/B][axis][degree][node]: LpX at the sample coordinates
@@ -84,8 +84,8 @@ namespace hpsdf
                         {
                             v = blk == 1 ? -1.0 : 1.0;
                             v *= lr[id]; v *= c_nl[id][depthR]; v *= lc[jd]; v *= c_nl[jd][depthC];
-                            key  = ((uint64_t)(rowStart + i) << 32) | (uint64_t)(colStart + j);
-                            keyT = ((uint64_t)(colStart + j) << 32) | (uint64_t)(rowStart + i);
+                            key  = ((uint64_t)(rowStart + i) << keyShift) | (uint64_t)(colStart + j);
+                            keyT = ((uint64_t)(colStart + j) << keyShift) | (uint64_t)(rowStart + i);
                         }
                     }
                     emitOrdered(keep, key, v, keys, vals, base, sWarp);
@@ -157,11 +157,11 @@ namespace hpsdf
                 const double v = fabsf((float)integral) > 0.000001f ? integral : 0.0;                   // EPSILON_F32 drop (:1336)
                 // dense layout per block: candidate order; the AB block is followed by its transpose
                 const unsigned long long pos = base + (blk == 1 ? 2ull * cand : (unsigned long long)cand);
-                keys[pos] = ((uint64_t)(rowStart + i) << 32) | (uint64_t)(colStart + j);
+                keys[pos] = ((uint64_t)(rowStart + i) << keyShift) | (uint64_t)(colStart + j);
                 vals[pos] = v;
                 if (blk == 1)
                 {
-                    keys[pos + 1] = ((uint64_t)(colStart + j) << 32) | (uint64_t)(rowStart + i);
+                    keys[pos + 1] = ((uint64_t)(colStart + j) << keyShift) | (uint64_t)(rowStart + i);
                     vals[pos + 1] = v;
                 }
             }
@@ -279,10 +279,10 @@ namespace hpsdf
         if (counts) counts[i] = mine;
     }
 
-    __global__ void diagEmitKernel(uint64_t* __restrict__ keys, double* __restrict__ vals, uint32_t n, double lambda)
+    __global__ void diagEmitKernel(uint64_t* __restrict__ keys, double* __restrict__ vals, uint32_t n, double lambda, int keyShift)
     {
         const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-        if (i < n) { keys[i] = ((uint64_t)i << 32) | i; vals[i] = lambda; }                   // Octree.cpp:1724-1729
+        if (i < n) { keys[i] = ((uint64_t)i << keyShift) | i; vals[i] = lambda; }                   // Octree.cpp:1724-1729
     }
 
     __global__ void flagNonZeroKernel(const double* __restrict__ v, uint32_t n, uint8_t* __restrict__ flags)
@@ -293,13 +293,13 @@ namespace hpsdf
 
     // rowPtr from sorted unique keys: rowPtr[r] = first entry whose row >= r
     __global__ void rowPtrKernel(const uint64_t* __restrict__ keys, uint32_t nnz, uint32_t n, uint32_t* __restrict__ rowPtr,
-                                 uint32_t* __restrict__ col)
+                                 uint32_t* __restrict__ col, int keyShift)
     {
         const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
         if (k > nnz) return;
-        const uint32_t rowHere = k < nnz ? (uint32_t)(keys[k] >> 32) : n;
-        const uint32_t rowPrev = k > 0 ? (uint32_t)(keys[k - 1] >> 32) : 0xFFFFFFFFu;
-        if (k < nnz) col[k] = (uint32_t)(keys[k] & 0xFFFFFFFFu);
+        const uint32_t rowHere = k < nnz ? (uint32_t)(keys[k] >> keyShift) : n;
+        const uint32_t rowPrev = k > 0 ? (uint32_t)(keys[k - 1] >> keyShift) : 0xFFFFFFFFu;
+        if (k < nnz) col[k] = (uint32_t)(keys[k] & ((1ull << keyShift) - 1ull));
         if (k == 0) { for (uint32_t r = 0; r <= rowHere && r <= n; ++r) rowPtr[r] = 0; }
         else if (rowHere != rowPrev) { for (uint32_t r = rowPrev + 1; r <= rowHere && r <= n; ++r) rowPtr[r] = k; }
     }

@@ -131,7 +131,7 @@ namespace hpsdf
                                unsigned char* dHit, double* dT, cudaStream_t stream);
     cudaError_t launchQueryGradient(const DeviceTreeView& view, const double* dXyz, size_t n, double* dOut, double* dGrad, cudaStream_t stream);
     // continuity (continuity_kernels.cuh)
-    cudaError_t launchFaceEmit(const FaceJobDev* dFaces, uint32_t nFaces, const DeviceCtx& ctx, uint64_t* keys, double* vals, cudaStream_t stream);
+    cudaError_t launchFaceEmit(const FaceJobDev* dFaces, uint32_t nFaces, const DeviceCtx& ctx, uint64_t* keys, double* vals, uint32_t n, cudaStream_t stream);
     size_t      faceEnumTempBytes(uint32_t nNodes);
     cudaError_t launchFaceCount(const unsigned char* image, uint32_t nNodes, const uint32_t* matchCount, char* scratch, unsigned long long* hostTotals,
                                 cudaStream_t stream);

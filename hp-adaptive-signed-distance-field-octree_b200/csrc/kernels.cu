@@ -88,17 +88,26 @@ namespace hpsdf
         return cudaGetLastError();
     }
 
-    cudaError_t launchFaceEmit(const FaceJobDev* dFaces, uint32_t nFaces, const DeviceCtx& ctx, uint64_t* keys, double* vals, cudaStream_t stream)
+    // COO keys are row << cooKeyShift(n) | col: as few significant bits as the matrix size allows, because every 8 of them
+    // are one pass of the radix sort (n = 94 850: 34 bits = 5 passes; row << 32 | col needed 7)
+    int cooKeyShift(uint32_t n)
+    {
+        int bits = 1;
+        while (bits < 32 && (1ull << bits) < (uint64_t)n) ++bits;
+        return bits;
+    }
+
+    cudaError_t launchFaceEmit(const FaceJobDev* dFaces, uint32_t nFaces, const DeviceCtx& ctx, uint64_t* keys, double* vals, uint32_t n, cudaStream_t stream)
     {
         if (!nFaces) return cudaSuccess;
-        faceEmitKernel<<<nFaces, kFaceThreads, 0, stream>>>(dFaces, nFaces, ctx.fitTab.bidx, ctx.glRoots, ctx.glWeights, keys, vals);
+        faceEmitKernel<<<nFaces, kFaceThreads, 0, stream>>>(dFaces, nFaces, ctx.fitTab.bidx, ctx.glRoots, ctx.glWeights, keys, vals, cooKeyShift(n));
         return cudaGetLastError();
     }
 
     cudaError_t launchDiagEmit(uint64_t* keys, double* vals, uint32_t n, double lambda, cudaStream_t stream)
     {
         if (!n) return cudaSuccess;
-        diagEmitKernel<<<(n + 255) / 256, 256, 0, stream>>>(keys, vals, n, lambda);
+        diagEmitKernel<<<(n + 255) / 256, 256, 0, stream>>>(keys, vals, n, lambda, cooKeyShift(n));
         return cudaGetLastError();
     }
 
@@ -115,8 +124,8 @@ namespace hpsdf
         size_t tmpSort = 0, tmpRed = 0;
         cub::DoubleBuffer<uint64_t> kb((uint64_t*)nullptr, (uint64_t*)nullptr);
         cub::DoubleBuffer<double>   vb((double*)nullptr, (double*)nullptr);
-        int bits = 1; while (bits < 32 && (1ull << bits) < (uint64_t)n) ++bits;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmpSort, kb, vb, (int)nCoo, 0, 32 + bits, (cudaStream_t)0);
+        const int bits = cooKeyShift(n);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmpSort, kb, vb, (int)nCoo, 0, 2 * bits, (cudaStream_t)0);
         cub::DeviceReduce::ReduceByKey(nullptr, tmpRed, (uint64_t*)nullptr, (uint64_t*)nullptr, (double*)nullptr, (double*)nullptr,
                                        (uint32_t*)nullptr, cub::Sum(), (int)nCoo, (cudaStream_t)0);
         size_t tmpSel = 0;
@@ -133,11 +142,11 @@ namespace hpsdf
     {
         cub::DoubleBuffer<uint64_t> kb(keys, keysAlt);
         cub::DoubleBuffer<double>   vb(vals, valsAlt);
-        // keys are (row << 32 | col) with row, col < n: only the significant bits need sorting; radix sort is stable, so
-        // duplicates keep their emission order and are summed in that order
-        int bits = 1; while (bits < 32 && (1ull << bits) < (uint64_t)n) ++bits;
+        // keys are (row << bits | col) with row, col < n <= 2^bits: only the significant bits are sorted; radix sort is stable,
+        // so duplicates keep their emission order and are summed in that order
+        const int bits = cooKeyShift(n);
         size_t tb = tmpBytes;
-        cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tb, kb, vb, (int)nCoo, 0, 32 + bits, stream);
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tb, kb, vb, (int)nCoo, 0, 2 * bits, stream);
         tb = tmpBytes;
         if (e == cudaSuccess) e = cub::DeviceReduce::ReduceByKey(tmp, tb, kb.Current(), uniq, vb.Current(), csr.val, dNum, cub::Sum(), (int)nCoo, stream);
         uint32_t nUniq = 0;
@@ -164,7 +173,7 @@ namespace hpsdf
         }
         if (e == cudaSuccess)
         {
-            rowPtrKernel<<<(nnz + 1 + 255) / 256, 256, 0, stream>>>(selKeys, nnz, n, csr.rowPtr, csr.col);
+            rowPtrKernel<<<(nnz + 1 + 255) / 256, 256, 0, stream>>>(selKeys, nnz, n, csr.rowPtr, csr.col, bits);
             e = cudaGetLastError();
         }
         csr.n = n; csr.nnz = nnz;
