@@ -21,7 +21,9 @@
 struct hpsdf_mesh
 {
     int      device = 0;
-    void*    blob = nullptr;                  // nodes | triVerts | pseudo | view
+    hpsdf::DeviceCtx* ctx = nullptr;
+    void*    blob = nullptr;                  // nodes | triVerts | pseudo | oriented boxes | wide nodes | view (from the device's blob cache)
+    size_t   blobBytes = 0;
     hpsdf::DeviceMeshView  view{};
     hpsdf::DeviceMeshView* dView = nullptr;
     float    mn[3] = { 0, 0, 0 }, mx[3] = { 0, 0, 0 };
@@ -135,7 +137,10 @@ extern "C"
         auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
         const size_t bNodes = align((size_t)nNodes * sizeof(BvhNode)), bTv = align((size_t)nT * 48), bPs = align((size_t)nT * 84),
                      bObb = align((size_t)nNodes * 64), bWide = align((size_t)nWide * 272);
-        cudaError_t e = cudaMalloc(&m->blob, bNodes + bTv + bPs + bObb + bWide + 256);
+        // the ~200 MB of a large mesh come from the device's cache of released allocations (cudaMalloc + cudaFree of that size
+        // cost 5-25 ms, more than the set-up kernels, when meshes are created and destroyed in a loop)
+        m->ctx = ctx;
+        cudaError_t e = acquireBlob(*ctx, bNodes + bTv + bPs + bObb + bWide + 256, &m->blob, &m->blobBytes);
         if (e != cudaSuccess) { delete m; return failCuda(e, "mesh allocation"); }
         char* p = (char*)m->blob;
         m->view.nodes = (const BvhNode*)p;
@@ -148,7 +153,7 @@ extern "C"
 
         std::lock_guard<std::mutex> wsLock(*(std::mutex*)ctx->wsMutex);         // the temporaries live in the device's build workspace
         cudaStream_t stream = ctx->ws.stream;
-        auto fail = [&](hpsdf_status st) { cudaStreamSynchronize(stream); cudaFree(m->blob); delete m; return st; };
+        auto fail = [&](hpsdf_status st) { cudaStreamSynchronize(stream); releaseBlob(*ctx, m->blob, m->blobBytes); delete m; return st; };
         const size_t bIn = align((size_t)nV * 12) + align((size_t)nT * 12);
         e = ctx->ws.meshTmp.reserve(bIn + meshBuildTempBytes(nT, nNodes));
         if (e != cudaSuccess) return fail(failCuda(e, "mesh workspace"));
@@ -226,7 +231,9 @@ extern "C"
     {
         if (!mesh) return;
         cudaSetDevice(mesh->device);
-        cudaFree(mesh->blob);
+        cudaDeviceSynchronize();                       // what cudaFree did implicitly: nothing in flight may still read the mesh
+        if (mesh->ctx) releaseBlob(*mesh->ctx, mesh->blob, mesh->blobBytes);
+        else cudaFree(mesh->blob);
         delete mesh;
     }
 }
