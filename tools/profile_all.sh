@@ -9,9 +9,9 @@ $N -k regex:meshSample -s 1 -c 1 -o /tmp/prof/mesh python tools/ncu_target.py me
 $N -k regex:fitKernel -s 2 -c 2 -o /tmp/prof/fitjit python tools/ncu_target.py fitjit > gpurun_out/ncu_fitjit.log 2>&1
 $N -k regex:queryKernel -s 2 -c 1 -o /tmp/prof/query python tools/ncu_target.py query > gpurun_out/ncu_query.log 2>&1
 $N -k regex:"schedRound|schedSelect|schedIngest" -s 12 -c 6 -o /tmp/prof/sched python tools/ncu_target.py sched > gpurun_out/ncu_sched.log 2>&1
-$N -k regex:"cgKernel|faceEnum|faceEmit" -c 3 -o /tmp/prof/cont python tools/ncu_target.py continuity > gpurun_out/ncu_cont.log 2>&1
+timeout 240 $N -k regex:"cgKernel|faceEnum|faceEmit" -c 4 -o /tmp/prof/cont python tools/ncu_target.py continuity > gpurun_out/ncu_cont.log 2>&1
 $N -k regex:"meshPseudo|meshLevelKeys|meshObb|meshRefit" -c 4 -o /tmp/prof/meshbuild python tools/mesh_create_time.py > gpurun_out/ncu_meshbuild.log 2>&1
-python tools/summarize_ncu.py report /tmp/prof/mesh.ncu-rep gpurun_out/r2_mesh_sample_kernel.md "Round 2: meshSampleKernel, first round of the 870 000-triangle config (4096 coarse fits, 3.0 M samples)"
+python tools/summarize_ncu.py report /tmp/prof/mesh.ncu-rep gpurun_out/r2_mesh_sample_kernel.md "Round 2: meshSampleKernel (with the tail phase), first round of the 870 000-triangle config (4096 coarse fits, 3.0 M samples)"
 python tools/summarize_ncu.py report /tmp/prof/fitjit.ncu-rep gpurun_out/r2_fit_kernel_jit.md "Round 2: fitKernel<D,false> specialised at run time (NVRTC, parameters in constant memory) for the C2 program, synthetic frontier p=2"
 python tools/summarize_ncu.py report /tmp/prof/query.ncu-rep gpurun_out/r2_query_kernel.md "Round 2: queryKernel, 16.7 M uniform points on the C2 tree"
 python tools/summarize_ncu.py report /tmp/prof/sched.ncu-rep gpurun_out/r2_scheduler_kernels.md "Round 2: device-resident scheduler kernels of a C2 build (rounds 3-5)"
