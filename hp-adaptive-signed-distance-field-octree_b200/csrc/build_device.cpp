@@ -3,7 +3,7 @@
 // Reference (Source/HP/Octree.cpp): Create :312-352 -> CreateRoot :792-801 -> UniformlyRefine :112-191 -> RunBuildThreadPool
 // :194-309 + TickBuildThread :558-659 -> ReallocCoeffs :474-555 -> PerformContinuityPostProcess :1717-1762.
 //
-// Per round the host does three things: read the 128-byte header the scheduler kernel wrote into mapped pinned memory (how
+// Per round the host does three things: read the 112-byte header the scheduler kernel wrote into mapped pinned memory (how
 // many fits of which degree the next round has), launch expandJobsKernel + one fit kernel per degree present (+ the NCCL
 // exchange when the round is sharded over several GPUs), and launch the scheduler kernel again. Queue, decision, error
 // bookkeeping, node allocation and job selection never leave the device; at the end the node arrays come back once.

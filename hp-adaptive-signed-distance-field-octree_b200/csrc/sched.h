@@ -4,7 +4,7 @@
 // Reference: RunBuildThreadPool (Source/HP/Octree.cpp:194-309) pops the max-error leaf from a std::priority_queue, evaluates
 // its refinement job on a worker (TickBuildThread :558-659), applies the h- or p-refinement, pushes the results back and stops
 // when totalCoeffError < threshold. Here the queue, the decision, the error bookkeeping and the node allocation live on the
-// device; the host only launches kernels and reads one 128-byte header per round.
+// device; the host only launches kernels and reads one 112-byte header per round.
 //
 //   nodes      structure of arrays, children in blocks of 8 (Subdivide :1115-1128), same numbering scheme as the reference for
 //              the uniform depth-4 start (UniformlyRefine :112-191)
@@ -74,6 +74,8 @@ namespace hpsdf
         uint32_t nNodes, nOpen, nCached, poolUsed;
         uint32_t pad[6];
     };
+
+    static_assert(sizeof(RoundHeader) == 112, "RoundHeader: the size quoted in include/hpsdf.h and DESIGN.md");
 
     // Device templates of the uniform depth-4 start (built once per device).
     struct SchedTemplates

@@ -134,7 +134,7 @@ typedef struct hpsdf_build_opts
                                      (the next-largest errors beyond the guaranteed level); 0 = 512 for closed-form programs,
                                      128 for mesh / octree programs (device scheduler; the host replay uses 1 for those) */
     uint32_t scheduler;           /* 0 = the greedy loop (queue, h-vs-p decision, error bookkeeping, node allocation, job selection) runs
-                                     on the device, one 128-byte header per round comes back; 1 = the loop is replayed on the host from
+                                     on the device, one 112-byte header per round comes back; 1 = the loop is replayed on the host from
                                      16-byte fit records (round-1 implementation; also used when strict_order = 1) */
     uint32_t cg_guess;            /* initial guess of the continuity solve (M + lambda I) x = lambda c: 0 = the unconstrained coefficients c
                                      (the solution is c plus a small correction: 38 iterations instead of 71 on the README config, same
