@@ -194,7 +194,7 @@ namespace hpsdf
             const size_t sizes[] = {
                 n * 16, n * 4, n * 4, n * 8, n * 4, n * 4, n, n, n,                 // nodes: cell child slot err code jobOf depth degree state
                 n * 4, n * 4, n * 4, n * 4, n * 4, n * 72, n,                        // jobs: node hslot pslot hpos ppos err flags
-                n * 4, n * 4, 2 * n * 4, n * 4, (n / 8192 + 2) * 64,                // open, cached, scratch, second open list, chunk counters
+                n * 4, n * 4, 2 * n * 4, n * 4, (n / kSelChunk + 2) * 64,           // open, cached, scratch, second open list, chunk counters
                 (size_t)kSubBuckets * 4, (size_t)kSubBuckets * 8, (size_t)kSubBuckets * 4,
                 n * sizeof(JobDesc), sizeof(RoundLayout), n * sizeof(hpsdf_apply_log_entry), 4096 * sizeof(hpsdf_decision_log_entry),
                 sizeof(SchedCounters),

@@ -18,6 +18,8 @@
 namespace hpsdf
 {
     constexpr int      kSchedThreads  = 1024;
+    constexpr uint32_t kSelItems      = 1;                   // open-list entries per thread of the split-mode selection kernels
+    constexpr uint32_t kSelChunk      = kSchedThreads * kSelItems;      // entries per CTA
     constexpr int      kSubPerOctave  = 16;
     constexpr int      kOctaves       = 2200;
     constexpr int      kSubBuckets    = kOctaves * kSubPerOctave;

@@ -1156,9 +1156,8 @@ namespace hpsdf
         }
     }
 
-    constexpr uint32_t kSelItems = 8, kSelChunk = kSchedThreads * kSelItems;
 
-    // what one thread sees of its 8 consecutive open-list entries
+    // what one thread sees of its kSelItems consecutive open-list entries
     struct SelView
     {
         uint32_t node[kSelItems];
@@ -1186,7 +1185,7 @@ namespace hpsdf
         }
     }
 
-    // pass 1: per chunk of 8192 entries: live entries, selected entries, fits per degree -> chunkCounts[chunk][16]
+    // pass 1: per chunk of kSelChunk entries: live entries, selected entries, fits per degree -> chunkCounts[chunk][16]
     __global__ void __launch_bounds__(kSchedThreads, 1) schedSelectCountKernel(const SchedDev S)
     {
         __shared__ uint32_t sCnt[16];
