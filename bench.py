@@ -460,6 +460,9 @@ def bench_c2(cx, args, fp64_peak, with_cpu):
            "gpu_busy_frac": agg["fit_kernel_ms"] / args.steps / ms,
            "roofline": {"kernel": "fitKernel<D> specialised to the program (all fit launches of the timed builds)", "bound": "fp64",
                         "achieved": fit_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fit_tflops / fp64_peak,
+                        # FP64 on the CUDA cores (tcgen05 has no FP64 kind): neither of the contract's "hbm" / "tensor"; DRAM traffic of
+                        # these kernels is 32 B read per fit (ncu: 8.4 MB for 262 144 fits, profiles/r2_fit_kernel_jit.md), so no HBM figure
+                        "traffic": None, "peak_source": "DFMA rate measured in this run (dfmaPeakKernel); MEASURED_PEAKS.json holds no FP64 figure",
                         "whole_step_frac": agg["algorithmic_flops"] / args.steps / (ms * 1e-3) / 1e12 / fp64_peak}}
     frontier = {}
     if cx.rank == 0:
