@@ -349,6 +349,9 @@ static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
     }
 }
 
+/* test hook: one Philox4x32-10 block (tests/test_oracle_vs_ref.py checks it against the Random123 known-answer vectors) */
+void hporacle_philox(uint32_t c[4], uint32_t k0, uint32_t k1) { philox4x32_10(c, k0, k1); }
+
 static double f_approx(const double* coeffs, uint32_t degree, const Box* aabb, const double pt[3], uint32_t depth);
 
 static double nearness_mean(const double* coeffs, uint32_t degree, const Box* aabb, uint32_t depth)
