@@ -12,6 +12,8 @@ CG converged to 1e-13 where continuity is on):
   sample_leaves, sample_coeffs   full coefficients of 48 seeded leaves (concatenated)
   query_pts, query_vals     2000 seeded points in (a slightly enlarged) root and the reference's Query values
   n_nodes, n_coeffs, applied_p, applied_h, fits, final_total
+sphere_exp_1e8_mc2017.npz: the same contents for the mc_counter nearness mode (seed 2017): 100 calls of the reference's FApprox per fit
+on Philox4x32-10 points instead of std::rand() ones.
 fits.npz: single reference FitPolynomial calls (coefficients + raw top-shell energy) for seeded cells/degrees.
 """
 import os
@@ -28,18 +30,21 @@ from cases import CASES, root_points, leaf_table, path_code  # noqa: E402
 TREE_CASES = ["c1_readme", "sphere_poly_1e8", "csg_cont", "custom_domain", "csg_small"]
 
 
-def tree_golden(name):
+MC_SEED = 2017          # mc_counter fixture: the reference's 100-sample nearness estimator (through its own FApprox) on Philox points
+
+
+def tree_golden(name, mc_seed=None, out_name=None):
     c = CASES[name]
     cfg = hpref.make_config(threads=8, **c["cfg"])
     prog = hpref.make_program(c["prog"])
-    t = hpref.RefTree.build(cfg, prog, mode=1, threads=8, cg_tol=1e-13)
+    t = hpref.RefTree.build(cfg, prog, mode=1, threads=8, cg_tol=1e-13, mc_seed=mc_seed)
     blk = hpref.parse_block(t.block())
     paths, depth, deg, cs = leaf_table(blk, hpref.NCOEF)
     rng = np.random.default_rng(1234)
     sample = np.sort(rng.choice(len(cs), size=min(48, len(cs)), replace=False))
     pts = root_points(c["cfg"], 2000, seed=99, margin=0.02)
     st = t.stats()
-    np.savez_compressed(os.path.join(HERE, name + ".npz"),
+    np.savez_compressed(os.path.join(HERE, (out_name or name) + ".npz"),
                         leaf_depth=depth.astype(np.uint8), leaf_degree=deg.astype(np.uint8),
                         leaf_code=np.array([path_code(p) for p in paths], np.uint64),
                         leaf_c0=np.array([x[0] for x in cs]), leaf_norm=np.array([np.linalg.norm(x) for x in cs]),
@@ -47,7 +52,7 @@ def tree_golden(name):
                         query_pts=pts, query_vals=t.query(pts),
                         n_nodes=blk["n_nodes"], n_coeffs=blk["n_coeffs"], applied_p=st["applied_p"],
                         applied_h=st["applied_h"], fits=st["fits"], final_total=st["final_total"])
-    print(name, blk["n_nodes"], blk["n_coeffs"], st["applied_p"], st["applied_h"])
+    print(out_name or name, blk["n_nodes"], blk["n_coeffs"], st["applied_p"], st["applied_h"])
 
 
 def fit_golden():
@@ -89,7 +94,11 @@ def mesh_golden():
 
 if __name__ == "__main__":
     assert hpref.available(), "build oracle/_ref first: make -C oracle ref"
+    if len(sys.argv) > 1 and sys.argv[1] == "mc":            # only the mc_counter fixture
+        tree_golden("sphere_exp_1e8", mc_seed=MC_SEED, out_name="sphere_exp_1e8_mc2017")
+        sys.exit(0)
     fit_golden()
     mesh_golden()
     for n in TREE_CASES:
         tree_golden(n)
+    tree_golden("sphere_exp_1e8", mc_seed=MC_SEED, out_name="sphere_exp_1e8_mc2017")

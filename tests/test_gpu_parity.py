@@ -229,6 +229,13 @@ def test_mc_counter_nearness_matches_oracle(hp, oracle, name):
     t = hp.Octree()
     t.Create(cfg, prog, hp.BuildOpts(nearness_mode=hp.NEARNESS_MC_COUNTER, nearness_seed=2017))
     worst, ndiv = compare_with_oracle_tree(hp, t, o, kw)
+    if name == "sphere_exp_1e8":
+        # the same tree as the fixture generated by the reference's own sources (tests/golden/make_golden.py mc)
+        g = golden("sphere_exp_1e8_mc2017")
+        gw, gd = check_tree_against_golden(hp.parse_block(t.ToMemoryBlockBytes()), g, hp.COEFF_COUNT, COEFF_TOL, tree=t)
+        assert gw <= COEFF_TOL
+        if gd == 0:
+            assert np.abs(t.Query(g["query_pts"]) - g["query_vals"]).max() <= QUERY_TOL
     exact = hp.Octree()
     exact.Create(cfg, prog)
     other = hp.Octree()

@@ -63,6 +63,22 @@ def test_tree_matches_reference_golden(oracle, name):
     assert (g["query_vals"] == np.finfo(np.float64).max).any()
 
 
+def test_mc_counter_tree_matches_reference_golden(oracle):
+    """mc_counter nearness (seed 2017): the fixture was built by the reference's sources calling their own FApprox 100 times
+    per fit on Philox points (tests/golden/make_golden.py mc); the restatement reproduces it."""
+    from oracle import hpref
+    cfg, prog = oracle_cfg(hpref, "sphere_exp_1e8")
+    t = oracle.OracleTree.build(cfg, prog, threads=8, mc_seed=2017)
+    g = golden("sphere_exp_1e8_mc2017")
+    worst, ndiv = check_tree_against_golden(hpref.parse_block(t.block()), g, oracle.NCOUNT, 1e-13)
+    assert ndiv == 0
+    st = t.stats()
+    assert st["applied_p"] == float(g["applied_p"]) and st["applied_h"] == float(g["applied_h"])
+    assert np.abs(t.query(g["query_pts"]) - g["query_vals"]).max() <= 1e-13
+    # and it is not the exact-mean tree
+    assert int(g["n_coeffs"]) != int(golden("sphere_poly_1e8")["n_coeffs"])
+
+
 def test_memory_block_round_trip(oracle):
     from oracle import hpref
     cfg, prog = oracle_cfg(hpref, "csg_small")
